@@ -1,0 +1,438 @@
+"""B200Backend -- the drop-in replacement for the reference's CythonBackend (qip/backend.py:68-175).
+
+Use it through the reference's own plug-in hook (qip/pipeline.py:71-76, 95-96, 133):
+
+    from qip_b200 import B200Backend
+    out, classic = run(node, feed={...}, backend_constructor=B200Backend.make_state)
+
+It implements every method of the reference's abstract StateType (qip/backend.py:14-65) with the
+same names, argument meaning, return values and exception types.  All state lives in B200 HBM; all
+arithmetic runs in the hand-written sm_100a kernels of libqipb200.so through the C ABI
+(include/qip_b200.h).  PyTorch is used only to own device buffers, for H2D/D2H copies and for the
+CUDA stream.  There is NO CPU fallback: without the library or a GPU every call raises.
+
+Differences from the reference that are deliberate ("quirks"):
+  * in place, no arena: 33 qubits complex128 is 128 GiB of a 180 GB GPU;
+  * gates are queued lazily and flushed as fused passes before anything observes the state;
+  * 64-bit indices (the reference's kernels are int32, n <= 30); complex64 states are supported;
+  * non-zero input_offset/output_offset windows (the reference's distributed-worker mode) are
+    rejected -- sharding is done by qip_b200.sharded instead.
+"""
+import ctypes
+import math
+import random
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import lib as _lib
+from .ops import BitGate, Gate, Pass, decode_mats, lower, plan_passes, simplify
+
+_HOST_STATE_MAX_QUBITS = 28     # get_state() returns a host ndarray up to here, a lazy handle beyond
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DeviceState(object):
+    """Array-like handle on a device-resident state (returned by get_state() for large n, accepted
+    back as a feed).  Supports len(), .shape, numpy.asarray(), slicing (D2H of the slice only)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.shape = (tensor.shape[0],)
+        self.dtype = np.complex128 if tensor.dtype == _torch().complex128 else np.complex64
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.tensor.cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __getitem__(self, item):
+        return self.tensor[item].cpu().numpy()
+
+
+class B200Backend(object):
+    """StateType implementation on one B200 (see module docstring)."""
+
+    def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6):
+        torch = _torch()
+        self.L = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.QipbError("qip_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.n = int(n)
+        if np.dtype(dtype) == np.complex128:
+            self.code, self.tdtype, self.amp_bytes = _lib.C128, torch.complex128, 16
+        elif np.dtype(dtype) == np.complex64:
+            self.code, self.tdtype, self.amp_bytes = _lib.C64, torch.complex64, 8
+        else:
+            raise ValueError("Buffer dtype mismatch: statetype must be numpy.complex128 or numpy.complex64")
+        self.np_dtype = np.dtype(dtype)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.fuse = fuse
+        self.tile_bits = tile_bits
+        self.min_low_bits = min_low_bits
+        ctx = ctypes.c_void_p()
+        _lib.check(self.L.qipb_create(self.device.index or 0, ctypes.byref(ctx)))
+        self.ctx = ctx
+        self.state = None            # torch tensor, 2^n amplitudes
+        self.queue: List[BitGate] = []
+        self.stats = {"gates": 0, "passes": 0, "fused_passes": 0, "flushes": 0}
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def make_state(n: int, index_groups: Sequence[Sequence[int]], feed_list: Sequence, statetype=np.complex128,
+                   device=None, **kwargs) -> "B200Backend":
+        """Signature of CythonBackend.make_state (qip/backend.py:73-77); called once per run()
+        by qip/pipeline.py:133."""
+        b = B200Backend(n, statetype, device=device, **kwargs)
+        b._init_state(index_groups, feed_list)
+        return b
+
+    def _stream(self):
+        torch = _torch()
+        _lib.check(self.L.qipb_set_stream(self.ctx, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def _ptr(self, t=None):
+        return ctypes.c_void_p((self.state if t is None else t).data_ptr())
+
+    def _init_state(self, index_groups, feed_list):
+        torch = _torch()
+        n = self.n
+        if len(index_groups) != len(feed_list):
+            raise ValueError("index_groups and feed_list must have the same length")
+        groups = [[int(q) for q in g] for g in index_groups]
+        flat = [q for g in groups for q in g]
+        if len(set(flat)) != len(flat):
+            raise ValueError("a qubit appears in more than one feed group")
+        for q in flat:
+            if not (0 <= q < n):
+                raise ValueError("qubit index {} out of range for {} qubits".format(q, n))
+        with torch.cuda.device(self.device):
+            self._stream()
+            # whole-register feed that is already on the device: adopt a copy, no host round trip
+            if len(groups) == 1 and groups[0] == list(range(n)) and isinstance(feed_list[0], (DeviceState, torch.Tensor)):
+                src = feed_list[0].tensor if isinstance(feed_list[0], DeviceState) else feed_list[0]
+                if src.shape[0] != 2 ** n:
+                    raise ValueError("feed length must be 2**len(group)")
+                self.state = src.to(device=self.device, dtype=self.tdtype, copy=True)
+                return
+            self.state = torch.empty(2 ** n, dtype=self.tdtype, device=self.device)
+            if len(groups) == 0:                               # qip/backend.py:90-91
+                _lib.check(self.L.qipb_init_basis(self.ctx, self._ptr(), n, self.code, 0))
+                return
+            feeds = []
+            for g, f in zip(groups, feed_list):
+                if isinstance(f, (int, np.integer)):           # one-hot index, qip/distributed/backend.py:42-45
+                    v = np.zeros(2 ** len(g), dtype=np.complex128)
+                    v[int(f)] = 1.0
+                elif isinstance(f, DeviceState):
+                    v = np.asarray(f, dtype=np.complex128)
+                else:
+                    v = np.asarray(f, dtype=np.complex128).reshape(-1)
+                if v.shape[0] != 2 ** len(g):
+                    raise ValueError("feed length {} does not match 2**{} for group {}".format(v.shape[0], len(g), g))
+                feeds.append(v)
+            cat = np.ascontiguousarray(np.concatenate(feeds))
+            dev_feeds = torch.from_numpy(cat).to(self.device)
+            zero_mask = 0
+            fed = set(flat)
+            for q in range(n):
+                if q not in fed:
+                    zero_mask |= 1 << (n - 1 - q)
+            glen = _lib.int_array([len(g) for g in groups])
+            gbits = _lib.int_array([n - 1 - q for q in flat])
+            _lib.check(self.L.qipb_init_kron(self.ctx, self._ptr(), n, self.code, len(groups), glen, gbits,
+                                             ctypes.c_void_p(dev_feeds.data_ptr()), zero_mask, 0))
+            self._keepalive = dev_feeds
+
+    # ------------------------------------------------------------------ gate path
+    def kronselect_dot(self, mats, input_offset: int = 0, output_offset: int = 0) -> None:
+        """qip/backend.py:112-116.  Validates eagerly, executes lazily (fused at the next flush)."""
+        if input_offset != 0 or output_offset != 0:
+            raise ValueError("B200Backend holds the whole state; offset windows are not supported")
+        for g in decode_mats(mats, self.n):
+            s = simplify(g)
+            if s is not None:
+                self.queue.append(lower(s, self.n))
+                self.stats["gates"] += 1
+
+    def _launch_single(self, g: BitGate):
+        if g.kind == "swap":
+            _lib.check(self.L.qipb_apply_swap(self.ctx, self._ptr(), self.n, self.code, g.bits[0], g.bits[1], g.ctrl_mask))
+        else:
+            _lib.check(self.L.qipb_apply_matrix(self.ctx, self._ptr(), self.n, self.code, g.k, _lib.int_array(g.bits),
+                                                _lib.mat_array(g.mat), g.ctrl_mask, 1 if g.diagonal else 0))
+
+    _SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+    def _launch_fused(self, p: Pass):
+        arr = (_lib.Gate * len(p.gates))()
+        for i, g in enumerate(p.gates):
+            mat, diag = (self._SWAP4, False) if g.kind == "swap" else (g.mat, g.diagonal)
+            arr[i].k = g.k
+            arr[i].diagonal = 1 if diag else 0
+            for j, b in enumerate(g.bits):
+                arr[i].bits[j] = b
+            arr[i].ctrl_mask = g.ctrl_mask
+            flat = np.ascontiguousarray(mat, dtype=np.complex128).reshape(-1)
+            ctypes.memmove(arr[i].mat, flat.ctypes.data, 16 * flat.size)
+        _lib.check(self.L.qipb_apply_fused(self.ctx, self._ptr(), self.n, self.code, len(p.tile_bits),
+                                           _lib.int_array(p.tile_bits), len(p.gates), arr))
+
+    def flush(self) -> None:
+        """Execute every queued gate.  Called before anything reads or measures the state."""
+        if not self.queue:
+            return
+        torch = _torch()
+        passes = plan_passes(self.queue, self.n, self.amp_bytes, tile_bits=self.tile_bits,
+                             min_low_bits=self.min_low_bits, enable=self.fuse)
+        self.queue = []
+        with torch.cuda.device(self.device):
+            self._stream()
+            for p in passes:
+                if p.fused:
+                    self._launch_fused(p)
+                    self.stats["fused_passes"] += 1
+                else:
+                    self._launch_single(p.gates[0])
+                self.stats["passes"] += 1
+        self.stats["flushes"] += 1
+
+    def func_apply(self, reg1_indices, reg2_indices, func: Callable[[int], int],
+                   input_offset: int = 0, output_offset: int = 0) -> None:
+        """qip/backend.py:118-121.  Offsets are accepted and ignored like the reference does
+        (FOp passes n as input_offset, qip/operators.py:289-291)."""
+        torch = _torch()
+        n = self.n
+        reg1 = [int(i) for i in reg1_indices]
+        reg2 = [int(i) for i in reg2_indices]
+        allq = reg1 + reg2
+        if len(set(allq)) != len(allq) or any(not (0 <= q < n) for q in allq):
+            raise ValueError("func_apply registers must be disjoint qubit indices in [0, n)")
+        table = tabulate(func, len(reg1))
+        self.flush()
+        with torch.cuda.device(self.device):
+            self._stream()
+            dev_table = torch.from_numpy(table).to(self.device)
+            _lib.check(self.L.qipb_func_xor(self.ctx, self._ptr(), n, self.code, len(reg1),
+                                            _lib.int_array([n - 1 - q for q in reg1]), len(reg2),
+                                            _lib.int_array([n - 1 - q for q in reg2]),
+                                            ctypes.c_void_p(dev_table.data_ptr()), 0))
+            self._keepalive = dev_table
+
+    # ------------------------------------------------------------------ measurement
+    def _probabilities(self, indices, order: str, filter_mask: int = 0, filter_value: int = 0):
+        """order 'given-le': bit j of the bin = qubit indices[j] (measure_probabilities,
+        qip/ext/kronprod.pyx:258-259).  order 'sorted-be': big-endian over the measured qubits
+        sorted by index (entwine_bit, qip/ext/util.pyx:1-23)."""
+        torch = _torch()
+        n = self.n
+        idx = [int(i) for i in indices]
+        k = len(idx)
+        if len(set(idx)) != k or any(not (0 <= q < n) for q in idx):
+            raise ValueError("measured indices must be distinct qubit indices in [0, n)")
+        if order == "given-le":
+            bits = [n - 1 - q for q in idx]
+            outb = list(range(k))
+        else:
+            srt = sorted(idx)
+            bits = [n - 1 - q for q in srt]
+            outb = [k - 1 - j for j in range(k)]
+        self.flush()
+        with torch.cuda.device(self.device):
+            self._stream()
+            out = torch.empty(2 ** k, dtype=torch.float64, device=self.device)
+            _lib.check(self.L.qipb_probabilities(self.ctx, self._ptr(), n, self.code, k, _lib.int_array(bits),
+                                                 _lib.int_array(outb), filter_mask, filter_value,
+                                                 ctypes.c_void_p(out.data_ptr())))
+            return out.cpu().numpy()
+
+    def _mask_value(self, indices, m):
+        """State-index mask of the measured qubits and the bit pattern of outcome m (big-endian
+        over the sorted qubits)."""
+        n = self.n
+        srt = sorted(int(i) for i in indices)
+        k = len(srt)
+        mask = want = 0
+        for j, q in enumerate(srt):
+            bit = 1 << (n - 1 - q)
+            mask |= bit
+            if (m >> (k - 1 - j)) & 1:
+                want |= bit
+        return mask, want
+
+    def total_prob(self) -> float:
+        """qip/backend.py:123-124 (sum of |a|^2, from zero: SURVEY 8g-5)."""
+        return float(self._probabilities([], "sorted-be")[0])
+
+    def soft_measure(self, indices, measured: Optional[int] = None, input_offset: int = 0):
+        """qip/backend.py:153-156 -> qip/ext/kronprod.pyx:331-383.  Consumes exactly one
+        random.random() like the reference (:362); the state is untouched."""
+        if input_offset != 0:
+            raise ValueError("B200Backend holds the whole state; offset windows are not supported")
+        k = len(indices)
+        r = random.random()
+        if measured is not None:
+            mask, want = self._mask_value(indices, int(measured))
+            p = float(self._probabilities([], "sorted-be", mask, want)[0])
+            return int(measured), p
+        probs = self._probabilities(indices, "sorted-be")
+        return scan_outcome(probs, r)
+
+    def measure(self, indices, measured: Optional[int] = None, measured_prob: Optional[float] = None,
+                input_offset: int = 0, output_offset: int = 0):
+        """qip/backend.py:126-134 -> qip/ext/kronprod.pyx:388-446."""
+        torch = _torch()
+        k = len(indices)
+        _check_measure_args(k, measured, measured_prob)
+        if input_offset != 0 or output_offset != 0:
+            raise ValueError("B200Backend holds the whole state; offset windows are not supported")
+        if measured is None or measured_prob is None:
+            m, p = self.soft_measure(indices, measured=measured)
+        else:
+            m, p = int(measured), float(measured_prob)
+        mask, want = self._mask_value(indices, m)
+        self.flush()
+        with torch.cuda.device(self.device):
+            self._stream()
+            _lib.check(self.L.qipb_collapse(self.ctx, self._ptr(), self.n, self.code, mask, want, math.sqrt(1.0 / p)))
+        return m, p
+
+    def reduce_measure(self, indices, measured: Optional[int] = None, measured_prob: Optional[float] = None,
+                       input_offset: int = 0, output_offset: int = 0):
+        """qip/backend.py:136-151 -> qip/ext/kronprod.pyx:451-490, with the intended 2^(n-k)
+        result: the state shrinks and n decreases by k."""
+        torch = _torch()
+        k = len(indices)
+        _check_measure_args(k, measured, measured_prob)
+        if measured is None or measured_prob is None:
+            m, p = self.soft_measure(indices, measured=measured)
+        else:
+            m, p = int(measured), float(measured_prob)
+        mask, want = self._mask_value(indices, m)
+        self.flush()
+        with torch.cuda.device(self.device):
+            self._stream()
+            dst = torch.empty(2 ** (self.n - k), dtype=self.tdtype, device=self.device)
+            _lib.check(self.L.qipb_reduce(self.ctx, self._ptr(), self._ptr(dst), self.n, self.code, mask, want,
+                                          math.sqrt(1.0 / p)))
+            torch.cuda.current_stream(self.device).synchronize()
+            self.state = dst
+            self.n -= k
+        return m, p
+
+    def measure_probabilities(self, indices, top_k: int = 0):
+        """qip/backend.py:158-163."""
+        if top_k:
+            probs = self._probabilities(indices, "sorted-be")
+            return top_probabilities(probs, top_k)
+        return self._probabilities(indices, "given-le")
+
+    # ------------------------------------------------------------------ state access
+    def get_state(self):
+        """qip/backend.py:106-107.  Host ndarray for n <= 28, DeviceState handle beyond."""
+        torch = _torch()
+        self.flush()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            if self.n <= _HOST_STATE_MAX_QUBITS:
+                return self.state.cpu().numpy()
+            return DeviceState(self.state)
+
+    def get_state_size(self) -> int:
+        return 2 ** self.n
+
+    def get_relative_range(self, start: int, end: int):
+        self.flush()
+        return self.state[start:end].cpu().numpy()
+
+    def overwrite_relative_range(self, start: int, end: int, data):
+        torch = _torch()
+        self.flush()
+        src = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=self.np_dtype)))
+        self.state[start:end].copy_(src)
+
+    def addto_relative_range(self, start: int, end: int, data):
+        torch = _torch()
+        self.flush()
+        with torch.cuda.device(self.device):
+            self._stream()
+            src = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=self.np_dtype))).to(self.device)
+            _lib.check(self.L.qipb_add_range(self.ctx, self._ptr(), self.code, start, end - start,
+                                             ctypes.c_void_p(src.data_ptr())))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def launch_count(self) -> int:
+        return int(self.L.qipb_launch_count(self.ctx))
+
+    def synchronize(self):
+        self.flush()
+        _torch().cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.qipb_destroy(self.ctx)
+            self.ctx = None
+        self.state = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------- host helpers (CPU-testable)
+def _check_measure_args(k, measured, measured_prob):
+    # qip/ext/kronprod.pyx:402-407 / 453-458
+    if measured is not None and not (0 <= measured < 2 ** k):
+        raise ValueError("Measured value must be less than 2**len(indices)")
+    if measured_prob is not None and not (0.0 < measured_prob <= 1.0):
+        raise ValueError("measured_prob must be 0 < p <= 1")
+
+
+def scan_outcome(probs, r01):
+    """The sampling scan of soft_measure (qip/ext/kronprod.pyx:364-381): scale the uniform draw
+    by the total probability, subtract outcome probabilities in ascending order, stop at r <= 0;
+    the last outcome if it never gets there.  numpy.cumsum is a sequential
+    left-to-right sum, i.e. exactly ((r - p0) - p1) - ..."""
+    probs = np.asarray(probs, dtype=np.float64)
+    r = r01 * float(np.sum(probs))
+    run = np.cumsum(np.concatenate(([r], -probs)))[1:]
+    hit = np.flatnonzero(run <= 0.0)
+    m = int(hit[0]) if len(hit) else len(probs) - 1
+    return m, float(probs[m])
+
+
+def top_probabilities(probs_big_endian, top_k):
+    """measure_top_probabilities (qip/ext/kronprod.pyx:266-315): top_k outcomes by probability,
+    descending, ties by ascending outcome."""
+    probs = np.asarray(probs_big_endian)
+    k = min(int(top_k), len(probs))
+    order = np.argsort(-probs, kind="stable")[:k]
+    return [int(i) for i in order], [float(probs[i]) for i in order]
+
+
+def tabulate(func, nbits_in: int) -> np.ndarray:
+    """f(x) for x < 2^nbits_in as int64 (qip/ext/func_apply.pyx:66-69).  Tries one vectorised call
+    on a numpy array first (and cross-checks it on a sample), falls back to the reference's loop."""
+    size = 2 ** nbits_in
+    xs = np.arange(size, dtype=np.int64)
+    try:
+        ys = func(xs)
+        ys = np.asarray(ys)
+        if ys.shape == ():
+            ys = np.full(size, int(ys), dtype=np.int64)
+        if ys.shape == (size,) and ys.dtype.kind in "iub":
+            ys = ys.astype(np.int64)
+            probe = np.unique(np.concatenate(([0, size - 1], np.random.default_rng(0).integers(0, size, 14))))
+            if all(int(func(int(x))) == int(ys[x]) for x in probe):
+                return np.ascontiguousarray(ys)
+    except Exception:
+        pass
+    return np.array([int(func(int(x))) for x in range(size)], dtype=np.int64)

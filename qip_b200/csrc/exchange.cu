@@ -1,0 +1,130 @@
+// qip_b200/csrc/exchange.cu -- multi-GPU state exchange over NVLink peer memory for sm_100a.
+//
+// Replaces the reference's worker<->worker socket exchange (qip/distributed/worker/worker.py:
+// 302-357: protobuf chunks of 2048 amplitudes over TCP) and the per-gate reduce-to-diagonal +
+// re-broadcast of qip/distributed/manager.py:224-236.  The state is sharded by its top qubits,
+// one process per GPU; each process maps its peers' shards with CUDA IPC and the kernels below
+// load/store the partner's HBM directly through NVLink 5 / NVSwitch.
+//   peer_swap_kernel  : in-place exchange of an amplitude range with the partner (global<->local
+//                       qubit swap); one kernel, no staging buffer, traffic in both directions.
+//   peer_gate1_kernel : FUSED compute + exchange -- a 1-qubit gate on a global (rank) bit is
+//                       applied while the halves cross the link: (lo,hi) <- M (lo,hi).
+// Each rank of a pair processes a disjoint half of the range, so both directions of the link and
+// both GPUs' SMs are used.  Roofline: NVLink-bound, sizeof(amp)*count/2 bytes out and in per rank.
+#include "common.cuh"
+#include "../../include/qip_b200.h"
+
+namespace qipb {
+
+template <typename A, int U>
+__global__ void __launch_bounds__(256) peer_swap_kernel(A *__restrict__ local, A *__restrict__ peer, u64 count) {
+    A a[U], b[U];
+    u64 idx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        idx[u] = ((u64)blockIdx.x * U + u) * blockDim.x + threadIdx.x;
+        if (idx[u] < count) { a[u] = local[idx[u]]; b[u] = peer[idx[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (idx[u] < count) { local[idx[u]] = b[u]; peer[idx[u]] = a[u]; }
+}
+
+struct PeerGateArgs {
+    u64 count;
+    u64 ctrl_mask;        // local-index bits that must be 1
+    int local_is_hi;
+    double2 m[4];
+};
+
+template <typename A, int U>
+__global__ void __launch_bounds__(256) peer_gate1_kernel(A *__restrict__ local, A *__restrict__ peer, u64 off,
+                                                         const __grid_constant__ PeerGateArgs g) {
+    A l[U], p[U];
+    u64 idx[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const u64 w = ((u64)blockIdx.x * U + u) * blockDim.x + threadIdx.x;
+        idx[u] = off + w;
+        live[u] = w < g.count && ((idx[u] & g.ctrl_mask) == g.ctrl_mask);
+        if (live[u]) { l[u] = local[idx[u]]; p[u] = peer[idx[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (live[u]) {
+            const A lo = g.local_is_hi ? p[u] : l[u], hi = g.local_is_hi ? l[u] : p[u];
+            A r0 = cmul<A>(g.m[0], lo);
+            cfma<A>(r0, g.m[1], hi);
+            A r1 = cmul<A>(g.m[2], lo);
+            cfma<A>(r1, g.m[3], hi);
+            local[idx[u]] = g.local_is_hi ? r1 : r0;
+            peer[idx[u]] = g.local_is_hi ? r0 : r1;
+        }
+}
+
+}  // namespace qipb
+
+using namespace qipb;
+
+extern "C" int qipb_ipc_export(qipb_ctx *ctx, void *dev_ptr, unsigned char handle_out[64]) {
+    QIPB_REQUIRE(ctx && dev_ptr && handle_out, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    QIPB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return QIPB_OK;
+}
+
+extern "C" int qipb_ipc_open(qipb_ctx *ctx, const unsigned char handle[64], void **peer_ptr_out) {
+    QIPB_REQUIRE(ctx && handle && peer_ptr_out, "null argument");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    QIPB_CUDA(cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return QIPB_OK;
+}
+
+extern "C" int qipb_ipc_close(qipb_ctx *ctx, void *peer_ptr) {
+    QIPB_REQUIRE(ctx && peer_ptr, "null argument");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    QIPB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return QIPB_OK;
+}
+
+extern "C" int qipb_peer_swap(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t local_off, uint64_t peer_off,
+                              uint64_t count) {
+    QIPB_REQUIRE(ctx && local && peer, "null argument");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    if (count == 0) return QIPB_OK;
+    const u64 blocks = (count + 256ull * 4 - 1) / (256ull * 4);
+    QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
+    if (dtype == QIPB_C128) peer_swap_kernel<double2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)local + local_off, (double2 *)peer + peer_off, count);
+    else if (dtype == QIPB_C64) peer_swap_kernel<float2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)local + local_off, (float2 *)peer + peer_off, count);
+    else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
+    ctx->launches++;
+    QIPB_CUDA(cudaGetLastError());
+    return QIPB_OK;
+}
+
+extern "C" int qipb_peer_gate1(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t off, uint64_t count,
+                               const double *mat, int local_is_hi, uint64_t ctrl_mask) {
+    QIPB_REQUIRE(ctx && local && peer && mat, "null argument");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    if (count == 0) return QIPB_OK;
+    PeerGateArgs g;
+    memset(&g, 0, sizeof(g));
+    g.count = count;
+    g.ctrl_mask = ctrl_mask;
+    g.local_is_hi = local_is_hi;
+    for (int e = 0; e < 4; ++e) g.m[e] = make_double2(mat[2 * e], mat[2 * e + 1]);
+    const u64 blocks = (count + 256ull * 4 - 1) / (256ull * 4);
+    QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
+    if (dtype == QIPB_C128) peer_gate1_kernel<double2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)local, (double2 *)peer, off, g);
+    else if (dtype == QIPB_C64) peer_gate1_kernel<float2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)local, (float2 *)peer, off, g);
+    else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
+    ctx->launches++;
+    QIPB_CUDA(cudaGetLastError());
+    return QIPB_OK;
+}

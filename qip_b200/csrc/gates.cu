@@ -1,0 +1,300 @@
+// qip_b200/csrc/gates.cu -- in-place k-qubit gate application for sm_100a.
+//
+// Replaces the reference's cdot_loop (qip/ext/kronprod.pyx:157-197), which computes every output
+// row as a gather over 2^K columns into a second buffer.  Here one thread owns whole 2^k-amplitude
+// groups: it loads the group (one 128-bit transaction per complex128 amplitude), multiplies by the
+// 2^k x 2^k matrix held in the kernel's constant bank, and stores back IN PLACE, so a pass moves
+// exactly 2 * sizeof(amp) * (#touched amplitudes) bytes of HBM and needs no arena.
+//
+// Roofline: HBM-bound (14-30 flop per 32 B moved for 1-2 qubit gates); see DESIGN.md.
+//
+// Work decomposition: a group is named by a work index w in [0, 2^(nbits - nins)); zeros are
+// inserted at the `nins` fixed positions (targets + controls, ascending) to get the base index,
+// control bits are ORed in, and the 2^k members sit at base + off[j].  Consecutive threads get
+// consecutive w, so as long as the lowest index bits are not fixed, a warp's j-th load covers
+// 32 consecutive amplitudes = 512 contiguous bytes.  Each thread handles U groups and issues all
+// of its loads before the first FMA to keep >= 8 independent 128-bit loads in flight.
+#include "common.cuh"
+#include "../../include/qip_b200.h"
+
+namespace qipb {
+
+#define QIPB_MAX_INS 48
+
+template <int K>
+struct GateArgs {
+    u64 nwork;                    // number of groups
+    u64 fixed_or;                 // control bits (all must be 1)
+    int nins;
+    unsigned char ins[QIPB_MAX_INS];   // ascending positions where a zero bit is inserted
+    u64 off[1 << K];              // member offsets, matrix-index order
+    double2 m[(1 << K) * (1 << K)];
+};
+
+__device__ __forceinline__ u64 expand_index(u64 w, const unsigned char *ins, int nins, u64 fixed_or) {
+    for (int j = 0; j < nins; ++j) w = insert_zero(w, ins[j]);
+    return w | fixed_or;
+}
+
+// 256-bit (two complex128) accesses for the case where the two members of a group are adjacent
+// in memory (target bit 0): one LDG.256 / STG.256 per group instead of two half-used sectors.
+__device__ __forceinline__ void ld256(const double2 *p, double2 &a, double2 &b) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void st256(double2 *p, const double2 a, const double2 b) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
+template <typename A, int K, int U, bool DIAG>
+__global__ void __launch_bounds__(256) gate_kernel(A *__restrict__ state, const __grid_constant__ GateArgs<K> g) {
+    constexpr int D = 1 << K;
+    A a[U][D];
+    u64 base[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const u64 w = ((u64)blockIdx.x * U + u) * blockDim.x + threadIdx.x;
+        live[u] = w < g.nwork;
+        base[u] = expand_index(w, g.ins, g.nins, g.fixed_or);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (live[u]) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) a[u][j] = state[base[u] + g.off[j]];
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (live[u]) {
+            if (DIAG) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) state[base[u] + g.off[i]] = cmul<A>(g.m[i * D + i], a[u][i]);
+            } else {
+                A r[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    r[i] = cmul<A>(g.m[i * D], a[u][0]);
+#pragma unroll
+                    for (int j = 1; j < D; ++j) cfma<A>(r[i], g.m[i * D + j], a[u][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) state[base[u] + g.off[i]] = r[i];
+            }
+        }
+}
+
+// K = 1, complex128, target bit 0: the pair is one aligned 32-byte object.
+template <int U>
+__global__ void __launch_bounds__(256) gate1_bit0_kernel(double2 *__restrict__ state, const __grid_constant__ GateArgs<1> g) {
+    double2 a0[U], a1[U];
+    u64 base[U];
+    bool live[U];
+    const bool rev = g.off[0] != 0;     // matrix index 0 sits at the odd address
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const u64 w = ((u64)blockIdx.x * U + u) * blockDim.x + threadIdx.x;
+        live[u] = w < g.nwork;
+        base[u] = expand_index(w, g.ins, g.nins, g.fixed_or);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (live[u]) ld256(state + base[u], a0[u], a1[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (live[u]) {
+            const double2 x0 = rev ? a1[u] : a0[u], x1 = rev ? a0[u] : a1[u];
+            double2 r0 = cmul<double2>(g.m[0], x0);
+            cfma<double2>(r0, g.m[1], x1);
+            double2 r1 = cmul<double2>(g.m[2], x0);
+            cfma<double2>(r1, g.m[3], x1);
+            st256(state + base[u], rev ? r1 : r0, rev ? r0 : r1);
+        }
+}
+
+// Dense gate on many target bits (QIPB_MAX_DENSE_K < k <= QIPB_MAX_BIG_K): one CTA per group
+// batch, group staged in shared memory, matrix streamed from global memory (L2 resident).
+struct BigArgs {
+    u64 nwork;
+    u64 fixed_or;
+    int nins;
+    int k;
+    unsigned char ins[QIPB_MAX_INS];
+    unsigned char tbit[QIPB_MAX_BIG_K];   // bit position of matrix-index bit j (j = 0 least significant)
+};
+template <typename A>
+__global__ void __launch_bounds__(256) big_gate_kernel(A *__restrict__ state, const double2 *__restrict__ mat,
+                                                        const __grid_constant__ BigArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    A *grp = reinterpret_cast<A *>(smem_raw);
+    const int D = 1 << g.k;
+    for (u64 w = blockIdx.x; w < g.nwork; w += gridDim.x) {
+        const u64 base = expand_index(w, g.ins, g.nins, g.fixed_or);
+        for (int j = threadIdx.x; j < D; j += blockDim.x) {
+            u64 off = 0;
+            for (int b = 0; b < g.k; ++b) off |= (u64)((j >> b) & 1) << g.tbit[b];
+            grp[j] = state[base + off];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < D; i += blockDim.x) {
+            A r = make_amp<A>(0, 0);
+            const double2 *row = mat + (size_t)i * D;
+            for (int j = 0; j < D; ++j) cfma<A>(r, row[j], grp[j]);
+            u64 off = 0;
+            for (int b = 0; b < g.k; ++b) off |= (u64)((i >> b) & 1) << g.tbit[b];
+            state[base + off] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+template <int K>
+static int fill_args(GateArgs<K> &g, int nbits, const int *bits, const double *mat, u64 ctrl_mask) {
+    u64 tmask = 0;
+    for (int j = 0; j < K; ++j) {
+        QIPB_REQUIRE(bits[j] >= 0 && bits[j] < nbits, "target bit %d out of range [0,%d)", bits[j], nbits);
+        QIPB_REQUIRE(!((tmask >> bits[j]) & 1ull), "repeated target bit %d", bits[j]);
+        tmask |= 1ull << bits[j];
+    }
+    QIPB_REQUIRE((ctrl_mask & tmask) == 0, "control mask overlaps target bits");
+    QIPB_REQUIRE(nbits == 64 || (ctrl_mask >> nbits) == 0, "control mask outside the %d local bits", nbits);
+    const u64 fixed = tmask | ctrl_mask;
+    g.nins = 0;
+    for (int b = 0; b < nbits; ++b)
+        if ((fixed >> b) & 1ull) {
+            QIPB_REQUIRE(g.nins < QIPB_MAX_INS, "too many fixed bits");
+            g.ins[g.nins++] = (unsigned char)b;
+        }
+    g.fixed_or = ctrl_mask;
+    g.nwork = 1ull << (nbits - g.nins);
+    for (int j = 0; j < (1 << K); ++j) {
+        u64 off = 0;
+        for (int t = 0; t < K; ++t)
+            if ((j >> (K - 1 - t)) & 1) off |= 1ull << bits[t];   // bits[0] = MSB of the matrix index
+        g.off[j] = off;
+    }
+    for (int e = 0; e < (1 << K) * (1 << K); ++e) g.m[e] = make_double2(mat[2 * e], mat[2 * e + 1]);
+    return QIPB_OK;
+}
+
+template <typename A, int K, int U, bool DIAG>
+static int launch_gate(qipb_ctx *ctx, A *state, const GateArgs<K> &g) {
+    const u64 per_block = 256ull * U;
+    const u64 blocks = (g.nwork + per_block - 1) / per_block;
+    QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
+    gate_kernel<A, K, U, DIAG><<<(unsigned)blocks, 256, 0, ctx->stream>>>(state, g);
+    ctx->launches++;
+    QIPB_CUDA(cudaGetLastError());
+    return QIPB_OK;
+}
+
+template <typename A, int K>
+static int apply_k(qipb_ctx *ctx, A *state, int nbits, const int *bits, const double *mat, u64 ctrl_mask, int diagonal) {
+    GateArgs<K> g;
+    memset(&g, 0, sizeof(g));
+    int rc = fill_args<K>(g, nbits, bits, mat, ctrl_mask);
+    if (rc) return rc;
+    // groups per thread chosen so that every thread has 8 amplitudes (128 B of c128) in flight
+    constexpr int U = (K == 0) ? 8 : (K == 1) ? 4 : (K == 2) ? 2 : 1;
+    if (diagonal) return launch_gate<A, K, U, true>(ctx, state, g);
+    return launch_gate<A, K, U, false>(ctx, state, g);
+}
+
+template <typename A>
+static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits, const double *mat, u64 ctrl_mask) {
+    BigArgs g;
+    memset(&g, 0, sizeof(g));
+    u64 tmask = 0;
+    for (int j = 0; j < k; ++j) {
+        QIPB_REQUIRE(bits[j] >= 0 && bits[j] < nbits, "target bit out of range");
+        QIPB_REQUIRE(!((tmask >> bits[j]) & 1ull), "repeated target bit");
+        tmask |= 1ull << bits[j];
+        g.tbit[k - 1 - j] = (unsigned char)bits[j];
+    }
+    QIPB_REQUIRE((ctrl_mask & tmask) == 0, "control mask overlaps target bits");
+    const u64 fixed = tmask | ctrl_mask;
+    for (int b = 0; b < nbits; ++b)
+        if ((fixed >> b) & 1ull) g.ins[g.nins++] = (unsigned char)b;
+    g.fixed_or = ctrl_mask;
+    g.k = k;
+    g.nwork = 1ull << (nbits - g.nins);
+    const size_t D = (size_t)1 << k;
+    double2 *dmat = nullptr;
+    QIPB_CUDA(cudaMallocAsync(&dmat, D * D * sizeof(double2), ctx->stream));
+    QIPB_CUDA(cudaMemcpyAsync(dmat, mat, D * D * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    u64 blocks = g.nwork < (u64)ctx->sm_count * 8 ? g.nwork : (u64)ctx->sm_count * 8;
+    big_gate_kernel<A><<<(unsigned)blocks, 256, D * sizeof(A), ctx->stream>>>(state, dmat, g);
+    ctx->launches++;
+    QIPB_CUDA(cudaGetLastError());
+    QIPB_CUDA(cudaFreeAsync(dmat, ctx->stream));
+    return QIPB_OK;
+}
+
+template <typename A>
+static int apply_matrix_t(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits, const double *mat,
+                          u64 ctrl_mask, int diagonal) {
+    switch (k) {
+        case 0: return apply_k<A, 0>(ctx, state, nbits, bits, mat, ctrl_mask, 1);
+        case 1: return apply_k<A, 1>(ctx, state, nbits, bits, mat, ctrl_mask, diagonal);
+        case 2: return apply_k<A, 2>(ctx, state, nbits, bits, mat, ctrl_mask, diagonal);
+        case 3: return apply_k<A, 3>(ctx, state, nbits, bits, mat, ctrl_mask, diagonal);
+        case 4: return apply_k<A, 4>(ctx, state, nbits, bits, mat, ctrl_mask, diagonal);
+        default: return apply_big<A>(ctx, state, nbits, k, bits, mat, ctrl_mask);
+    }
+}
+
+}  // namespace qipb
+
+using namespace qipb;
+
+extern "C" int qipb_apply_matrix(qipb_ctx *ctx, void *state, int nbits, int dtype, int k, const int *bits,
+                                 const double *mat, uint64_t ctrl_mask, int diagonal) {
+    QIPB_REQUIRE(ctx && state && mat, "null argument");
+    QIPB_REQUIRE(nbits >= 0 && nbits <= 40, "nbits %d unsupported", nbits);
+    QIPB_REQUIRE(k >= 0 && k <= QIPB_MAX_BIG_K && k <= nbits, "k=%d unsupported (0..%d, <= nbits)", k, QIPB_MAX_BIG_K);
+    QIPB_REQUIRE(k == 0 || bits, "null bits");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    // complex128, k == 1, target bit 0, dense: 256-bit path
+    if (dtype == QIPB_C128 && k == 1 && !diagonal && bits[0] == 0 && nbits >= 1) {
+        GateArgs<1> g;
+        memset(&g, 0, sizeof(g));
+        int rc = fill_args<1>(g, nbits, bits, mat, (u64)ctrl_mask);
+        if (rc) return rc;
+        const u64 per_block = 256ull * 4;
+        const u64 blocks = (g.nwork + per_block - 1) / per_block;
+        gate1_bit0_kernel<4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)state, g);
+        ctx->launches++;
+        QIPB_CUDA(cudaGetLastError());
+        return QIPB_OK;
+    }
+    if (dtype == QIPB_C128) return apply_matrix_t<double2>(ctx, (double2 *)state, nbits, k, bits, mat, ctrl_mask, diagonal);
+    if (dtype == QIPB_C64) return apply_matrix_t<float2>(ctx, (float2 *)state, nbits, k, bits, mat, ctrl_mask, diagonal);
+    QIPB_REQUIRE(false, "unknown dtype %d", dtype);
+}
+
+// Swap of two index bits = exchange of the members 01 <-> 10 of every group; expressed as a
+// one-"qubit" X gate whose two members sit at base + 2^a and base + 2^b, so only the amplitudes
+// that actually move are touched (half of the state).
+extern "C" int qipb_apply_swap(qipb_ctx *ctx, void *state, int nbits, int dtype, int bit_a, int bit_b,
+                               uint64_t ctrl_mask) {
+    QIPB_REQUIRE(ctx && state, "null argument");
+    QIPB_REQUIRE(bit_a >= 0 && bit_a < nbits && bit_b >= 0 && bit_b < nbits && bit_a != bit_b, "bad swap bits %d,%d", bit_a, bit_b);
+    QIPB_REQUIRE(!(ctrl_mask & ((1ull << bit_a) | (1ull << bit_b))), "control mask overlaps swap bits");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    GateArgs<1> g;
+    memset(&g, 0, sizeof(g));
+    const u64 fixed = (1ull << bit_a) | (1ull << bit_b) | ctrl_mask;
+    for (int b = 0; b < nbits; ++b)
+        if ((fixed >> b) & 1ull) g.ins[g.nins++] = (unsigned char)b;
+    g.fixed_or = ctrl_mask;
+    g.nwork = 1ull << (nbits - g.nins);
+    g.off[0] = 1ull << bit_a;
+    g.off[1] = 1ull << bit_b;
+    g.m[0] = make_double2(0, 0); g.m[1] = make_double2(1, 0);
+    g.m[2] = make_double2(1, 0); g.m[3] = make_double2(0, 0);
+    if (dtype == QIPB_C128) return launch_gate<double2, 1, 4, false>(ctx, (double2 *)state, g);
+    if (dtype == QIPB_C64) return launch_gate<float2, 1, 4, false>(ctx, (float2 *)state, g);
+    QIPB_REQUIRE(false, "unknown dtype %d", dtype);
+}

@@ -1,0 +1,255 @@
+"""Host-side decoding of the boundary's `mats` vocabulary into primitive gates, and the fusion planner.
+
+Pure python / numpy -- no device code -- so it is covered by the CPU test tier.
+
+decode_mats     : `{int | tuple : ndarray | list | CMat | SwapMat}` -> list[Gate], with the same
+                  validation (exception types, order, messages) as qip/util.py:29-58 and
+                  qip/ext/kronprod.pyx:114-116.
+simplify        : exact structural rewrites that cut HBM traffic: identity removal, promotion of
+                  "identity unless this qubit is 1" targets to control bits (what CMat means,
+                  qip/ext/kronprod.pyx:215-225, discovered for plain ndarrays too -- e.g. the
+                  R/Rm phase gate diag(1, e^{i phi}) of qip/operators.py:108-127 becomes a scalar
+                  phase on a controlled sub-space), diagonal detection.
+plan_passes     : greedy grouping of consecutive gates into fused tile passes (qip_b200/csrc/fused.cu)
+                  under a bytes-moved cost model.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+@dataclass
+class Gate:
+    """One primitive: `mat` (2^k x 2^k) on `targets`, enabled where all `controls` are 1.
+
+    Qubit numbers are the reference's global qubit indices (0 = most significant bit of the
+    state index, qip/ext/kronprod.pyx:168,187).  targets[0] is the most significant bit of the
+    matrix index (kronprod.pyx:184-189).  kind == "swap": exchange of two qubits (SwapMat(1))."""
+    kind: str                       # "matrix" | "swap"
+    targets: Tuple[int, ...]
+    controls: Tuple[int, ...] = ()
+    mat: Optional[np.ndarray] = None
+    diagonal: bool = False
+
+    @property
+    def k(self):
+        return len(self.targets)
+
+    def qubits(self):
+        return tuple(self.targets) + tuple(self.controls)
+
+
+# --------------------------------------------------------------------------------- decoding
+def _is_ctrl(m):
+    return getattr(m, "_kron_struct", None) == 2
+
+
+def _is_swap(m):
+    return getattr(m, "_kron_struct", None) == 3
+
+
+def decode_mats(mats, n: int) -> List[Gate]:
+    """Validate and decode one kronselect_dot call.  Entries are returned in dict order; they act
+    on disjoint targets (shared qubits may only be controls) so applying them one after another
+    equals the reference's single product-matrix op."""
+    norm = []
+    for key in mats:                                           # qip/util.py:35-58
+        if type(key) != tuple and type(key) != int:
+            raise Exception("Type of indices must be tuple: {}".format(key))
+        m = mats[key]
+        if type(m) == list:
+            m = np.array(m)
+        tkey = key if type(key) == tuple else (key,)
+        if not hasattr(m, "shape"):
+            raise ValueError("Cannot pass matrices which are not numpy, SwapMat, or CMat")
+        if 2 ** len(tkey) != m.shape[0] or 2 ** len(tkey) != m.shape[1]:
+            raise Exception("Shape of square submatrix must equal 2**(number of indices): "
+                            "{}: {}".format(key, m))
+        norm.append((tuple(int(i) for i in tkey), m))
+
+    gates: List[Gate] = []
+    target_owner = {}
+    control_users = set()
+    for key, m in norm:
+        for q in key:
+            if not (0 <= q < n):
+                raise ValueError("qubit index {} out of range for {} qubits".format(q, n))
+        if len(set(key)) != len(key):
+            raise ValueError("repeated qubit index in {}".format(key))
+        controls = []
+        inner, rest = m, list(key)
+        while _is_ctrl(inner):                                 # kronprod.pyx:215-225
+            controls.append(rest.pop(0))
+            inner = inner.m
+            if type(inner) == list:
+                inner = np.array(inner)
+        entry_gates = []
+        if _is_swap(inner):                                    # kronprod.pyx:227-231
+            w = int(inner.n)
+            if len(rest) != 2 * w:
+                raise Exception("Shape of square submatrix must equal 2**(number of indices): "
+                                "{}: {}".format(key, m))
+            for a, b in zip(rest[:w], rest[w:]):
+                entry_gates.append(Gate("swap", (a, b), tuple(controls)))
+        elif isinstance(inner, np.ndarray):
+            if inner.ndim != 2 or inner.shape[0] != 2 ** len(rest) or inner.shape[1] != 2 ** len(rest):
+                raise Exception("Shape of square submatrix must equal 2**(number of indices): "
+                                "{}: {}".format(key, m))
+            mat = np.ascontiguousarray(inner, dtype=np.complex128)   # kronprod.pyx:99
+            entry_gates.append(Gate("matrix", tuple(rest), tuple(controls), mat))
+        else:                                                  # kronprod.pyx:114-116
+            raise ValueError("Cannot pass matrices which are not numpy, SwapMat, or CMat")
+        for q in rest:
+            if q in target_owner or q in control_users:
+                raise ValueError("qubit {} is acted on by more than one entry of one op; entries may "
+                                 "share control qubits only".format(q))
+            target_owner[q] = key
+        for q in controls:
+            if q in target_owner:
+                raise ValueError("qubit {} is a control of one entry and a target of another".format(q))
+        control_users.update(controls)
+        gates.extend(entry_gates)
+    return gates
+
+
+# --------------------------------------------------------------------------------- simplification
+def _bit_split(mat, k, j):
+    """Blocks of `mat` w.r.t. matrix-index bit for target j (0 = MSB): (M00, M01, M10, M11)."""
+    d = 1 << k
+    pos = k - 1 - j
+    idx0 = [i for i in range(d) if not (i >> pos) & 1]
+    idx1 = [i for i in range(d) if (i >> pos) & 1]
+    return (mat[np.ix_(idx0, idx0)], mat[np.ix_(idx0, idx1)], mat[np.ix_(idx1, idx0)], mat[np.ix_(idx1, idx1)])
+
+
+def simplify(g: Gate) -> Optional[Gate]:
+    """Exact rewrites (only comparisons with exactly 0.0 / 1.0).  Returns None for the identity."""
+    if g.kind != "matrix":
+        return g
+    mat, targets, controls = g.mat, list(g.targets), list(g.controls)
+    changed = True
+    while changed and targets:
+        changed = False
+        k = len(targets)
+        for j in range(k):
+            m00, m01, m10, m11 = _bit_split(mat, k, j)
+            if not m01.any() and not m10.any() and np.array_equal(m00, np.eye(m00.shape[0])):
+                controls.append(targets.pop(j))
+                mat = np.ascontiguousarray(m11)
+                changed = True
+                break
+    d = mat.shape[0]
+    if np.array_equal(mat, np.eye(d)):
+        return None
+    diagonal = not (mat - np.diag(np.diag(mat))).any()
+    return Gate("matrix", tuple(targets), tuple(controls), np.ascontiguousarray(mat, dtype=np.complex128), diagonal)
+
+
+# --------------------------------------------------------------------------------- bit-level form
+@dataclass
+class BitGate:
+    """A Gate lowered to local index bits.  ctrl_mask: bits that must be 1."""
+    kind: str
+    bits: Tuple[int, ...]           # bits[0] = most significant matrix-index bit
+    ctrl_mask: int = 0
+    mat: Optional[np.ndarray] = None
+    diagonal: bool = False
+
+    @property
+    def k(self):
+        return len(self.bits)
+
+    def nctrl(self):
+        return bin(self.ctrl_mask).count("1")
+
+
+def lower(g: Gate, n: int) -> BitGate:
+    bits = tuple(n - 1 - q for q in g.targets)
+    cm = 0
+    for q in g.controls:
+        cm |= 1 << (n - 1 - q)
+    return BitGate(g.kind, bits, cm, g.mat, g.diagonal)
+
+
+# --------------------------------------------------------------------------------- fusion planner
+@dataclass
+class Pass:
+    """Either one stand-alone kernel (fused == False, exactly one gate) or a fused tile pass."""
+    fused: bool
+    gates: List[BitGate]
+    tile_bits: Tuple[int, ...] = ()
+
+
+def _fusable(g: BitGate) -> bool:
+    if g.kind == "swap":
+        return True                 # lowered to a dense 4x4 permutation inside a tile
+    return g.k <= 2
+
+
+def _needs(g: BitGate):
+    """Bits that must be tile bits for g to run inside a fused pass."""
+    if g.kind == "swap":
+        return set(g.bits)
+    if g.diagonal or g.k == 0:
+        return set()
+    return set(g.bits)
+
+
+def gate_bytes(g: BitGate, nbits: int, amp_bytes: int) -> float:
+    """HBM bytes of a stand-alone launch: read + write of every touched amplitude."""
+    touched = 2.0 ** (nbits - g.nctrl())
+    if g.kind == "swap":
+        touched /= 2.0
+    return 2.0 * amp_bytes * touched
+
+
+def choose_tile(required, nbits: int, tile_bits: int):
+    tb = min(tile_bits, nbits)
+    tile = set(required)
+    b = 0
+    while len(tile) < tb and b < nbits:
+        tile.add(b)
+        b += 1
+    return tuple(sorted(tile))
+
+
+def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_bits: int = 12,
+                min_low_bits: int = 6, max_gates: int = 96, enable: bool = True) -> List[Pass]:
+    """Greedy, order-preserving fusion.  A group grows while the union of the bits its non-diagonal
+    gates need, together with the `min_low_bits` lowest bits, still fits in a tile; a group is run
+    fused only when that moves fewer bytes than launching its gates one by one."""
+    passes: List[Pass] = []
+    tb = min(tile_bits, nbits)
+    low = set(range(min(min_low_bits, tb)))
+    cur: List[BitGate] = []
+    need = set()
+
+    def flush():
+        nonlocal cur, need
+        if not cur:
+            return
+        solo = sum(gate_bytes(g, nbits, amp_bytes) for g in cur)
+        fused_cost = 2.0 * amp_bytes * 2.0 ** nbits
+        if len(cur) >= 2 and enable and fused_cost < solo:
+            passes.append(Pass(True, cur, choose_tile(need, nbits, tb)))
+        else:
+            passes.extend(Pass(False, [g]) for g in cur)
+        cur, need = [], set()
+
+    for g in gates:
+        if not enable or not _fusable(g):
+            flush()
+            passes.append(Pass(False, [g]))
+            continue
+        nn = need | _needs(g)
+        if len(nn | low) > tb or len(cur) >= max_gates:
+            flush()
+            nn = _needs(g)
+            if len(nn | low) > tb:        # cannot happen for k <= 2 and tb >= min_low_bits + 2
+                passes.append(Pass(False, [g]))
+                continue
+        cur.append(g)
+        need = nn
+    flush()
+    return passes
