@@ -82,6 +82,7 @@ class B200Backend(object):
         self.state = None            # torch tensor, 2^n amplitudes
         self.queue: List[BitGate] = []
         self.stats = {"gates": 0, "passes": 0, "fused_passes": 0, "flushes": 0}
+        self.profile = None          # list of (kernel label, algorithmic bytes, start event, end event) when enabled
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -195,11 +196,18 @@ class B200Backend(object):
         with torch.cuda.device(self.device):
             self._stream()
             for p in passes:
+                if self.profile is not None:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 if p.fused:
                     self._launch_fused(p)
                     self.stats["fused_passes"] += 1
                 else:
                     self._launch_single(p.gates[0])
+                if self.profile is not None:
+                    e1.record()
+                    self.profile.append(kernel_label(p, self.n, self.amp_bytes) + (e0, e1))
                 self.stats["passes"] += 1
         self.stats["flushes"] += 1
 
@@ -388,6 +396,21 @@ class B200Backend(object):
 
 
 # ---------------------------------------------------------------------- host helpers (CPU-testable)
+def kernel_label(p: Pass, nbits: int, amp_bytes: int):
+    """(kernel name, algorithmic HBM bytes of the launch) for bench.py's roofline accounting."""
+    from .ops import gate_bytes
+    if p.fused:
+        return ("fused_kernel", 2.0 * amp_bytes * 2.0 ** nbits)
+    g = p.gates[0]
+    if g.kind == "swap":
+        name = "gate_kernel<K=1,swap>"
+    elif g.k <= _lib.MAX_DENSE_K:
+        name = "gate_kernel<K=%d%s%s>" % (g.k, ",diag" if (g.diagonal or g.k == 0) else "", ",ctrl" if g.ctrl_mask else "")
+    else:
+        name = "big_gate_kernel"
+    return (name, gate_bytes(g, nbits, amp_bytes))
+
+
 def _check_measure_args(k, measured, measured_prob):
     # qip/ext/kronprod.pyx:402-407 / 453-458
     if measured is not None and not (0 <= measured < 2 ** k):

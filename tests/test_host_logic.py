@@ -1,0 +1,221 @@
+"""CPU tier: host-side logic of the product (op decoding, exact simplification, lowering, fusion
+planner, sampling scan, func tabulation, circuit generators) -- no device code involved.
+The planner is executed by a tests-only numpy simulator (tests/bitsim.py) and compared with the
+golden streams recorded from the reference."""
+import numpy as np
+import pytest
+
+import bitsim
+import replay
+from oracle import oracle as orc
+from qip_b200 import ops
+from qip_b200.backend import scan_outcome, tabulate, top_probabilities
+from qip_b200.circuits import H2, X2, layered_stream, qfft_stream, rm_mat
+from qip_b200.mats import CMat, SwapMat
+
+META, STREAMS, ARRAYS = replay.load_streams()
+
+
+class PlannedHostBackend(orc.OracleBackend):
+    """Oracle state container whose kronselect_dot goes through the PRODUCT's host pipeline
+    (decode -> simplify -> lower -> plan_passes) and a numpy executor of the resulting plan."""
+    fuse = True
+
+    @staticmethod
+    def make_state(n, index_groups, feed_list, statetype=np.complex128, **_):
+        ob = orc.OracleBackend.make_state(n, index_groups, feed_list)
+        b = PlannedHostBackend(n, ob.state)
+        b.queue = []
+        return b
+
+    def kronselect_dot(self, mats, input_offset=0, output_offset=0):
+        for g in ops.decode_mats(mats, self.n):
+            s = ops.simplify(g)
+            if s is not None:
+                self.queue.append(ops.lower(s, self.n))
+
+    def _flush(self):
+        if self.queue:
+            passes = ops.plan_passes(self.queue, self.n, 16, tile_bits=min(12, max(2, self.n - 1)),
+                                     min_low_bits=min(6, max(0, self.n - 3)), enable=self.fuse)
+            self.state = bitsim.run_passes(self.state, passes, self.n)
+            self.arena = np.empty_like(self.state)
+            self.queue = []
+
+    def get_state(self):
+        self._flush()
+        return self.state
+
+    def func_apply(self, *a, **k):
+        self._flush()
+        return super().func_apply(*a, **k)
+
+    def measure(self, *a, **k):
+        self._flush()
+        return super().measure(*a, **k)
+
+    def soft_measure(self, *a, **k):
+        self._flush()
+        return super().soft_measure(*a, **k)
+
+    def reduce_measure(self, *a, **k):
+        self._flush()
+        return super().reduce_measure(*a, **k)
+
+    def measure_probabilities(self, *a, **k):
+        self._flush()
+        return super().measure_probabilities(*a, **k)
+
+    def total_prob(self):
+        self._flush()
+        return super().total_prob()
+
+
+SMALL = [i for i, s in enumerate(STREAMS) if s["n"] <= 12]
+
+
+@pytest.mark.parametrize("i", SMALL, ids=[STREAMS[i]["label"] for i in SMALL])
+def test_host_pipeline_replays_golden_stream(i):
+    assert replay.replay(STREAMS[i], ARRAYS, PlannedHostBackend.make_state, tol=1e-12)
+
+
+def test_decode_validation_matches_reference_errors():       # qip/util.py:35-58, kronprod.pyx:114-116
+    with pytest.raises(Exception, match="Type of indices must be tuple"):
+        ops.decode_mats({"a": np.eye(2)}, 3)
+    with pytest.raises(Exception, match="Shape of square submatrix"):
+        ops.decode_mats({(0, 1): np.eye(2)}, 3)
+    with pytest.raises(ValueError, match="not numpy, SwapMat, or CMat"):
+        class Odd:
+            shape = (2, 2)
+        ops.decode_mats({0: Odd()}, 3)
+    with pytest.raises(ValueError):
+        ops.decode_mats({5: np.eye(2)}, 3)
+    with pytest.raises(ValueError, match="more than one entry"):
+        ops.decode_mats({0: H2, (0, 1): np.eye(4)}, 3)
+    # entries may share CONTROL qubits: C(C(Not)) onto a 2-qubit register
+    g = ops.decode_mats({(0, 1, 2): CMat(CMat(X2)), (0, 1, 3): CMat(CMat(X2))}, 4)
+    assert [x.controls for x in g] == [(0, 1), (0, 1)] and [x.targets for x in g] == [(2,), (3,)]
+    # list values and int keys are normalised
+    g = ops.decode_mats({1: [[0, 1], [1, 0]]}, 2)
+    assert g[0].targets == (1,) and g[0].mat.dtype == np.complex128
+
+
+def test_swapmat_decodes_to_bit_swaps():
+    g = ops.decode_mats({(0, 1, 2, 3, 4): CMat(SwapMat(2))}, 5)
+    assert [(x.kind, x.targets, x.controls) for x in g] == [("swap", (1, 3), (0,)), ("swap", (2, 4), (0,))]
+
+
+def test_simplify_promotes_controls_and_detects_diagonals():
+    rm = ops.simplify(ops.decode_mats({2: rm_mat(3)}, 4)[0])
+    assert rm.targets == () and rm.controls == (2,) and rm.mat.shape == (1, 1) and rm.diagonal
+    cp = ops.simplify(ops.decode_mats({(3, 1): CMat(rm_mat(2))}, 4)[0])
+    assert cp.targets == () and set(cp.controls) == {3, 1}
+    cx = ops.simplify(ops.decode_mats({(0, 1): np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])}, 2)[0])
+    assert cx.targets == (1,) and cx.controls == (0,) and np.array_equal(cx.mat, X2)
+    assert ops.simplify(ops.decode_mats({0: np.eye(2)}, 1)[0]) is None
+    z = ops.simplify(ops.decode_mats({0: np.array([[1, 0], [0j, -1]])}, 1)[0])
+    assert z.targets == () and z.mat[0, 0] == -1
+    d = ops.simplify(ops.decode_mats({0: np.diag([1j, -1j])}, 1)[0])
+    assert d.targets == (0,) and d.diagonal
+    h = ops.simplify(ops.decode_mats({0: H2}, 1)[0])
+    assert h.targets == (0,) and not h.diagonal
+
+
+def test_planner_fuses_qft_into_few_passes():
+    n = 24
+    gates = []
+    for mats in qfft_stream(n):
+        for g in ops.decode_mats(mats, n):
+            gates.append(ops.lower(ops.simplify(g), n))
+    assert len(gates) == n + n * (n - 1) // 2 + n // 2
+    passes = ops.plan_passes(gates, n, 16, tile_bits=12, min_low_bits=6)
+    assert sum(len(p.gates) for p in passes) == len(gates)
+    assert len(passes) <= 12, len(passes)
+    for p in passes:
+        if p.fused:
+            assert len(p.tile_bits) == 12 and p.tile_bits[:6] == (0, 1, 2, 3, 4, 5)
+    unfused = ops.plan_passes(gates, n, 16, enable=False)
+    assert len(unfused) == len(gates) and not any(p.fused for p in unfused)
+
+
+def test_planner_keeps_cheap_controlled_gates_unfused():
+    n = 20
+    g = ops.lower(ops.simplify(ops.decode_mats({(3, 1): CMat(rm_mat(2))}, n)[0]), n)
+    passes = ops.plan_passes([g, g], n, 16)
+    assert [p.fused for p in passes] == [False, False]      # 2 x 1/4 of the state < one full sweep
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_planned_execution_equals_oracle_on_random_circuits(seed):
+    rng = np.random.default_rng(seed)
+    n = 9
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    a = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+    b = PlannedHostBackend.make_state(n, [list(range(n))], [psi])
+    for mats in layered_stream(n, 3, seed):
+        a.kronselect_dot(mats)
+        b.kronselect_dot(mats)
+    assert replay.close(b.get_state(), a.get_state(), 1e-12)
+
+
+def test_scan_outcome_matches_reference_semantics():         # qip/ext/kronprod.pyx:364-381
+    probs = np.array([0.0, 0.64, 0.0, 0.36])
+    assert scan_outcome(probs, 0.0) == (0, 0.0)              # r == 0 stops at the first outcome
+    assert scan_outcome(probs, 0.5) == (1, 0.64)
+    assert scan_outcome(probs, 0.64 + 1e-9)[0] == 3
+    assert scan_outcome(probs, 1.0)[0] == 3
+    assert scan_outcome(np.array([0.5, 0.5]), 0.999999)[0] == 1
+    # a draw that rounding leaves positive after the last outcome returns the last outcome
+    assert scan_outcome(np.array([0.25, 0.25]), 1.0 + 1e-12)[0] == 1
+
+
+def test_top_probabilities():
+    assert top_probabilities([0.0, 0.0, 0.64, 0.36], 4) == ([2, 3, 0, 1], [0.64, 0.36, 0.0, 0.0])
+    assert top_probabilities([0.1, 0.2, 0.3, 0.4], 3)[0] == [3, 2, 1]
+    assert top_probabilities([0.5, 0.5], 9)[0] == [0, 1]
+
+
+def test_tabulate_vectorised_and_fallback():
+    assert np.array_equal(tabulate(lambda x: (x + 1) % 4, 2), [1, 2, 3, 0])
+    assert np.array_equal(tabulate(lambda x: 1, 3), np.ones(8))
+    assert np.array_equal(tabulate(lambda x: int(x == 5), 3), [0, 0, 0, 0, 0, 1, 0, 0])      # int() of an array raises
+    assert np.array_equal(tabulate(lambda x: pow(3, int(x), 8), 3), [pow(3, x, 8) for x in range(8)])
+    assert np.array_equal(tabulate(lambda x: (x == 5) * 1, 12)[:8], [0, 0, 0, 0, 0, 1, 0, 0])
+
+
+def _stream_of(label):
+    return [s for s in STREAMS if s["label"] == label][0]
+
+
+def _same_mats(a, b):
+    if list(a.keys()) != list(b.keys()):
+        return False
+    for k in a:
+        x, y = a[k], b[k]
+        while getattr(x, "_kron_struct", None) == 2:
+            if getattr(y, "_kron_struct", None) != 2:
+                return False
+            x, y = x.m, y.m
+        if getattr(x, "_kron_struct", None) == 3:
+            if getattr(y, "_kron_struct", None) != 3 or x.n != y.n:
+                return False
+        elif not np.array_equal(np.asarray(x, dtype=np.complex128), np.asarray(y, dtype=np.complex128)):
+            return False
+    return True
+
+
+def test_qfft_generator_equals_reference_front_end_stream():
+    s = _stream_of("config/qfft8")
+    ref_ops = [replay.dec_mats(ARRAYS, op["mats"]) for op in s["ops"]]
+    mine = list(qfft_stream(8))
+    assert len(ref_ops) == len(mine) == 8 + 28 + 4
+    assert all(_same_mats(a, b) for a, b in zip(mine, ref_ops))
+
+
+def test_layered_generator_equals_reference_front_end_stream():
+    s = _stream_of("config/layered_n8_d4_s33")
+    ref_ops = [replay.dec_mats(ARRAYS, op["mats"]) for op in s["ops"]]
+    mine = list(layered_stream(8, 4, 33))
+    assert len(ref_ops) == len(mine)
+    assert all(_same_mats(a, b) for a, b in zip(mine, ref_ops))
