@@ -234,7 +234,7 @@ def test_func_apply_with_remaining_qubits_and_scattered_registers():
 def test_probabilities_all_shapes(n):
     rng = np.random.default_rng(n)
     g, c = _pair(n, _rand_state(rng, n))
-    cases = [[0], [n - 1], [n - 1, 0], list(range(n)), list(range(n))[::-1], [1, n - 2]]
+    cases = [[0], [n - 1], [n - 1, 0], list(range(n)), list(range(n))[::-1], [1, n - 1]]
     if n >= 9:
         cases += [[8, 3, 5, 0], [2, 7, 6], list(range(n - 4, n)), list(range(0, n, 2))]
     for idx in cases:
