@@ -26,7 +26,7 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 from . import lib as _lib
-from .ops import BitGate, Gate, Pass, decode_mats, lower, plan_passes, simplify
+from .ops import BitGate, Gate, Pass, decode_mats, lower, plan, simplify
 
 _HOST_STATE_MAX_QUBITS = 28     # get_state() returns a host ndarray up to here, a lazy handle beyond
 
@@ -59,7 +59,8 @@ class DeviceState(object):
 class B200Backend(object):
     """StateType implementation on one B200 (see module docstring)."""
 
-    def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6):
+    def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6,
+                 strategy: str = "auto"):
         torch = _torch()
         self.L = _lib.load()
         if not torch.cuda.is_available():
@@ -76,11 +77,12 @@ class B200Backend(object):
         self.fuse = fuse
         self.tile_bits = tile_bits
         self.min_low_bits = min_low_bits
+        self.strategy = strategy
         ctx = ctypes.c_void_p()
         _lib.check(self.L.qipb_create(self.device.index or 0, ctypes.byref(ctx)))
         self.ctx = ctx
         self.state = None            # torch tensor, 2^n amplitudes
-        self.queue: List[BitGate] = []
+        self.queue: List[Gate] = []        # logical gates, merged / lowered / planned at flush time
         self.stats = {"gates": 0, "passes": 0, "fused_passes": 0, "flushes": 0}
         self.profile = None          # list of (kernel label, algorithmic bytes, start event, end event) when enabled
 
@@ -159,7 +161,7 @@ class B200Backend(object):
         for g in decode_mats(mats, self.n):
             s = simplify(g)
             if s is not None:
-                self.queue.append(lower(s, self.n))
+                self.queue.append(s)
                 self.stats["gates"] += 1
 
     def _launch_single(self, g: BitGate):
@@ -190,8 +192,9 @@ class B200Backend(object):
         if not self.queue:
             return
         torch = _torch()
-        passes = plan_passes(self.queue, self.n, self.amp_bytes, tile_bits=self.tile_bits,
-                             min_low_bits=self.min_low_bits, enable=self.fuse)
+        passes, chosen = plan(self.queue, self.n, self.amp_bytes, fuse=self.fuse, tile_bits=self.tile_bits,
+                              min_low_bits=self.min_low_bits, strategy=self.strategy)
+        self.stats["strategy_" + chosen] = self.stats.get("strategy_" + chosen, 0) + 1
         self.queue = []
         with torch.cuda.device(self.device):
             self._stream()

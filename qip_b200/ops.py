@@ -114,6 +114,9 @@ def decode_mats(mats, n: int) -> List[Gate]:
 
 
 # --------------------------------------------------------------------------------- simplification
+_SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
 def _bit_split(mat, k, j):
     """Blocks of `mat` w.r.t. matrix-index bit for target j (0 = MSB): (M00, M01, M10, M11)."""
     d = 1 << k
@@ -142,8 +145,88 @@ def simplify(g: Gate) -> Optional[Gate]:
     d = mat.shape[0]
     if np.array_equal(mat, np.eye(d)):
         return None
+    if d == 4 and np.array_equal(mat, _SWAP4):
+        return Gate("swap", tuple(targets), tuple(controls))
     diagonal = not (mat - np.diag(np.diag(mat))).any()
     return Gate("matrix", tuple(targets), tuple(controls), np.ascontiguousarray(mat, dtype=np.complex128), diagonal)
+
+
+# --------------------------------------------------------------------------------- block merging
+def gate_unitary(g: Gate):
+    """(qubit list, dense matrix) of a gate over controls ++ targets (first qubit = MSB)."""
+    if g.kind == "swap":
+        inner = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+    else:
+        inner = g.mat
+    qs = list(g.controls) + list(g.targets)
+    d = 1 << len(qs)
+    di = inner.shape[0]
+    full = np.eye(d, dtype=np.complex128)
+    full[d - di:, d - di:] = inner          # all controls = 1 is the last block of the index space
+    return qs, full
+
+
+def _apply_to_block(block_mat, block_qubits, u, u_qubits):
+    """(u acting on u_qubits, embedded in block space) @ block_mat."""
+    m = len(block_qubits)
+    t = block_mat.reshape([2] * m + [1 << m])
+    axes = [block_qubits.index(q) for q in u_qubits]
+    ku = len(u_qubits)
+    ut = u.reshape([2] * (2 * ku))
+    r = np.tensordot(ut, t, axes=(list(range(ku, 2 * ku)), axes))
+    r = np.moveaxis(r, list(range(ku)), axes)
+    return np.ascontiguousarray(r.reshape(1 << m, 1 << m))
+
+
+def merge_blocks(gates: Sequence[Gate], max_k: int = 4) -> List[Gate]:
+    """Order-preserving greedy merge of consecutive small gates into dense blocks on at most max_k
+    qubits by multiplying their matrices on the host (changes rounding at the 1e-16 level only).
+    A gate may slide back over blocks it shares no qubit with.  Every block is re-simplified, so a
+    block made only of controlled / diagonal gates keeps its cheap form."""
+    blocks: List[Optional[list]] = []          # [qubits(list), matrix] or [None, Gate] for opaque gates
+    last = {}                                   # qubit -> index of the last block that touches it
+    for g in gates:
+        qs, u = gate_unitary(g) if len(g.qubits()) <= max_k else (list(g.qubits()), None)
+        b = max([last.get(q, -1) for q in qs] + [-1])
+        if u is None:
+            blocks.append([None, g])
+            for q in qs:
+                last[q] = len(blocks) - 1
+            continue
+        target = None
+        if b >= 0 and blocks[b][0] is not None and len(set(blocks[b][0]) | set(qs)) <= max_k:
+            target = b
+        else:
+            # pack with a later block on disjoint qubits (tensor product), smallest result first
+            best = None
+            for j in range(b + 1, len(blocks)):
+                if blocks[j][0] is None:
+                    continue
+                size = len(set(blocks[j][0]) | set(qs))
+                if size <= max_k and (best is None or size < best[0]):
+                    best = (size, j)
+            if best is not None:
+                target = best[1]
+        if target is None:
+            blocks.append([list(qs), u])
+            target = len(blocks) - 1
+        else:
+            bq, bm = blocks[target]
+            new_q = bq + [q for q in qs if q not in bq]
+            if len(new_q) != len(bq):
+                bm = _apply_to_block(np.eye(1 << len(new_q), dtype=np.complex128), new_q, bm, bq)
+            blocks[target] = [new_q, _apply_to_block(bm, new_q, u, qs)]
+        for q in qs:
+            last[q] = max(last.get(q, -1), target)
+    out: List[Gate] = []
+    for bq, bm in blocks:
+        if bq is None:
+            out.append(bm)
+            continue
+        s = simplify(Gate("matrix", tuple(bq), (), bm))
+        if s is not None:
+            out.append(s)
+    return out
 
 
 # --------------------------------------------------------------------------------- bit-level form
@@ -253,3 +336,42 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
         need = nn
     flush()
     return passes
+
+
+# --------------------------------------------------------------------------------- strategy choice
+# Cost of one gate inside a fused tile pass, as a fraction of one full HBM sweep (read + write of
+# the whole state), calibrated on B200 (profiles/): the tile kernel becomes shared-memory / issue
+# bound once the gate list is long.  plan() uses it to choose between
+#   A. blocks of <= 2 qubits -> fused tile passes (diagonal gates and controls anywhere), and
+#   B. blocks of <= 4 qubits -> one register-blocked stand-alone launch per block (HBM roofline).
+TILE_GATE_COST = 0.40
+
+
+def pass_cost(p: Pass, nbits: int, amp_bytes: int) -> float:
+    full = 2.0 * amp_bytes * 2.0 ** nbits
+    if not p.fused:
+        return gate_bytes(p.gates[0], nbits, amp_bytes)
+    work = 0.0
+    for g in p.gates:
+        frac = 2.0 ** (-g.nctrl())
+        if g.kind == "swap":
+            frac *= 0.5
+        work += TILE_GATE_COST * max(frac, 0.05)
+    return full * max(1.0, work)
+
+
+def plan(gates: Sequence[Gate], n: int, amp_bytes: int = 16, fuse: bool = True, tile_bits: int = 12,
+         min_low_bits: int = 6, strategy: str = "auto"):
+    """Logical gates -> (list[Pass], name of the chosen strategy)."""
+    if not fuse:
+        return [Pass(False, [lower(g, n)]) for g in gates], "unfused"
+    out = {}
+    if strategy in ("auto", "tile"):
+        a = plan_passes([lower(g, n) for g in merge_blocks(gates, 2)], n, amp_bytes, tile_bits=tile_bits,
+                        min_low_bits=min_low_bits)
+        out["tile"] = (sum(pass_cost(p, n, amp_bytes) for p in a), a)
+    if strategy in ("auto", "dense4"):
+        b = [Pass(False, [lower(g, n)]) for g in merge_blocks(gates, 4)]
+        out["dense4"] = (sum(pass_cost(p, n, amp_bytes) for p in b), b)
+    name = min(out, key=lambda k: out[k][0])
+    return out[name][1], name

@@ -1,0 +1,208 @@
+"""Scheduling of a gate stream onto a state sharded over P = 2^G GPUs by its top G index bits.
+
+Pure host logic (numpy only): it is exercised on the CPU tier by a virtual-shard numpy executor and
+a world_size-2 gloo run (tests/test_sharding.py); qip_b200/sharded.py executes the same actions
+with the CUDA kernels and NVLink peer memory.
+
+Replaces qip/distributed's manager/worker decomposition (qip/distributed/manager.py:138-236,
+worker/worker.py:57-169): there every gate is computed as a P x P grid of mat-vec blocks followed by
+a reduce-to-diagonal and a re-broadcast.  Here the shard of rank r is the contiguous index range
+whose top G bits equal r (the same slicing as manager.py:162-170, but P shards, not P^2 blocks) and
+gate locality is exploited:
+  * control bits on global (rank) positions switch a gate on or off per rank -- no communication;
+  * diagonal gates with targets on global positions pick a sub-diagonal per rank -- none either;
+  * un-controlled Swap is a relabelling of the logical->physical map -- free;
+  * a dense 1-qubit gate on a global position whose qubit is not needed again soon runs as ONE
+    fused compute+exchange kernel over peer memory (PeerGate1);
+  * anything else non-diagonal on a global position first swaps that position with a local one
+    (Exchange: each rank trades half of its shard with one partner), victims chosen Belady-style
+    among the high local positions, whose halves are contiguous.
+"""
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .ops import BitGate, Gate
+
+SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+class Layout(object):
+    """Logical qubit -> physical index-bit position.  Positions >= nl are rank bits."""
+
+    def __init__(self, n: int, gbits: int):
+        self.n, self.G, self.nl = n, gbits, n - gbits
+        self.pos = [n - 1 - q for q in range(n)]          # canonical: qubit 0 = most significant bit
+
+    def copy(self):
+        c = Layout(self.n, self.G)
+        c.pos = list(self.pos)
+        return c
+
+    def qubit_at(self, p: int) -> int:
+        return self.pos.index(p)
+
+    def swap_qubits(self, a: int, b: int):
+        self.pos[a], self.pos[b] = self.pos[b], self.pos[a]
+
+    def is_global(self, q: int) -> bool:
+        return self.pos[q] >= self.nl
+
+    def canonical(self) -> bool:
+        return all(self.pos[q] == self.n - 1 - q for q in range(self.n))
+
+
+@dataclass
+class PhysGate:
+    """A gate in PHYSICAL positions over the whole (sharded) index; rank-independent."""
+    bits: Tuple[int, ...]
+    ctrl_mask: int
+    mat: np.ndarray
+    diagonal: bool
+
+
+@dataclass
+class Apply:
+    gate: PhysGate
+
+
+@dataclass
+class Exchange:
+    gpos: int        # physical rank-bit position (>= nl)
+    lpos: int        # physical local position (< nl)
+
+
+@dataclass
+class PeerGate1:
+    gpos: int
+    mat: np.ndarray
+    ctrl_mask: int   # physical mask (may contain rank bits)
+
+
+@dataclass
+class LocalSwap:
+    a: int
+    b: int
+
+
+def to_phys(g: Gate, lay: Layout) -> PhysGate:
+    cm = 0
+    for q in g.controls:
+        cm |= 1 << lay.pos[q]
+    if g.kind == "swap":
+        return PhysGate(tuple(lay.pos[q] for q in g.targets), cm, SWAP4, False)
+    return PhysGate(tuple(lay.pos[q] for q in g.targets), cm, g.mat, g.diagonal)
+
+
+def lower_for_rank(pg: PhysGate, nl: int, rank: int) -> Optional[BitGate]:
+    """Rank-local form of a PhysGate whose non-diagonal targets are all local; None = no-op here."""
+    lowmask = (1 << nl) - 1
+    cg = pg.ctrl_mask >> nl
+    if (rank & cg) != cg:
+        return None
+    k = len(pg.bits)
+    glob = [j for j, b in enumerate(pg.bits) if b >= nl]
+    if not glob:
+        return BitGate("matrix", pg.bits, pg.ctrl_mask & lowmask, pg.mat, pg.diagonal)
+    if not pg.diagonal:
+        raise ValueError("non-diagonal target on a rank bit must be localised first")
+    d = np.diag(pg.mat)
+    keep = [j for j in range(k) if j not in glob]
+    sub = np.zeros(1 << len(keep), dtype=np.complex128)
+    for c in range(1 << len(keep)):
+        idx = 0
+        for t, j in enumerate(keep):
+            if (c >> (len(keep) - 1 - t)) & 1:
+                idx |= 1 << (k - 1 - j)
+        for j in glob:
+            if (rank >> (pg.bits[j] - nl)) & 1:
+                idx |= 1 << (k - 1 - j)
+        sub[c] = d[idx]
+    if len(keep) == 0 and sub[0] == 1.0:
+        return None
+    return BitGate("matrix", tuple(pg.bits[j] for j in keep), pg.ctrl_mask & lowmask, np.diag(sub), True)
+
+
+def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8) -> List[object]:
+    """Turn logical gates into rank-independent actions; `lay` is updated in place."""
+    nl = lay.nl
+    actions: List[object] = []
+
+    def nondiag_targets(g: Gate):
+        if g.kind == "swap":
+            return list(g.targets) if g.controls else []
+        return [] if (g.diagonal or g.k == 0) else list(g.targets)
+
+    uses = [nondiag_targets(g) for g in gates]
+
+    def next_use(q: int, start: int) -> int:
+        for j in range(start, len(gates)):
+            if q in uses[j]:
+                return j
+        return 1 << 30
+
+    for i, g in enumerate(gates):
+        if g.kind == "swap" and not g.controls:
+            lay.swap_qubits(g.targets[0], g.targets[1])          # pure relabel
+            continue
+        need = uses[i]
+        glob = [q for q in need if lay.is_global(q)]
+        if glob and lay.G > 0:
+            if (g.kind == "matrix" and g.k == 1 and next_use(glob[0], i + 1) >= (1 << 30)):
+                cm = 0
+                for q in g.controls:
+                    cm |= 1 << lay.pos[q]
+                actions.append(PeerGate1(lay.pos[glob[0]], g.mat, cm))
+                continue
+            # batch: other global qubits that are needed non-diagonally before any victim would be
+            batch = list(glob)
+            for j in range(i + 1, min(len(gates), i + 1 + 4 * lay.n)):
+                for q in uses[j]:
+                    if lay.is_global(q) and q not in batch and len(batch) < lay.G:
+                        batch.append(q)
+            window = [lay.qubit_at(p) for p in range(nl - 1, max(-1, nl - 1 - top_window), -1)]
+            taken = set()
+            for q in batch:
+                cands = [v for v in window if v not in need and v not in taken and v not in batch]
+                if not cands:
+                    if q in glob:
+                        raise ValueError("cannot localise qubit %d: no free local position" % q)
+                    continue
+                victim = max(cands, key=lambda v: next_use(v, i))
+                if q not in glob and next_use(victim, i) <= next_use(q, i):
+                    continue                                   # bringing q in early would evict something needed sooner
+                taken.add(victim)
+                actions.append(Exchange(lay.pos[q], lay.pos[victim]))
+                lay.swap_qubits(q, victim)
+        actions.append(Apply(to_phys(g, lay)))
+    return actions
+
+
+def canonicalise(lay: Layout) -> List[object]:
+    """Actions that bring the layout back to qubit q at bit n-1-q (needed before the state is
+    read out in index order).  Rank-bit <-> rank-bit swaps go through a local position."""
+    nl = lay.nl
+    actions: List[object] = []
+
+    def swap_positions(p1: int, p2: int):
+        if p1 == p2:
+            return
+        a, b = lay.qubit_at(p1), lay.qubit_at(p2)
+        hi, lo = max(p1, p2), min(p1, p2)
+        if hi < nl:
+            actions.append(LocalSwap(p1, p2))
+        elif lo < nl:
+            actions.append(Exchange(hi, lo))
+        else:
+            t = nl - 1                                          # via the top local position
+            actions.append(Exchange(p1, t))
+            actions.append(Exchange(p2, t))
+            actions.append(Exchange(p1, t))
+        lay.swap_qubits(a, b)
+
+    for q in range(lay.n):
+        want = lay.n - 1 - q
+        if lay.pos[q] != want:
+            swap_positions(lay.pos[q], want)
+    return actions

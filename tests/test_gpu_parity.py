@@ -144,15 +144,17 @@ def test_multi_entry_ops_and_wide_swap():
 def test_layered_circuit_fused_and_unfused_match_oracle(n, depth, seed):
     rng = np.random.default_rng(seed)
     psi = _rand_state(rng, n)
-    gf, c = _pair(n, psi)
+    gf, c = _pair(n, psi, strategy="tile")
+    gd = _backend().make_state(n, [list(range(n))], [psi], strategy="dense4")
     gu = _backend().make_state(n, [list(range(n))], [psi], fuse=False)
     for mats in layered_stream(n, depth, seed):
-        gf.kronselect_dot(mats)
-        gu.kronselect_dot(mats)
-        c.kronselect_dot(mats)
+        for b in (gf, gd, gu, c):
+            b.kronselect_dot(mats)
     _agree(gf, c)
+    _agree(gd, c)
     _agree(gu, c)
-    assert gf.stats["fused_passes"] >= 1 and gu.stats["fused_passes"] == 0
+    assert gf.stats["fused_passes"] >= 1 and gu.stats["fused_passes"] == 0 and gd.stats["fused_passes"] == 0
+    assert gd.stats["passes"] < gu.stats["passes"]
 
 
 @pytest.mark.parametrize("n", [5, 12, 16])
@@ -178,7 +180,7 @@ def test_fused_pass_with_tile_bits_in_the_middle_and_top():
     n = 20
     rng = np.random.default_rng(9)
     psi = _rand_state(rng, n)
-    g, c = _pair(n, psi)
+    g, c = _pair(n, psi, strategy="tile")
     ops_ = [{0: H2}, {(19, 0): CMat(rm_mat(2))}, {1: haar_unitary(rng, 2)}, {(7, 1): CMat(X2)},
             {(0, 2): haar_unitary(rng, 4)}, {(12, 3): np.diag(np.exp(1j * rng.normal(size=4)))},
             {(0, 1): SwapMat(1)}, {(15, 2, 0): CMat(CMat(haar_unitary(rng, 2)))}, {10: rm_mat(5)},
@@ -326,7 +328,7 @@ def test_raw_c_abi_call_sequence():
     out = np.zeros(2 ** n, dtype=np.complex128)
     lib.check(L.qipb_memcpy_d2h(ctx, out.ctypes.data_as(ctypes.c_void_p), ptr, 16 << n))
     want = np.zeros(2 ** n, dtype=np.complex128)
-    want[0] = want[2 ** n - 1] = 1 / np.sqrt(2)                 # Bell pair on (qubit 0, qubit n-1)
+    want[0] = want[(1 << (n - 1)) | 1] = 1 / np.sqrt(2)        # Bell pair on index bits n-1 and 0
     assert np.allclose(out, want, rtol=0, atol=1e-15)
     assert L.qipb_launch_count(ctx) == 3
     assert L.qipb_apply_matrix(ctx, ptr, n, lib.C128, 1, lib.int_array([n]), lib.mat_array(H2), 0, 0) != 0

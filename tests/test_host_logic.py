@@ -20,24 +20,33 @@ class PlannedHostBackend(orc.OracleBackend):
     """Oracle state container whose kronselect_dot goes through the PRODUCT's host pipeline
     (decode -> simplify -> lower -> plan_passes) and a numpy executor of the resulting plan."""
     fuse = True
+    strategy = "auto"
 
-    @staticmethod
-    def make_state(n, index_groups, feed_list, statetype=np.complex128, **_):
+    @classmethod
+    def make_state(cls, n, index_groups, feed_list, statetype=np.complex128, **_):
         ob = orc.OracleBackend.make_state(n, index_groups, feed_list)
-        b = PlannedHostBackend(n, ob.state)
+        b = cls(n, ob.state)
         b.queue = []
         return b
+
+
+class TileHostBackend(PlannedHostBackend):
+    strategy = "tile"
+
+
+class Dense4HostBackend(PlannedHostBackend):
+    strategy = "dense4"
 
     def kronselect_dot(self, mats, input_offset=0, output_offset=0):
         for g in ops.decode_mats(mats, self.n):
             s = ops.simplify(g)
             if s is not None:
-                self.queue.append(ops.lower(s, self.n))
+                self.queue.append(s)
 
     def _flush(self):
         if self.queue:
-            passes = ops.plan_passes(self.queue, self.n, 16, tile_bits=min(12, max(2, self.n - 1)),
-                                     min_low_bits=min(6, max(0, self.n - 3)), enable=self.fuse)
+            passes, _ = ops.plan(self.queue, self.n, 16, fuse=self.fuse, tile_bits=min(12, max(2, self.n - 1)),
+                                 min_low_bits=min(6, max(0, self.n - 3)), strategy=self.strategy)
             self.state = bitsim.run_passes(self.state, passes, self.n)
             self.arena = np.empty_like(self.state)
             self.queue = []
@@ -76,7 +85,8 @@ SMALL = [i for i, s in enumerate(STREAMS) if s["n"] <= 12]
 
 @pytest.mark.parametrize("i", SMALL, ids=[STREAMS[i]["label"] for i in SMALL])
 def test_host_pipeline_replays_golden_stream(i):
-    assert replay.replay(STREAMS[i], ARRAYS, PlannedHostBackend.make_state, tol=1e-12)
+    assert replay.replay(STREAMS[i], ARRAYS, TileHostBackend.make_state, tol=1e-12)
+    assert replay.replay(STREAMS[i], ARRAYS, Dense4HostBackend.make_state, tol=1e-12)
 
 
 def test_decode_validation_matches_reference_errors():       # qip/util.py:35-58, kronprod.pyx:114-116
@@ -126,22 +136,49 @@ def test_planner_fuses_qft_into_few_passes():
     gates = []
     for mats in qfft_stream(n):
         for g in ops.decode_mats(mats, n):
-            gates.append(ops.lower(ops.simplify(g), n))
+            gates.append(ops.simplify(g))
     assert len(gates) == n + n * (n - 1) // 2 + n // 2
-    passes = ops.plan_passes(gates, n, 16, tile_bits=12, min_low_bits=6)
-    assert sum(len(p.gates) for p in passes) == len(gates)
+    passes, name = ops.plan(gates, n, 16, strategy="tile")
     assert len(passes) <= 12, len(passes)
     for p in passes:
         if p.fused:
             assert len(p.tile_bits) == 12 and p.tile_bits[:6] == (0, 1, 2, 3, 4, 5)
-    unfused = ops.plan_passes(gates, n, 16, enable=False)
-    assert len(unfused) == len(gates) and not any(p.fused for p in unfused)
+    unfused, name = ops.plan(gates, n, 16, fuse=False)
+    assert name == "unfused" and len(unfused) == len(gates) and not any(p.fused for p in unfused)
+    _, auto = ops.plan(gates, n, 16)
+    assert auto == "tile"                                   # diagonal-heavy: tile passes beat dense blocks
+
+
+def test_merge_blocks_is_exact_and_shrinks_layered_circuits():
+    n = 10
+    gates = []
+    for mats in layered_stream(n, 2, 5):
+        for g in ops.decode_mats(mats, n):
+            s = ops.simplify(g)
+            if s is not None:
+                gates.append(s)
+    rng = np.random.default_rng(0)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    ref = psi.copy()
+    for g in gates:
+        ref = bitsim.apply_bitgate(ref, ops.lower(g, n), n)
+    for mk in (2, 3, 4):
+        merged = ops.merge_blocks(gates, mk)
+        assert len(merged) < len(gates) and all(len(g.qubits()) <= mk for g in merged)
+        out = psi.copy()
+        for g in merged:
+            out = bitsim.apply_bitgate(out, ops.lower(g, n), n)
+        assert float(np.max(np.abs(out - ref))) <= 1e-13
+    # a lone swap stays a (half-traffic) swap, CX stays controlled after merging
+    keep = ops.merge_blocks([ops.Gate("swap", (0, 1)), ops.simplify(ops.decode_mats({(2, 3): CMat(X2)}, 4)[0])], 2)
+    assert keep[0].kind == "swap" and keep[1].controls == (2,)
 
 
 def test_planner_keeps_cheap_controlled_gates_unfused():
     n = 20
     g = ops.lower(ops.simplify(ops.decode_mats({(3, 1): CMat(rm_mat(2))}, n)[0]), n)
-    passes = ops.plan_passes([g, g], n, 16)
+    g2 = ops.lower(ops.simplify(ops.decode_mats({(5, 7): CMat(rm_mat(2))}, n)[0]), n)
+    passes = ops.plan_passes([g, g2], n, 16)
     assert [p.fused for p in passes] == [False, False]      # 2 x 1/4 of the state < one full sweep
 
 
