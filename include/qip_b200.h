@@ -153,6 +153,10 @@ int qipb_add_range(qipb_ctx *ctx, void *state, int dtype, uint64_t start, uint64
  *   with qipb_dev_alloc, and the peer-side mapping of it.
  * qipb_peer_swap: in place, exchanges `count` amplitudes starting at local[local_off] with
  *   peer[peer_off] -- one kernel, loads and stores straight over NVLink, no staging buffer.
+ * qipb_peer_swap_bit: in place, swaps a GLOBAL (rank) index bit with local bit `lbit`: this rank's
+ *   amplitudes whose bit lbit != my_gbit trade places with the partner's amplitudes whose bit lbit
+ *   == my_gbit.  The 2^(nbits-1) pairs are indexed by w (the local index with bit lbit removed);
+ *   the two ranks of a pair each process a disjoint [w_begin, w_begin+count) half.
  * qipb_peer_gate1: the fused compute+exchange kernel for a 1-qubit gate whose target is a GLOBAL
  *   (rank) bit: for count amplitudes, (lo, hi) <- mat * (lo, hi) where `lo` lives on the shard
  *   whose rank bit is 0 and `hi` on its partner.  The caller that owns `local` passes
@@ -162,6 +166,8 @@ int qipb_ipc_open(qipb_ctx *ctx, const unsigned char handle[64], void **peer_ptr
 int qipb_ipc_close(qipb_ctx *ctx, void *peer_ptr);
 int qipb_peer_swap(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t local_off,
                    uint64_t peer_off, uint64_t count);
+int qipb_peer_swap_bit(qipb_ctx *ctx, void *local, void *peer, int nbits, int dtype, int lbit,
+                       int my_gbit, uint64_t w_begin, uint64_t count);
 int qipb_peer_gate1(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t off,
                     uint64_t count, const double *mat, int local_is_hi, uint64_t ctrl_mask);
 

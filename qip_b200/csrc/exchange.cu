@@ -30,6 +30,29 @@ __global__ void __launch_bounds__(256) peer_swap_kernel(A *__restrict__ local, A
         if (idx[u] < count) { local[idx[u]] = b[u]; peer[idx[u]] = a[u]; }
 }
 
+// Swap of a rank (global) index bit with local bit `lbit`: the amplitudes whose local bit differs
+// from this rank's global-bit value trade places with the partner's amplitudes whose local bit
+// equals it.  w enumerates the 2^(nbits-1) indices with bit `lbit` removed.
+template <typename A, int U>
+__global__ void __launch_bounds__(256) peer_swap_bit_kernel(A *__restrict__ local, A *__restrict__ peer, int lbit, int my_g,
+                                                            u64 w_begin, u64 count) {
+    A a[U], b[U];
+    u64 li[U], pi[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const u64 t = ((u64)blockIdx.x * U + u) * blockDim.x + threadIdx.x;
+        live[u] = t < count;
+        const u64 base = insert_zero(w_begin + t, lbit);
+        li[u] = base | ((u64)(1 - my_g) << lbit);
+        pi[u] = base | ((u64)my_g << lbit);
+        if (live[u]) { a[u] = local[li[u]]; b[u] = peer[pi[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (live[u]) { local[li[u]] = b[u]; peer[pi[u]] = a[u]; }
+}
+
 struct PeerGateArgs {
     u64 count;
     u64 ctrl_mask;        // local-index bits that must be 1
@@ -102,6 +125,23 @@ extern "C" int qipb_peer_swap(qipb_ctx *ctx, void *local, void *peer, int dtype,
     QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
     if (dtype == QIPB_C128) peer_swap_kernel<double2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)local + local_off, (double2 *)peer + peer_off, count);
     else if (dtype == QIPB_C64) peer_swap_kernel<float2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)local + local_off, (float2 *)peer + peer_off, count);
+    else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
+    ctx->launches++;
+    QIPB_CUDA(cudaGetLastError());
+    return QIPB_OK;
+}
+
+extern "C" int qipb_peer_swap_bit(qipb_ctx *ctx, void *local, void *peer, int nbits, int dtype, int lbit, int my_gbit,
+                                  uint64_t w_begin, uint64_t count) {
+    QIPB_REQUIRE(ctx && local && peer, "null argument");
+    QIPB_REQUIRE(nbits >= 1 && nbits <= 40 && lbit >= 0 && lbit < nbits && (my_gbit == 0 || my_gbit == 1), "bad peer_swap_bit arguments");
+    QIPB_REQUIRE(w_begin + count <= (1ull << (nbits - 1)), "peer_swap_bit range exceeds 2^(nbits-1)");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    if (count == 0) return QIPB_OK;
+    const u64 blocks = (count + 256ull * 4 - 1) / (256ull * 4);
+    QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
+    if (dtype == QIPB_C128) peer_swap_bit_kernel<double2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)local, (double2 *)peer, lbit, my_gbit, w_begin, count);
+    else if (dtype == QIPB_C64) peer_swap_bit_kernel<float2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)local, (float2 *)peer, lbit, my_gbit, w_begin, count);
     else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());

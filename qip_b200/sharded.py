@@ -1,0 +1,409 @@
+"""ShardedB200Backend -- the StateType surface over P = 2^G B200s, one process per GPU.
+
+Replaces qip/distributed (DistributedBackend + manager + workers, qip/distributed/backend.py:31-129,
+manager.py, worker/worker.py) for a single NVSwitch box: the state is sharded by its top G index
+bits (rank r owns the contiguous range whose top bits are r, the slicing of manager.py:162-170),
+gates are scheduled by qip_b200.shardplan, local work runs through the same fused sm_100a kernels
+as the single-GPU backend, and the only data motion is
+  * qipb_peer_swap_bit  -- global<->local qubit swap, in place over NVLink peer memory (CUDA IPC),
+  * qipb_peer_gate1     -- fused compute+exchange for a 1-qubit gate on a rank bit,
+  * a float64 all-reduce (NCCL, via torch.distributed) of probability histograms.
+Every rank runs the same python program (SPMD) and must make the same calls in the same order.
+torch.distributed supplies rendezvous, handle exchange, the stream-ordered barriers around peer
+kernels and the histogram all-reduce; it never carries amplitudes.
+"""
+import ctypes
+import math
+import random
+from typing import List, Optional
+
+import numpy as np
+
+from . import lib as _lib
+from . import shardplan as sp
+from .backend import (B200Backend, _check_measure_args, scan_outcome, tabulate, top_probabilities)
+from .ops import BitGate, Gate, Pass, decode_mats, merge_blocks, plan_passes, simplify
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _RawCuda(object):
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class ShardedB200Backend(object):
+    def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6):
+        torch = _torch()
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise _lib.QipbError("ShardedB200Backend needs torch.distributed initialised (one rank per GPU)")
+        self.dist = dist
+        self.rank, self.P = dist.get_rank(), dist.get_world_size()
+        self.G = int(round(math.log2(self.P)))
+        if (1 << self.G) != self.P:
+            raise ValueError("number of ranks must be a power of two")
+        self.n = int(n)
+        self.nl = self.n - self.G
+        if self.nl < 1:
+            raise ValueError("need at least one local qubit per rank")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        # local engine: a single-GPU backend over the nl local bits, re-used for its launch helpers
+        self.eng = B200Backend(self.nl, dtype, device=self.device, fuse=fuse, tile_bits=tile_bits, min_low_bits=min_low_bits)
+        self.L = self.eng.L
+        self.ctx = self.eng.ctx
+        self.code, self.amp_bytes, self.np_dtype = self.eng.code, self.eng.amp_bytes, self.eng.np_dtype
+        self.layout = sp.Layout(self.n, self.G)
+        self.queue: List[Gate] = []
+        self.fuse = fuse
+        self.stats = {"gates": 0, "exchanges": 0, "peer_gates": 0, "nvlink_bytes_out": 0}
+        # shard memory comes from cudaMalloc (qipb_dev_alloc) so that its IPC handle maps it exactly
+        count = 1 << self.nl
+        ptr = ctypes.c_void_p()
+        _lib.check(self.L.qipb_dev_alloc(self.ctx, count * self.amp_bytes, ctypes.byref(ptr)))
+        self.ptr = ptr
+        self.eng.state = torch.as_tensor(_RawCuda(ptr.value, count, "<c16" if self.amp_bytes == 16 else "<c8"),
+                                         device=self.device)
+        assert self.eng.state.data_ptr() == ptr.value
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(self.L.qipb_ipc_export(self.ctx, ptr, handle))
+        handles = [None] * self.P
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.peers = {}
+        for r in range(self.P):
+            if r != self.rank:
+                pp = ctypes.c_void_p()
+                _lib.check(self.L.qipb_ipc_open(self.ctx, handles[r], ctypes.byref(pp)))
+                self.peers[r] = pp
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._sync_all()
+
+    # ------------------------------------------------------------------ plumbing
+    def _sync_all(self):
+        """Stream-ordered barrier: peers' earlier kernels are complete when later work starts."""
+        self.dist.all_reduce(self._token)
+
+    def _stream(self):
+        self.eng._stream()
+
+    @property
+    def profile(self):
+        return self.eng.profile
+
+    @profile.setter
+    def profile(self, v):
+        self.eng.profile = v
+
+    def launch_count(self):
+        return self.eng.launch_count()
+
+    @staticmethod
+    def make_state(n, index_groups, feed_list, statetype=np.complex128, **kwargs) -> "ShardedB200Backend":
+        b = ShardedB200Backend(n, statetype, **kwargs)
+        b._init_state(index_groups, feed_list)
+        return b
+
+    def _init_state(self, index_groups, feed_list):
+        torch = _torch()
+        n, nl = self.n, self.nl
+        groups = [[int(q) for q in g] for g in index_groups]
+        flat = [q for g in groups for q in g]
+        if len(groups) != len(feed_list) or len(set(flat)) != len(flat) or any(not (0 <= q < n) for q in flat):
+            raise ValueError("bad feed groups")
+        self._stream()
+        if not groups:
+            _lib.check(self.L.qipb_init_basis(self.ctx, self.ptr, nl, self.code, 0 if self.rank == 0 else -1))
+            return
+        feeds = []
+        for g, f in zip(groups, feed_list):
+            if isinstance(f, (int, np.integer)):
+                v = np.zeros(2 ** len(g), dtype=np.complex128)
+                v[int(f)] = 1.0
+            else:
+                v = np.asarray(f, dtype=np.complex128).reshape(-1)
+            if v.shape[0] != 2 ** len(g):
+                raise ValueError("feed length does not match 2**len(group)")
+            feeds.append(v)
+        dev_feeds = torch.from_numpy(np.ascontiguousarray(np.concatenate(feeds))).to(self.device)
+        zero_mask = 0
+        for q in range(n):
+            if q not in flat:
+                zero_mask |= 1 << (n - 1 - q)
+        _lib.check(self.L.qipb_init_kron(self.ctx, self.ptr, nl, self.code, len(groups),
+                                         _lib.int_array([len(g) for g in groups]),
+                                         _lib.int_array([n - 1 - q for q in flat]),
+                                         ctypes.c_void_p(dev_feeds.data_ptr()), zero_mask, self.rank))
+        self._keep = dev_feeds
+
+    # ------------------------------------------------------------------ gates
+    def kronselect_dot(self, mats, input_offset: int = 0, output_offset: int = 0) -> None:
+        if input_offset != 0 or output_offset != 0:
+            raise ValueError("offset windows are not supported; the state is sharded by its top qubits")
+        for g in decode_mats(mats, self.n):
+            s = simplify(g)
+            if s is not None:
+                self.queue.append(s)
+                self.stats["gates"] += 1
+
+    def _run_local(self, batch: List[BitGate]):
+        if not batch:
+            return
+        torch = _torch()
+        passes = plan_passes(batch, self.nl, self.amp_bytes, tile_bits=self.eng.tile_bits,
+                             min_low_bits=self.eng.min_low_bits, enable=self.fuse)
+        for p in passes:
+            if self.eng.profile is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if p.fused:
+                self.eng._launch_fused(p)
+            else:
+                self.eng._launch_single(p.gates[0])
+            if self.eng.profile is not None:
+                from .backend import kernel_label
+                e1.record()
+                self.eng.profile.append(kernel_label(p, self.nl, self.amp_bytes) + (e0, e1))
+
+    def _exchange(self, a: sp.Exchange):
+        gb = a.gpos - self.nl
+        my_g = (self.rank >> gb) & 1
+        partner = self.rank ^ (1 << gb)
+        half = 1 << (self.nl - 2) if self.nl >= 2 else 0
+        total = 1 << (self.nl - 1)
+        begin, count = (0, total - half) if my_g == 0 else (total - half, half)
+        self._sync_all()
+        _lib.check(self.L.qipb_peer_swap_bit(self.ctx, self.ptr, self.peers[partner], self.nl, self.code, a.lpos, my_g,
+                                             begin, count))
+        self._sync_all()
+        self.stats["exchanges"] += 1
+        self.stats["nvlink_bytes_out"] += self.amp_bytes * total
+
+    def _peer_gate(self, a: sp.PeerGate1):
+        gb = a.gpos - self.nl
+        my_g = (self.rank >> gb) & 1
+        partner = self.rank ^ (1 << gb)
+        cg = a.ctrl_mask >> self.nl
+        total = 1 << self.nl
+        half = total // 2
+        off, count = (0, total - half) if my_g == 0 else (total - half, half)
+        self._sync_all()
+        if (self.rank & cg) == cg:
+            _lib.check(self.L.qipb_peer_gate1(self.ctx, self.ptr, self.peers[partner], self.code, off, count,
+                                              _lib.mat_array(a.mat), my_g, a.ctrl_mask & ((1 << self.nl) - 1)))
+        self._sync_all()
+        self.stats["peer_gates"] += 1
+        self.stats["nvlink_bytes_out"] += self.amp_bytes * half
+
+    def _execute(self, actions):
+        torch = _torch()
+        batch: List[BitGate] = []
+        with torch.cuda.device(self.device):
+            self._stream()
+            for a in actions:
+                if isinstance(a, sp.Apply):
+                    bg = sp.lower_for_rank(a.gate, self.nl, self.rank)
+                    if bg is not None:
+                        batch.append(bg)
+                elif isinstance(a, sp.LocalSwap):
+                    batch.append(BitGate("swap", (a.a, a.b)))
+                else:
+                    self._run_local(batch)
+                    batch = []
+                    if isinstance(a, sp.Exchange):
+                        self._exchange(a)
+                    else:
+                        self._peer_gate(a)
+            self._run_local(batch)
+
+    def flush(self) -> None:
+        if not self.queue:
+            return
+        gates = merge_blocks(self.queue, 2) if self.fuse else list(self.queue)
+        self.queue = []
+        self._execute(sp.schedule(gates, self.layout))
+
+    def func_apply(self, reg1_indices, reg2_indices, func, input_offset: int = 0, output_offset: int = 0) -> None:
+        torch = _torch()
+        reg1 = [int(i) for i in reg1_indices]
+        reg2 = [int(i) for i in reg2_indices]
+        allq = reg1 + reg2
+        if len(set(allq)) != len(allq) or any(not (0 <= q < self.n) for q in allq):
+            raise ValueError("func_apply registers must be disjoint qubit indices in [0, n)")
+        table = tabulate(func, len(reg1))
+        self.flush()
+        # the written register must be local: swap any rank-held reg2 qubit with a free local one
+        moves = []
+        for q in reg2:
+            if self.layout.is_global(q):
+                for p in range(self.nl - 1, -1, -1):
+                    v = self.layout.qubit_at(p)
+                    if v not in reg2:
+                        moves.append(sp.Exchange(self.layout.pos[q], p))
+                        self.layout.swap_qubits(q, v)
+                        break
+                else:
+                    raise ValueError("func_apply: output register does not fit in one shard")
+        self._execute(moves)
+        x_fixed = 0
+        r1bits = []
+        for j, q in enumerate(reg1):
+            p = self.layout.pos[q]
+            if p >= self.nl:
+                r1bits.append(-1)
+                if (self.rank >> (p - self.nl)) & 1:
+                    x_fixed |= 1 << (len(reg1) - 1 - j)
+            else:
+                r1bits.append(p)
+        with torch.cuda.device(self.device):
+            self._stream()
+            dev_table = torch.from_numpy(table).to(self.device)
+            _lib.check(self.L.qipb_func_xor(self.ctx, self.ptr, self.nl, self.code, len(reg1), _lib.int_array(r1bits),
+                                            len(reg2), _lib.int_array([self.layout.pos[q] for q in reg2]),
+                                            ctypes.c_void_p(dev_table.data_ptr()), x_fixed))
+            self._keep = dev_table
+
+    # ------------------------------------------------------------------ measurement
+    def _split(self, pos_list):
+        loc = [p for p in pos_list if p < self.nl]
+        glob = [p for p in pos_list if p >= self.nl]
+        return loc, glob
+
+    def _probabilities(self, indices, order: str, filter_qubits=(), filter_value_bits=()):
+        """Histogram over `indices`; filter = (qubits, their required bit values)."""
+        torch = _torch()
+        n = self.n
+        idx = [int(i) for i in indices]
+        k = len(idx)
+        if len(set(idx)) != k or any(not (0 <= q < n) for q in idx):
+            raise ValueError("measured indices must be distinct qubit indices in [0, n)")
+        self.flush()
+        if order == "given-le":
+            qorder, outb = idx, list(range(k))
+        else:
+            qorder, outb = sorted(idx), [k - 1 - j for j in range(k)]
+        # split into local measured bits (histogrammed by the kernel) and rank-held ones (fixed per rank)
+        loc = [(self.layout.pos[q], ob) for q, ob in zip(qorder, outb) if self.layout.pos[q] < self.nl]
+        glo = [(self.layout.pos[q], ob) for q, ob in zip(qorder, outb) if self.layout.pos[q] >= self.nl]
+        fmask = fval = 0
+        active = True
+        for q, v in zip(filter_qubits, filter_value_bits):
+            p = self.layout.pos[q]
+            if p < self.nl:
+                fmask |= 1 << p
+                fval |= (v & 1) << p
+            elif ((self.rank >> (p - self.nl)) & 1) != (v & 1):
+                active = False
+        loc_sorted = sorted(loc, key=lambda t: t[1])           # keep relative output order
+        kl = len(loc_sorted)
+        with torch.cuda.device(self.device):
+            self._stream()
+            out = torch.zeros(2 ** k, dtype=torch.float64, device=self.device)
+            if active:
+                part = torch.empty(2 ** kl, dtype=torch.float64, device=self.device)
+                _lib.check(self.L.qipb_probabilities(self.ctx, self.ptr, self.nl, self.code, kl,
+                                                     _lib.int_array([p for p, _ in loc_sorted]),
+                                                     _lib.int_array(list(range(kl))), fmask, fval,
+                                                     ctypes.c_void_p(part.data_ptr())))
+                base = 0
+                for p, ob in glo:
+                    if (self.rank >> (p - self.nl)) & 1:
+                        base |= 1 << ob
+                j = np.arange(2 ** kl, dtype=np.int64)
+                tgt = np.full(2 ** kl, base, dtype=np.int64)
+                for t, (_, ob) in enumerate(loc_sorted):
+                    tgt |= ((j >> t) & 1) << ob
+                out.index_copy_(0, torch.from_numpy(tgt).to(self.device), part)
+            self.dist.all_reduce(out)
+            return out.cpu().numpy()
+
+    def total_prob(self) -> float:
+        return float(self._probabilities([], "sorted-be")[0])
+
+    def soft_measure(self, indices, measured: Optional[int] = None, input_offset: int = 0):
+        k = len(indices)
+        r = random.random()          # every rank draws the same value only if seeded identically
+        rt = _torch().tensor([r], dtype=_torch().float64, device=self.device)
+        self.dist.broadcast(rt, 0)   # rank 0's draw decides (one draw consumed per rank, like the reference)
+        r = float(rt.item())
+        if measured is not None:
+            srt = sorted(int(i) for i in indices)
+            bits = [(int(measured) >> (k - 1 - j)) & 1 for j in range(k)]
+            p = float(self._probabilities([], "sorted-be", srt, bits)[0])
+            return int(measured), p
+        return scan_outcome(self._probabilities(indices, "sorted-be"), r)
+
+    def measure(self, indices, measured: Optional[int] = None, measured_prob: Optional[float] = None,
+                input_offset: int = 0, output_offset: int = 0):
+        torch = _torch()
+        k = len(indices)
+        _check_measure_args(k, measured, measured_prob)
+        if measured is None or measured_prob is None:
+            m, p = self.soft_measure(indices, measured=measured)
+        else:
+            m, p = int(measured), float(measured_prob)
+        self.flush()
+        srt = sorted(int(i) for i in indices)
+        mask = want = 0
+        alive = True
+        for j, q in enumerate(srt):
+            v = (m >> (k - 1 - j)) & 1
+            pos = self.layout.pos[q]
+            if pos < self.nl:
+                mask |= 1 << pos
+                want |= v << pos
+            elif ((self.rank >> (pos - self.nl)) & 1) != v:
+                alive = False
+        with torch.cuda.device(self.device):
+            self._stream()
+            if alive:
+                _lib.check(self.L.qipb_collapse(self.ctx, self.ptr, self.nl, self.code, mask, want, math.sqrt(1.0 / p)))
+            else:
+                _lib.check(self.L.qipb_init_basis(self.ctx, self.ptr, self.nl, self.code, -1))
+        return m, p
+
+    def reduce_measure(self, *a, **k):
+        raise NotImplementedError("reduce_measure on a sharded state is not implemented yet (DESIGN.md, gaps)")
+
+    def measure_probabilities(self, indices, top_k: int = 0):
+        if top_k:
+            return top_probabilities(self._probabilities(indices, "sorted-be"), top_k)
+        return self._probabilities(indices, "given-le")
+
+    # ------------------------------------------------------------------ state access
+    def get_state(self):
+        """Canonical-order host copy of the WHOLE state on every rank (small n only)."""
+        torch = _torch()
+        self.flush()
+        if self.n > 30:
+            raise ValueError("get_state() of a sharded state is limited to 30 qubits; use measure_probabilities")
+        self._execute(sp.canonicalise(self.layout))
+        parts = [torch.empty(1 << self.nl, dtype=self.eng.tdtype, device=self.device) for _ in range(self.P)]
+        self.dist.all_gather(parts, self.eng.state)
+        return torch.cat(parts).cpu().numpy()
+
+    def get_state_size(self) -> int:
+        return 2 ** self.n
+
+    def synchronize(self):
+        self.flush()
+        _torch().cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        if getattr(self, "ptr", None) is None:
+            return
+        torch = _torch()
+        torch.cuda.synchronize()
+        self._sync_all()
+        torch.cuda.synchronize()
+        for pp in self.peers.values():
+            self.L.qipb_ipc_close(self.ctx, pp)
+        self.peers = {}
+        self.dist.barrier()
+        self.eng.state = None
+        self.L.qipb_dev_free(self.ctx, self.ptr)
+        self.ptr = None
+        self.eng.close()

@@ -1,0 +1,150 @@
+"""CPU tier: the multi-GPU path's host logic (qip_b200/shardplan.py).
+
+  * virtual shards: P = 2, 4, 8 logical shards in one process, executed with numpy, against the
+    single-shard result and the oracle -- every action kind (rank-resolved controls and diagonals,
+    relabelled swaps, fused peer gates, bit exchanges, canonicalisation);
+  * world_size-2 gloo run: two processes, one shard each, exchanging over torch.distributed.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import bitsim
+import shardsim
+from oracle import oracle as orc
+from qip_b200 import ops
+from qip_b200 import shardplan as sp
+from qip_b200.circuits import H2, X2, haar_unitary, layered_stream, qfft_stream, rm_mat
+from qip_b200.mats import CMat, SwapMat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def logical_gates(stream, n, merge=0):
+    gates = []
+    for mats in stream:
+        for g in ops.decode_mats(mats, n):
+            s = ops.simplify(g)
+            if s is not None:
+                gates.append(s)
+    return ops.merge_blocks(gates, merge) if merge else gates
+
+
+def run_sharded(psi, gates, n, gbits):
+    lay = sp.Layout(n, gbits)
+    actions = sp.schedule(gates, lay)
+    vs = shardsim.VirtualShards(psi, gbits)
+    vs.run(actions)
+    vs.run(sp.canonicalise(lay))
+    assert lay.canonical()
+    return vs, actions
+
+
+def reference_state(psi, gates, n):
+    st = psi.copy()
+    for g in gates:
+        st = bitsim.apply_bitgate(st, ops.lower(g, n), n)
+    return st
+
+
+@pytest.mark.parametrize("gbits", [1, 2, 3])
+@pytest.mark.parametrize("seed", range(4))
+def test_layered_circuit_on_virtual_shards(gbits, seed):
+    n = 9
+    rng = np.random.default_rng(seed)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    gates = logical_gates(layered_stream(n, 3, seed), n)
+    vs, actions = run_sharded(psi, gates, n, gbits)
+    assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-13
+    if gbits >= 2:
+        assert any(isinstance(a, (sp.Exchange, sp.PeerGate1)) for a in actions)
+
+
+@pytest.mark.parametrize("gbits", [1, 2, 3])
+def test_qft_on_virtual_shards_needs_few_exchanges(gbits):
+    n = 10
+    rng = np.random.default_rng(gbits)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    gates = logical_gates(qfft_stream(n), n)
+    lay = sp.Layout(n, gbits)
+    actions = sp.schedule(gates, lay)
+    moves = [a for a in actions if isinstance(a, (sp.Exchange, sp.PeerGate1))]
+    # only the H gates on the gbits rank qubits move data; every C-phase is communication-free and
+    # the final bit reversal is a relabel
+    assert len(moves) == gbits and all(isinstance(a, sp.PeerGate1) for a in moves)
+    vs = shardsim.VirtualShards(psi, gbits)
+    vs.run(actions)
+    vs.run(sp.canonicalise(lay))
+    want = np.fft.ifft(psi) * np.sqrt(2 ** n)
+    assert float(np.max(np.abs(vs.gather() - want))) <= 1e-12
+
+
+def test_rank_resolved_controls_diagonals_and_relabels_need_no_exchange():
+    n, gbits = 8, 2
+    rng = np.random.default_rng(0)
+    stream = [{(0, 5): CMat(X2)},                      # control on a rank qubit, local target
+              {(1, 0, 6): CMat(CMat(haar_unitary(rng, 2)))},
+              {0: rm_mat(3)}, {(1, 0): CMat(rm_mat(2))},        # diagonal on rank qubits
+              {(0, 4): np.diag(np.exp(1j * rng.normal(size=4)))},
+              {(0, 7): SwapMat(1)}, {(1, 2): SwapMat(1)}]        # swaps with rank qubits: relabels
+    gates = logical_gates(stream, n)
+    lay = sp.Layout(n, gbits)
+    actions = sp.schedule(gates, lay)
+    assert not any(isinstance(a, (sp.Exchange, sp.PeerGate1)) for a in actions)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    vs = shardsim.VirtualShards(psi, gbits)
+    vs.run(actions)
+    fix = sp.canonicalise(lay)
+    assert any(isinstance(a, sp.Exchange) for a in fix)          # the relabels are paid for at read-out only
+    vs.run(fix)
+    assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-13
+
+
+def test_lower_for_rank_skips_and_selects():
+    nl = 4
+    pg = sp.PhysGate((1,), (1 << 5) | (1 << 2), X2.astype(np.complex128), False)
+    assert sp.lower_for_rank(pg, nl, 0b01) is None                      # rank bit 5-4=1 is 0 on rank 1
+    bg = sp.lower_for_rank(pg, nl, 0b10)
+    assert bg.bits == (1,) and bg.ctrl_mask == (1 << 2)
+    d = np.diag([1, 2, 3, 4]).astype(np.complex128)
+    pg = sp.PhysGate((4, 0), 0, d, True)                                 # MSB target is rank bit 0
+    assert np.array_equal(np.diag(sp.lower_for_rank(pg, nl, 0).mat), [1, 2])
+    assert np.array_equal(np.diag(sp.lower_for_rank(pg, nl, 1).mat), [3, 4])
+    pg = sp.PhysGate((5,), 0, np.diag([1, 1j]).astype(np.complex128), True)
+    assert sp.lower_for_rank(pg, nl, 0) is None and sp.lower_for_rank(pg, nl, 2).mat[0, 0] == 1j
+    with pytest.raises(ValueError):
+        sp.lower_for_rank(sp.PhysGate((5,), 0, H2.astype(np.complex128), False), nl, 0)
+
+
+def test_merged_blocks_schedule_on_shards():
+    n, gbits = 9, 2
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    gates = logical_gates(layered_stream(n, 2, 11), n)
+    merged = ops.merge_blocks(gates, 4)
+    vs, _ = run_sharded(psi, merged, n, gbits)
+    assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-12
+
+
+def test_two_process_gloo_shards_match_oracle(tmp_path):
+    """world_size 2, gloo backend, one shard per process (tests/gloo_worker.py)."""
+    out = tmp_path / "res.npy"
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "gloo_worker.py"), str(out)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = np.load(out)
+    n = 8
+    rng = np.random.default_rng(42)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+    for mats in list(layered_stream(n, 2, 7)) + list(qfft_stream(n)):
+        c.kronselect_dot(mats)
+    assert float(np.max(np.abs(got - c.get_state()))) <= 1e-12
