@@ -178,55 +178,97 @@ def _apply_to_block(block_mat, block_qubits, u, u_qubits):
     return np.ascontiguousarray(r.reshape(1 << m, 1 << m))
 
 
-def merge_blocks(gates: Sequence[Gate], max_k: int = 4) -> List[Gate]:
-    """Order-preserving greedy merge of consecutive small gates into dense blocks on at most max_k
-    qubits by multiplying their matrices on the host (changes rounding at the 1e-16 level only).
-    A gate may slide back over blocks it shares no qubit with.  Every block is re-simplified, so a
-    block made only of controlled / diagonal gates keeps its cheap form."""
-    blocks: List[Optional[list]] = []          # [qubits(list), matrix] or [None, Gate] for opaque gates
-    last = {}                                   # qubit -> index of the last block that touches it
+def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True) -> List[Gate]:
+    """Order-preserving merge of small gates into dense blocks on at most max_k qubits by multiplying
+    their matrices on the host (changes rounding at the 1e-16 level only).  Three passes:
+      1. backward: a gate joins the latest earlier block it shares a qubit with (it may slide back
+         over blocks it shares no qubit with) when the union still fits;
+      2. forward: a block joins the NEXT block it shares a qubit with when the union fits (nothing in
+         between touches its qubits, so it may slide forward);
+      3. pack: blocks on disjoint qubits are tensored together while nothing between them touches
+         the later one's qubits.
+    Every block is re-simplified, so a block made only of controlled / diagonal gates keeps its
+    cheap form.  Gates wider than max_k stay as they are."""
+    # a block is [qubit list, matrix]; an opaque (too wide) gate is [qubit list, None, gate]
+    blocks: List[list] = []
+    last = {}
     for g in gates:
-        qs, u = gate_unitary(g) if len(g.qubits()) <= max_k else (list(g.qubits()), None)
-        b = max([last.get(q, -1) for q in qs] + [-1])
-        if u is None:
-            blocks.append([None, g])
-            for q in qs:
+        if len(g.qubits()) > max_k:
+            blocks.append([list(g.qubits()), None, g])
+            for q in g.qubits():
                 last[q] = len(blocks) - 1
             continue
-        target = None
-        if b >= 0 and blocks[b][0] is not None and len(set(blocks[b][0]) | set(qs)) <= max_k:
+        qs, u = gate_unitary(g)
+        b = max([last.get(q, -1) for q in qs] + [-1])
+        if b >= 0 and blocks[b][1] is not None and len(set(blocks[b][0]) | set(qs)) <= max_k:
+            _absorb(blocks[b], qs, u)
             target = b
         else:
-            # pack with a later block on disjoint qubits (tensor product), smallest result first
-            best = None
-            for j in range(b + 1, len(blocks)):
-                if blocks[j][0] is None:
-                    continue
-                size = len(set(blocks[j][0]) | set(qs))
-                if size <= max_k and (best is None or size < best[0]):
-                    best = (size, j)
-            if best is not None:
-                target = best[1]
-        if target is None:
             blocks.append([list(qs), u])
             target = len(blocks) - 1
-        else:
-            bq, bm = blocks[target]
-            new_q = bq + [q for q in qs if q not in bq]
-            if len(new_q) != len(bq):
-                bm = _apply_to_block(np.eye(1 << len(new_q), dtype=np.complex128), new_q, bm, bq)
-            blocks[target] = [new_q, _apply_to_block(bm, new_q, u, qs)]
         for q in qs:
-            last[q] = max(last.get(q, -1), target)
-    out: List[Gate] = []
-    for bq, bm in blocks:
-        if bq is None:
-            out.append(bm)
+            last[q] = target
+
+    # pass 2: forward merges
+    alive = [True] * len(blocks)
+    for i in range(len(blocks)):
+        if blocks[i][1] is None:
             continue
-        s = simplify(Gate("matrix", tuple(bq), (), bm))
+        qi = set(blocks[i][0])
+        for j in range(i + 1, len(blocks)):
+            if not alive[j]:
+                continue
+            qj = set(blocks[j][0])
+            if qi & qj:
+                if blocks[j][1] is not None and len(qi | qj) <= max_k:
+                    # i's content runs first, then j's: rebuild j as (j's matrix) . (i's matrix)
+                    merged = [list(blocks[i][0]), blocks[i][1]]
+                    _absorb(merged, blocks[j][0], blocks[j][1])
+                    blocks[j] = merged
+                    alive[i] = False
+                break
+    blocks = [b for b, a in zip(blocks, alive) if a]
+
+    # pass 3: pack disjoint blocks
+    if pack:
+        alive = [True] * len(blocks)
+        for i in range(len(blocks)):
+            if not alive[i] or blocks[i][1] is None:
+                continue
+            touched = set()
+            for j in range(i + 1, len(blocks)):
+                if len(blocks[i][0]) >= max_k:
+                    break
+                if not alive[j]:
+                    continue
+                qj = set(blocks[j][0])
+                if blocks[j][1] is not None and not (qj & touched) and not (qj & set(blocks[i][0])) \
+                        and len(blocks[i][0]) + len(qj) <= max_k:
+                    _absorb(blocks[i], blocks[j][0], blocks[j][1])
+                    alive[j] = False
+                else:
+                    touched |= qj
+        blocks = [b for b, a in zip(blocks, alive) if a]
+
+    out: List[Gate] = []
+    for b in blocks:
+        if b[1] is None:
+            out.append(b[2])
+            continue
+        s = simplify(Gate("matrix", tuple(b[0]), (), b[1]))
         if s is not None:
             out.append(s)
     return out
+
+
+def _absorb(block, qs, u):
+    """block <- (u on qs) . block, growing the block's qubit list if needed."""
+    bq, bm = block[0], block[1]
+    new_q = bq + [q for q in qs if q not in bq]
+    if len(new_q) != len(bq):
+        bm = _apply_to_block(np.eye(1 << len(new_q), dtype=np.complex128), new_q, bm, bq)
+    block[0] = new_q
+    block[1] = _apply_to_block(bm, new_q, u, qs)
 
 
 # --------------------------------------------------------------------------------- bit-level form
