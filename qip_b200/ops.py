@@ -297,6 +297,21 @@ def lower(g: Gate, n: int) -> BitGate:
     return BitGate(g.kind, bits, cm, g.mat, g.diagonal)
 
 
+def merge_bitgates(gates: Sequence["BitGate"], max_k: int = 2) -> List["BitGate"]:
+    """merge_blocks on gates that are already lowered to index bits (bit positions act as labels)."""
+    logical = []
+    for g in gates:
+        ctrl = tuple(b for b in range(64) if (g.ctrl_mask >> b) & 1)
+        logical.append(Gate(g.kind, tuple(g.bits), ctrl, g.mat, g.diagonal))
+    out = []
+    for g in merge_blocks(logical, max_k):
+        cm = 0
+        for b in g.controls:
+            cm |= 1 << b
+        out.append(BitGate(g.kind, tuple(g.targets), cm, g.mat, g.diagonal))
+    return out
+
+
 # --------------------------------------------------------------------------------- fusion planner
 @dataclass
 class Pass:

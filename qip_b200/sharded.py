@@ -22,7 +22,7 @@ import numpy as np
 from . import lib as _lib
 from . import shardplan as sp
 from .backend import (B200Backend, _check_measure_args, scan_outcome, tabulate, top_probabilities)
-from .ops import BitGate, Gate, Pass, decode_mats, merge_blocks, plan_passes, simplify
+from .ops import BitGate, Gate, Pass, decode_mats, merge_bitgates, plan_passes, simplify
 
 
 def _torch():
@@ -153,6 +153,8 @@ class ShardedB200Backend(object):
         if not batch:
             return
         torch = _torch()
+        if self.fuse:
+            batch = merge_bitgates(batch, 2)       # rank-local: every rank merges its own resolved list
         passes = plan_passes(batch, self.nl, self.amp_bytes, tile_bits=self.eng.tile_bits,
                              min_low_bits=self.eng.min_low_bits, enable=self.fuse)
         for p in passes:
@@ -222,7 +224,7 @@ class ShardedB200Backend(object):
     def flush(self) -> None:
         if not self.queue:
             return
-        gates = merge_blocks(self.queue, 2) if self.fuse else list(self.queue)
+        gates = list(self.queue)
         self.queue = []
         self._execute(sp.schedule(gates, self.layout))
 
