@@ -24,21 +24,26 @@ struct DevGate {
     unsigned char k;        // target bits in total (0..2)
     unsigned char kin;      // how many of them are tile bits
     unsigned char diag;
-    unsigned char nins;     // fixed tile-local positions (in-tile targets + in-tile controls)
+    unsigned char nins;     // fixed tile-local positions (dense: in-tile targets + controls; diagonal: controls below sb)
     unsigned char tl[2];    // target j (matrix order, 0 = MSB): tile-local position, 0xFF if outside
     unsigned char tg[2];    // target j: position in the state index
-    u32 nmask[FUSED_MAX_INS];   // ~((1 << p) - 1) for the fixed positions p, ascending
-    u32 in_or;              // tile-local mask of in-tile control bits
-    u32 pad;
+    unsigned char ins[FUSED_MAX_INS];   // the fixed positions, ascending
+    u32 in_or;              // tile-local mask of in-tile control bits (diagonal gates: those below the warp-slice bits)
+    u32 hi_need;            // diagonal gates: control bits at or above the warp-slice bits, as a mask over the warp id
+    u32 coef;               // offset of this gate's coefficients in FusedArgs::pool
     u64 out_ctrl;           // state-index mask of controls outside the tile
-    double2 m[16];
 };
+
+#define FUSED_MAX_GATES 400
+#define FUSED_POOL 800      // complex coefficients: dense 2q = 16, dense 1q = 4, diagonal k = 2^k
 
 struct FusedArgs {
     int nbits, tb, ngates, lowrun;      // lowrun = number of contiguous low tile bits (0..L-1)
+    int sb, wb;                         // diagonal runs: a warp owns 2^sb consecutive tile elements, 2^wb warps work
     u64 ntiles;
     unsigned char tbit[16];             // tile-local bit -> state bit, ascending
-    DevGate g[QIPB_MAX_FUSED_GATES];
+    DevGate g[FUSED_MAX_GATES];
+    double2 pool[FUSED_POOL];
 };
 static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel parameter space");
 
@@ -72,73 +77,80 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-__device__ __forceinline__ u32 expand_local(u32 w, const DevGate &g) {
-    for (int q = 0; q < g.nins; ++q) w += (w & g.nmask[q]);      // insert a zero bit at each fixed position
-    return w | g.in_or;
+// Pin a coefficient in a register: the value comes out of an asm volatile, so ptxas cannot
+// re-materialise it with another constant-bank load inside the inner loop.
+__device__ __forceinline__ double2 pin(const double2 v) {
+    double2 r;
+    asm volatile("mov.f64 %0, %2;\n\tmov.f64 %1, %3;" : "=d"(r.x), "=d"(r.y) : "d"(v.x), "d"(v.y));
+    return r;
+}
+// Same with the first four masks pre-loaded into registers (identity masks = 0 beyond nins).
+struct LocalIns { u32 m0, m1, m2, m3, orv; int more; };
+__device__ __forceinline__ LocalIns load_ins(const DevGate &g) {
+    LocalIns l;
+    l.m0 = g.nins > 0 ? ~((1u << g.ins[0]) - 1u) : 0u;     // w += w & mask inserts a zero bit at that position
+    l.m1 = g.nins > 1 ? ~((1u << g.ins[1]) - 1u) : 0u;
+    l.m2 = g.nins > 2 ? ~((1u << g.ins[2]) - 1u) : 0u;
+    l.m3 = g.nins > 3 ? ~((1u << g.ins[3]) - 1u) : 0u;
+    l.orv = g.in_or;
+    l.more = g.nins > 4;
+    return l;
+}
+__device__ __forceinline__ u32 expand_fast(u32 w, const LocalIns &l, const DevGate &g) {
+    w += (w & l.m0);
+    w += (w & l.m1);
+    w += (w & l.m2);
+    w += (w & l.m3);
+    if (l.more)
+        for (int q = 4; q < g.nins; ++q) w += (w & ~((1u << g.ins[q]) - 1u));
+    return w | l.orv;
 }
 
 template <typename A>
-__device__ __forceinline__ void run_gate(A *tile, const DevGate &g, u64 base, u32 tsize, int tid) {
+__device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double2 *M, u64 base, u32 tsize, int tid) {
     if ((base & g.out_ctrl) != g.out_ctrl) return;             // uniform per tile
     const u32 ngroups = tsize >> g.nins;
+    const LocalIns li = load_ins(g);
     if (g.diag) {
-        // effective diagonal over the in-tile targets; targets outside the tile are fixed by `base`
-        u32 sel_out = 0;
-        for (int j = 0; j < g.k; ++j)
-            if (g.tl[j] == 0xFF) sel_out |= (u32)((base >> g.tg[j]) & 1ull) << (g.k - 1 - j);
-        const int D = 1 << g.k;
-        if (g.kin == 0) {
-            const double2 d = g.m[sel_out * D + sel_out];
-            if (d.x == 1.0 && d.y == 0.0) return;
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g);
-                tile[e] = cmul<A>(d, tile[e]);
-            }
-        } else if (g.kin == 1) {
-            const int j = (g.tl[0] != 0xFF) ? 0 : 1;
-            const u32 o1 = 1u << g.tl[j];
-            const u32 s1 = 1u << (g.k - 1 - j);
-            const double2 d0 = g.m[sel_out * D + sel_out], d1 = g.m[(sel_out | s1) * D + (sel_out | s1)];
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g);
-                tile[e] = cmul<A>(d0, tile[e]);
-                tile[e | o1] = cmul<A>(d1, tile[e | o1]);
-            }
-        } else {
-            const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g);
-                tile[e] = cmul<A>(g.m[0], tile[e]);
-                tile[e | ol] = cmul<A>(g.m[5], tile[e | ol]);
-                tile[e | oh] = cmul<A>(g.m[10], tile[e | oh]);
-                tile[e | oh | ol] = cmul<A>(g.m[15], tile[e | oh | ol]);
-            }
-        }
+        return;   // diagonal gates run warp-sliced (run_diag)
     } else if (g.k == 1) {
         const u32 o1 = 1u << g.tl[0];
-        for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-            const u32 e = expand_local(w, g);
-            const A a0 = tile[e], a1 = tile[e | o1];
-            A r0 = cmul<A>(g.m[0], a0);
-            cfma<A>(r0, g.m[1], a1);
-            A r1 = cmul<A>(g.m[2], a0);
-            cfma<A>(r1, g.m[3], a1);
+        // coefficients hoisted into registers once per gate (the gate index is dynamic, so reading
+        // g.m inside the loop would be an LDC per use and every DFMA would wait on it)
+        const double2 m0 = pin(M[0]), m1 = pin(M[1]), m2 = pin(M[2]), m3 = pin(M[3]);
+        for (u32 w = tid; w < ngroups; w += 2 * FUSED_THREADS) {
+            const u32 w2 = w + FUSED_THREADS;
+            const bool two = w2 < ngroups;
+            const u32 e = expand_fast(w, li, g), e2 = expand_fast(two ? w2 : w, li, g);
+            const A a0 = tile[e], a1 = tile[e | o1], b0 = tile[e2], b1 = tile[e2 | o1];
+            A r0 = cmul<A>(m0, a0), r1 = cmul<A>(m2, a0), s0 = cmul<A>(m0, b0), s1 = cmul<A>(m2, b0);
+            cfma<A>(r0, m1, a1);
+            cfma<A>(r1, m3, a1);
+            cfma<A>(s0, m1, b1);
+            cfma<A>(s1, m3, b1);
             tile[e] = r0;
             tile[e | o1] = r1;
+            if (two) {
+                tile[e2] = s0;
+                tile[e2 | o1] = s1;
+            }
         }
     } else {   // dense k == 2
         const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
+        double2 m[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m[i] = pin(M[i]);
         for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-            const u32 e = expand_local(w, g);
+            const u32 e = expand_fast(w, li, g);
             const u32 idx[4] = {e, e | ol, e | oh, e | oh | ol};
             A a[4], r[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) a[j] = tile[idx[j]];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                r[i] = cmul<A>(g.m[i * 4], a[0]);
+                r[i] = cmul<A>(m[i * 4], a[0]);
 #pragma unroll
-                for (int j = 1; j < 4; ++j) cfma<A>(r[i], g.m[i * 4 + j], a[j]);
+                for (int j = 1; j < 4; ++j) cfma<A>(r[i], m[i * 4 + j], a[j]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) tile[idx[i]] = r[i];
@@ -146,10 +158,57 @@ __device__ __forceinline__ void run_gate(A *tile, const DevGate &g, u64 base, u3
     }
 }
 
+// Diagonal / phase gate, warp-sliced: warp `wid` owns tile elements [wid << sb, (wid+1) << sb), so a
+// run of consecutive diagonal gates needs only __syncwarp() between gates -- every element is always
+// touched by the same warp.  Elements satisfying the in-tile controls are enumerated (control bits
+// inserted as ones); the diagonal entry is selected per element from the target bits (bits outside
+// the tile are constant per tile and come from `base`).
+template <typename A>
+__device__ __forceinline__ void run_diag(A *tile, const DevGate &g, const double2 *M, u64 base, int sb, int wb, int wid, int lane) {
+    if ((base & g.out_ctrl) != g.out_ctrl) return;             // uniform per tile
+    if (wid >= (1 << wb) || ((u32)wid & g.hi_need) != g.hi_need) return;   // uniform per warp
+    const LocalIns li = load_ins(g);
+    const u32 n = (1u << sb) >> g.nins;
+    const u32 wbase = (u32)wid << sb;
+    u32 sel_out = 0;
+    for (int j = 0; j < g.k; ++j)
+        if (g.tl[j] == 0xFF) sel_out |= (u32)((base >> g.tg[j]) & 1ull) << (g.k - 1 - j);
+    if (g.kin == 0) {
+        const double2 d = pin(M[sel_out]);
+        if (d.x == 1.0 && d.y == 0.0) return;
+        for (u32 x = lane; x < n; x += 32) {
+            const u32 e = wbase | expand_fast(x, li, g);
+            tile[e] = cmul<A>(d, tile[e]);
+        }
+    } else if (g.kin == 1) {
+        const int j = (g.tl[0] != 0xFF) ? 0 : 1;
+        const int tb1 = g.tl[j];
+        const u32 s1 = 1u << (g.k - 1 - j);
+        const double2 d0 = pin(M[sel_out]), d1 = pin(M[sel_out | s1]);
+        for (u32 x = lane; x < n; x += 32) {
+            const u32 e = wbase | expand_fast(x, li, g);
+            const bool hi = (e >> tb1) & 1u;
+            const double2 d = make_double2(hi ? d1.x : d0.x, hi ? d1.y : d0.y);
+            tile[e] = cmul<A>(d, tile[e]);
+        }
+    } else {
+        const int t0 = g.tl[0], t1 = g.tl[1];
+        const double2 q0 = pin(M[0]), q1 = pin(M[1]), q2 = pin(M[2]), q3 = pin(M[3]);
+        for (u32 x = lane; x < n; x += 32) {
+            const u32 e = wbase | expand_fast(x, li, g);
+            const bool b1 = (e >> t0) & 1u, b0 = (e >> t1) & 1u;
+            const double2 lo = make_double2(b0 ? q1.x : q0.x, b0 ? q1.y : q0.y);
+            const double2 hi = make_double2(b0 ? q3.x : q2.x, b0 ? q3.y : q2.y);
+            const double2 d = make_double2(b1 ? hi.x : lo.x, b1 ? hi.y : lo.y);
+            tile[e] = cmul<A>(d, tile[e]);
+        }
+    }
+}
+
 // BULK: tile staging with cp.async.bulk (TMA 1-D bulk copies, one per contiguous run, completion on
 // an mbarrier) instead of LDG/STS through registers.  Requires runs of >= 16 bytes.
 template <typename A, bool BULK>
-__global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+__global__ void __launch_bounds__(FUSED_THREADS, 2) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     A *tile = reinterpret_cast<A *>(smem_raw);
@@ -195,10 +254,21 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(A *__restrict__ st
         }
 
         // ---- run the gate list on the tile ----
+        bool prev_diag = false;
         for (int gi = 0; gi < f.ngates; ++gi) {
-            run_gate<A>(tile, f.g[gi], base, tsize, tid);
-            __syncthreads();
+            const DevGate &g = f.g[gi];
+            if (g.diag) {
+                run_diag<A>(tile, g, f.pool + g.coef, base, f.sb, f.wb, tid >> 5, tid & 31);
+                __syncwarp();
+                prev_diag = true;
+            } else {
+                if (prev_diag) __syncthreads();
+                run_gate<A>(tile, g, f.pool + g.coef, base, tsize, tid);
+                __syncthreads();
+                prev_diag = false;
+            }
         }
+        if (prev_diag) __syncthreads();
 
         // ---- write the tile back ----
         if (BULK) {
@@ -254,10 +324,11 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     QIPB_REQUIRE(ctx && state && gates && tile_bits, "null argument");
     QIPB_REQUIRE(nbits >= 0 && nbits <= 40, "nbits %d unsupported", nbits);
     QIPB_REQUIRE(ntile_bits >= 0 && ntile_bits <= QIPB_MAX_TILE_BITS && ntile_bits <= nbits, "tile bits %d unsupported", ntile_bits);
-    QIPB_REQUIRE(ngates >= 1 && ngates <= QIPB_MAX_FUSED_GATES, "ngates %d unsupported (1..%d)", ngates, QIPB_MAX_FUSED_GATES);
+    QIPB_REQUIRE(ngates >= 1 && ngates <= FUSED_MAX_GATES, "ngates %d unsupported (1..%d)", ngates, FUSED_MAX_GATES);
     QIPB_CUDA(cudaSetDevice(ctx->device));
-    static thread_local FusedArgs f;    // ~29 KiB: keep it off the stack
+    static thread_local FusedArgs f;    // ~30 KiB: keep it off the stack
     memset(&f, 0, sizeof(f));
+    u32 pool_used = 0;
     f.nbits = nbits;
     f.tb = ntile_bits;
     f.ngates = ngates;
@@ -274,6 +345,8 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     }
     f.lowrun = 0;
     while (f.lowrun < ntile_bits && tile_bits[f.lowrun] == f.lowrun) f.lowrun++;
+    f.wb = ntile_bits - 5 < 0 ? 0 : (ntile_bits - 5 > 3 ? 3 : ntile_bits - 5);   // 2^wb of the 8 warps, >= 32 elements each
+    f.sb = ntile_bits - f.wb;
     for (int gi = 0; gi < ngates; ++gi) {
         const qipb_gate &s = gates[gi];
         DevGate &d = f.g[gi];
@@ -300,16 +373,30 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
         QIPB_REQUIRE(nbits == 64 || (s.ctrl_mask >> nbits) == 0, "fused gate %d: control outside local bits", gi);
         d.out_ctrl = s.ctrl_mask & ~tmask;
         d.in_or = 0;
+        d.hi_need = 0;
+        if (d.diag) fixed_local = 0;      // diagonal gates enumerate elements: only controls are fixed
         for (int b = 0; b < nbits; ++b)
             if (((s.ctrl_mask & tmask) >> b) & 1ull) {
-                d.in_or |= 1u << local_of[b];
-                fixed_local |= 1ull << local_of[b];
+                const int lb = local_of[b];
+                if (d.diag && lb >= f.sb) {
+                    d.hi_need |= 1u << (lb - f.sb);
+                } else {
+                    d.in_or |= 1u << lb;
+                    fixed_local |= 1ull << lb;
+                }
             }
         d.nins = 0;
         for (int j = 0; j < ntile_bits; ++j)
-            if ((fixed_local >> j) & 1ull) d.nmask[d.nins++] = ~((1u << j) - 1u);
+            if ((fixed_local >> j) & 1ull) d.ins[d.nins++] = (unsigned char)j;
         const int D = 1 << s.k;
-        for (int e = 0; e < D * D; ++e) d.m[e] = make_double2(s.mat[2 * e], s.mat[2 * e + 1]);
+        const int ncoef = d.diag ? D : D * D;
+        QIPB_REQUIRE(pool_used + ncoef <= FUSED_POOL, "fused pass needs more than %d matrix coefficients", FUSED_POOL);
+        d.coef = pool_used;
+        for (int e = 0; e < ncoef; ++e) {
+            const int src = d.diag ? e * D + e : e;
+            f.pool[pool_used + e] = make_double2(s.mat[2 * src], s.mat[2 * src + 1]);
+        }
+        pool_used += ncoef;
     }
     if (dtype == QIPB_C128) return launch_fused<double2>(ctx, (double2 *)state, f);
     if (dtype == QIPB_C64) return launch_fused<float2>(ctx, (float2 *)state, f);

@@ -178,7 +178,21 @@ def _apply_to_block(block_mat, block_qubits, u, u_qubits):
     return np.ascontiguousarray(r.reshape(1 << m, 1 << m))
 
 
-def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True) -> List[Gate]:
+def tile_cost(g: Optional[Gate]) -> float:
+    """Relative cost of a gate inside a fused tile pass (FP64 work + shared-memory traffic per
+    amplitude of the state, in units of one complex multiply): used to refuse merges that would turn
+    cheap controlled / diagonal gates into a more expensive dense block (e.g. H followed by a C-phase)."""
+    if g is None:
+        return 0.0
+    frac = 2.0 ** (-len(g.controls))
+    if g.kind == "swap":
+        return 0.5 * frac
+    if g.diagonal or g.k == 0:
+        return 2.0 * frac
+    return (2.0 ** g.k + 1.0) * frac
+
+
+def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True, cost_aware: bool = False) -> List[Gate]:
     """Order-preserving merge of small gates into dense blocks on at most max_k qubits by multiplying
     their matrices on the host (changes rounding at the 1e-16 level only).  Three passes:
       1. backward: a gate joins the latest earlier block it shares a qubit with (it may slide back
@@ -192,6 +206,18 @@ def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True) -> Li
     # a block is [qubit list, matrix]; an opaque (too wide) gate is [qubit list, None, gate]
     blocks: List[list] = []
     last = {}
+
+    def cost_of(bq, bm):
+        return tile_cost(simplify(Gate("matrix", tuple(bq), (), bm)))
+
+    def worth(block, qs, u, first=None):
+        """Would (u on qs) . block [or block . first] be cheaper than running the two apart?"""
+        if not cost_aware:
+            return True
+        trial = [list(block[0]), block[1]]
+        _absorb(trial, qs, u)
+        return cost_of(trial[0], trial[1]) <= cost_of(block[0], block[1]) + cost_of(list(qs), u) + 1.0
+
     for g in gates:
         if len(g.qubits()) > max_k:
             blocks.append([list(g.qubits()), None, g])
@@ -200,7 +226,8 @@ def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True) -> Li
             continue
         qs, u = gate_unitary(g)
         b = max([last.get(q, -1) for q in qs] + [-1])
-        if b >= 0 and blocks[b][1] is not None and len(set(blocks[b][0]) | set(qs)) <= max_k:
+        if b >= 0 and blocks[b][1] is not None and len(set(blocks[b][0]) | set(qs)) <= max_k \
+                and worth(blocks[b], qs, u):
             _absorb(blocks[b], qs, u)
             target = b
         else:
@@ -220,7 +247,7 @@ def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True) -> Li
                 continue
             qj = set(blocks[j][0])
             if qi & qj:
-                if blocks[j][1] is not None and len(qi | qj) <= max_k:
+                if blocks[j][1] is not None and len(qi | qj) <= max_k and worth(blocks[i], blocks[j][0], blocks[j][1]):
                     # i's content runs first, then j's: rebuild j as (j's matrix) . (i's matrix)
                     merged = [list(blocks[i][0]), blocks[i][1]]
                     _absorb(merged, blocks[j][0], blocks[j][1])
@@ -243,7 +270,7 @@ def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True) -> Li
                     continue
                 qj = set(blocks[j][0])
                 if blocks[j][1] is not None and not (qj & touched) and not (qj & set(blocks[i][0])) \
-                        and len(blocks[i][0]) + len(qj) <= max_k:
+                        and len(blocks[i][0]) + len(qj) <= max_k and not cost_aware:
                     _absorb(blocks[i], blocks[j][0], blocks[j][1])
                     alive[j] = False
                 else:
@@ -304,7 +331,7 @@ def merge_bitgates(gates: Sequence["BitGate"], max_k: int = 2) -> List["BitGate"
         ctrl = tuple(b for b in range(64) if (g.ctrl_mask >> b) & 1)
         logical.append(Gate(g.kind, tuple(g.bits), ctrl, g.mat, g.diagonal))
     out = []
-    for g in merge_blocks(logical, max_k):
+    for g in merge_blocks(logical, max_k, cost_aware=True):
         cm = 0
         for b in g.controls:
             cm |= 1 << b
@@ -354,8 +381,14 @@ def choose_tile(required, nbits: int, tile_bits: int):
     return tuple(sorted(tile))
 
 
+def _ncoef(g: BitGate) -> int:
+    if g.kind == "swap":
+        return 16
+    return (1 << g.k) if (g.diagonal or g.k == 0) else (1 << g.k) ** 2
+
+
 def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_bits: int = 12,
-                min_low_bits: int = 6, max_gates: int = 96, enable: bool = True) -> List[Pass]:
+                min_low_bits: int = 6, max_gates: int = 400, enable: bool = True, max_coefs: int = 800) -> List[Pass]:
     """Greedy, order-preserving fusion.  A group grows while the union of the bits its non-diagonal
     gates need, together with the `min_low_bits` lowest bits, still fits in a tile; a group is run
     fused only when that moves fewer bytes than launching its gates one by one."""
@@ -383,7 +416,7 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
             passes.append(Pass(False, [g]))
             continue
         nn = need | _needs(g)
-        if len(nn | low) > tb or len(cur) >= max_gates:
+        if len(nn | low) > tb or len(cur) >= max_gates or sum(_ncoef(x) for x in cur) + _ncoef(g) > max_coefs:
             flush()
             nn = _needs(g)
             if len(nn | low) > tb:        # cannot happen for k <= 2 and tb >= min_low_bits + 2
@@ -424,8 +457,8 @@ def plan(gates: Sequence[Gate], n: int, amp_bytes: int = 16, fuse: bool = True, 
         return [Pass(False, [lower(g, n)]) for g in gates], "unfused"
     out = {}
     if strategy in ("auto", "tile"):
-        a = plan_passes([lower(g, n) for g in merge_blocks(gates, 2)], n, amp_bytes, tile_bits=tile_bits,
-                        min_low_bits=min_low_bits)
+        a = plan_passes([lower(g, n) for g in merge_blocks(gates, 2, cost_aware=True)], n, amp_bytes,
+                        tile_bits=tile_bits, min_low_bits=min_low_bits)
         out["tile"] = (sum(pass_cost(p, n, amp_bytes) for p in a), a)
     if strategy in ("auto", "dense4"):
         b = [Pass(False, [lower(g, n)]) for g in merge_blocks(gates, 4)]
