@@ -35,6 +35,10 @@ extern "C" int qipb_create(int device, qipb_ctx **out) {
     c->scratch = nullptr;
     c->scratch_bytes = 0;
     c->launches = 0;
+    c->tab_dev = nullptr;
+    c->tab_cap = 0;
+    c->tab_slot = 0;
+    for (int i = 0; i < 4; ++i) { c->tab_host[i] = nullptr; c->tab_ev[i] = nullptr; }
     *out = c;
     return QIPB_OK;
 }
@@ -43,6 +47,11 @@ extern "C" int qipb_destroy(qipb_ctx *ctx) {
     if (!ctx) return QIPB_OK;
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->tab_dev) cudaFree(ctx->tab_dev);
+    for (int i = 0; i < 4; ++i) {
+        if (ctx->tab_host[i]) cudaFreeHost(ctx->tab_host[i]);
+        if (ctx->tab_ev[i]) cudaEventDestroy(ctx->tab_ev[i]);
+    }
     delete ctx;
     return QIPB_OK;
 }

@@ -133,4 +133,10 @@ struct qipb_ctx {
     double *scratch;        // device scratch for reduction partials
     size_t scratch_bytes;
     unsigned long long launches;   // kernels launched through this context
+    // diagonal-stage tables of the fused pass (fused.cu): device buffer + pinned staging ring
+    double2 *tab_dev;
+    size_t tab_cap;                // capacity in double2 elements (device buffer and every ring slot)
+    double2 *tab_host[4];
+    cudaEvent_t tab_ev[4];
+    int tab_slot;
 };

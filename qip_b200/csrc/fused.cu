@@ -12,6 +12,9 @@
 //   * control bits anywhere (outside the tile they switch the gate on or off per tile).
 // Roofline: HBM-bound until the gate list is long enough for shared-memory bandwidth / FP64 to
 // take over (about 5 dense gates per pass at 3 CTAs/SM); 2 * sizeof(amp) * 2^nbits bytes per pass.
+#include <stdlib.h>
+#include <complex>
+#include <vector>
 #include "common.cuh"
 #include "../../include/qip_b200.h"
 
@@ -19,6 +22,8 @@ namespace qipb {
 
 #define FUSED_THREADS 256
 #define FUSED_MAX_INS 12
+#define FUSED_OUT_CELLS 4
+#define FUSED_LO_BITS 6          // tile-local bits 0..5 form the 'lo' table cell, the rest the 'hi' cell
 
 struct DevGate {
     unsigned char k;        // target bits in total (0..2)
@@ -30,18 +35,25 @@ struct DevGate {
     unsigned char ins[FUSED_MAX_INS];   // the fixed positions, ascending
     u32 in_or;              // tile-local mask of in-tile control bits (diagonal gates: those below the warp-slice bits)
     u32 hi_need;            // diagonal gates: control bits at or above the warp-slice bits, as a mask over the warp id
-    u32 coef;               // offset of this gate's coefficients in FusedArgs::pool
+    u32 coef;               // offset of this gate's coefficients in FusedArgs::pool (stage: in the table buffer)
     u64 out_ctrl;           // state-index mask of controls outside the tile
+    // diag == 2 ("stage"): a run of diagonal gates folded into per-cell phase tables
+    unsigned char nout;     // number of cells made of bits outside the tile
+    unsigned char cn[FUSED_OUT_CELLS];        // bits per outside cell
+    unsigned char cb[FUSED_OUT_CELLS][7];     // their state-index positions, ascending
+    unsigned char pad2[3];
 };
 
-#define FUSED_MAX_GATES 400
-#define FUSED_POOL 800      // complex coefficients: dense 2q = 16, dense 1q = 4, diagonal k = 2^k
+#define FUSED_MAX_GATES QIPB_MAX_FUSED_GATES
+#define FUSED_POOL QIPB_MAX_FUSED_COEFS      // complex coefficients: dense 2q = 16, dense 1q = 4, diagonal k = 2^k
 
 struct FusedArgs {
     int nbits, tb, ngates, lowrun;      // lowrun = number of contiguous low tile bits (0..L-1)
     int sb, wb;                         // diagonal runs: a warp owns 2^sb consecutive tile elements, 2^wb warps work
+    int npool, pad;
     u64 ntiles;
     unsigned char tbit[16];             // tile-local bit -> state bit, ascending
+    const double2 *tables;              // stage tables (global memory)
     DevGate g[FUSED_MAX_GATES];
     double2 pool[FUSED_POOL];
 };
@@ -106,7 +118,7 @@ __device__ __forceinline__ u32 expand_fast(u32 w, const LocalIns &l, const DevGa
     return w | l.orv;
 }
 
-template <typename A>
+template <typename A, bool NOPIN>
 __device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double2 *M, u64 base, u32 tsize, int tid) {
     if ((base & g.out_ctrl) != g.out_ctrl) return;             // uniform per tile
     const u32 ngroups = tsize >> g.nins;
@@ -117,7 +129,7 @@ __device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double
         const u32 o1 = 1u << g.tl[0];
         // coefficients hoisted into registers once per gate (the gate index is dynamic, so reading
         // g.m inside the loop would be an LDC per use and every DFMA would wait on it)
-        const double2 m0 = pin(M[0]), m1 = pin(M[1]), m2 = pin(M[2]), m3 = pin(M[3]);
+        const double2 m0 = NOPIN ? M[0] : pin(M[0]), m1 = NOPIN ? M[1] : pin(M[1]), m2 = NOPIN ? M[2] : pin(M[2]), m3 = NOPIN ? M[3] : pin(M[3]);
         for (u32 w = tid; w < ngroups; w += 2 * FUSED_THREADS) {
             const u32 w2 = w + FUSED_THREADS;
             const bool two = w2 < ngroups;
@@ -139,7 +151,7 @@ __device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double
         const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
         double2 m[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) m[i] = pin(M[i]);
+        for (int i = 0; i < 16; ++i) m[i] = NOPIN ? M[i] : pin(M[i]);   // NOPIN: ptxas may re-load them inside the loop
         for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
             const u32 e = expand_fast(w, li, g);
             const u32 idx[4] = {e, e | ol, e | oh, e | oh | ol};
@@ -205,15 +217,64 @@ __device__ __forceinline__ void run_diag(A *tile, const DevGate &g, const double
     }
 }
 
+// A "stage": a run of diagonal gates that share the control bits in_or/hi_need/out_ctrl and whose
+// remaining bits each fall into ONE cell of the index (tile-lo, tile-hi, or a group of <= 7 bits
+// outside the tile).  Their product is a phase  S * T_hi[e >> 6] * T_lo[e & 63]  per element, S being
+// the product of the outside-cell tables at this tile's base index: one shared-memory sweep and three
+// complex multiplies replace the whole run (a QFT stage is ~n controlled phases).
+template <typename A>
+__device__ __forceinline__ void run_stage(A *tile, const DevGate &g, const double2 *T, u64 base, int tb, int sb, int wb,
+                                          int wid, int lane) {
+    if ((base & g.out_ctrl) != g.out_ctrl) return;
+    if (wid >= (1 << wb) || ((u32)wid & g.hi_need) != g.hi_need) return;
+    const int lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
+    const u32 nlo = 1u << lo, nhi = 1u << (tb - lo);
+    double2 S = make_double2(1.0, 0.0);
+    const double2 *To = T + nlo + nhi;
+    for (int c = 0; c < g.nout; ++c) {
+        u32 idx = 0;
+        for (int j = 0; j < g.cn[c]; ++j) idx |= (u32)((base >> g.cb[c][j]) & 1ull) << j;
+        S = cmul<double2>(S, To[idx]);
+        To += 1u << g.cn[c];
+    }
+    const LocalIns li = load_ins(g);
+    const u32 n = (1u << sb) >> g.nins;
+    const u32 wbase = (u32)wid << sb;
+    for (u32 x = lane; x < n; x += 32) {
+        const u32 e = wbase | expand_fast(x, li, g);
+        double2 ph = cmul<double2>(S, T[nlo + (e >> lo)]);
+        ph = cmul<double2>(ph, T[e & (nlo - 1u)]);
+        tile[e] = cmul<A>(ph, tile[e]);
+    }
+}
+
 // BULK: tile staging with cp.async.bulk (TMA 1-D bulk copies, one per contiguous run, completion on
 // an mbarrier) instead of LDG/STS through registers.  Requires runs of >= 16 bytes.
-template <typename A, bool BULK>
-__global__ void __launch_bounds__(FUSED_THREADS, 2) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+// VAR 0: gate descriptors read from the kernel-parameter (constant) bank, 3 CTAs/SM.
+// VAR 1: descriptors + coefficients copied once per CTA into shared memory after the tile, 3 CTAs/SM.
+// VAR 2: as 1, dense coefficients pinned in registers (more registers: 2 CTAs/SM).
+template <typename A, bool BULK, int VAR>
+__global__ void __launch_bounds__(FUSED_THREADS, (VAR == 2 ? 2 : 3)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     A *tile = reinterpret_cast<A *>(smem_raw);
     const int tid = threadIdx.x;
     const u32 tsize = 1u << f.tb;
+    const DevGate *gates = f.g;
+    const double2 *pool = f.pool;
+    if (VAR >= 1) {
+        DevGate *sg = reinterpret_cast<DevGate *>(smem_raw + ((size_t)sizeof(A) << f.tb));
+        double2 *sp = reinterpret_cast<double2 *>(sg + ((f.ngates + 1) & ~1));
+        const u32 *src = reinterpret_cast<const u32 *>(f.g);
+        u32 *dst = reinterpret_cast<u32 *>(sg);
+        for (u32 i = tid; i < (u32)f.ngates * (sizeof(DevGate) / 4); i += FUSED_THREADS) dst[i] = src[i];
+        const u32 *psrc = reinterpret_cast<const u32 *>(f.pool);
+        u32 *pdst = reinterpret_cast<u32 *>(sp);
+        for (u32 i = tid; i < (u32)f.npool * 4; i += FUSED_THREADS) pdst[i] = psrc[i];
+        gates = sg;
+        pool = sp;
+        __syncthreads();
+    }
     const u32 lowmask = (1u << f.lowrun) - 1u;
     const u32 run_amps = 1u << f.lowrun;
     const u32 nruns = tsize >> f.lowrun;
@@ -256,14 +317,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) fused_kernel(A *__restrict__
         // ---- run the gate list on the tile ----
         bool prev_diag = false;
         for (int gi = 0; gi < f.ngates; ++gi) {
-            const DevGate &g = f.g[gi];
-            if (g.diag) {
-                run_diag<A>(tile, g, f.pool + g.coef, base, f.sb, f.wb, tid >> 5, tid & 31);
+            const DevGate &g = gates[gi];
+            if (g.diag == 2) {
+                run_stage<A>(tile, g, f.tables + g.coef, base, f.tb, f.sb, f.wb, tid >> 5, tid & 31);
+                __syncwarp();
+                prev_diag = true;
+            } else if (g.diag) {
+                run_diag<A>(tile, g, pool + g.coef, base, f.sb, f.wb, tid >> 5, tid & 31);
                 __syncwarp();
                 prev_diag = true;
             } else {
                 if (prev_diag) __syncthreads();
-                run_gate<A>(tile, g, f.pool + g.coef, base, tsize, tid);
+                run_gate<A, VAR != 2>(tile, g, pool + g.coef, base, tsize, tid);
                 __syncthreads();
                 prev_diag = false;
             }
@@ -294,25 +359,179 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) fused_kernel(A *__restrict__
     }
 }
 
-template <typename A>
-static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
-    const size_t smem = sizeof(A) << f.tb;
-    const bool bulk = (sizeof(A) << f.lowrun) >= 512 && f.ntiles >= 2;
+template <typename A, bool BULK, int VAR>
+static int launch_fused_v(qipb_ctx *ctx, A *state, const FusedArgs &f) {
+    const size_t tile_bytes = sizeof(A) << f.tb;
+    const size_t desc_bytes = VAR >= 1 ? (size_t)((f.ngates + 1) & ~1) * sizeof(DevGate) + (size_t)f.npool * sizeof(double2) : 0;
+    const size_t smem = tile_bytes + desc_bytes;
     int per_sm = (int)((220u * 1024u) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     u64 grid = (u64)ctx->sm_count * per_sm;
     if (grid > f.ntiles) grid = f.ntiles;
-    if (bulk) {
-        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_kernel<A, true><<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(state, f);
-    } else {
-        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_kernel<A, false><<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(state, f);
-    }
+    QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, BULK, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fused_kernel<A, BULK, VAR><<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(state, f);
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
     return QIPB_OK;
+}
+
+static int fused_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("QIPB_FUSED_VARIANT");     // tuning knob for profiling runs
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 2) v = 1;
+    }
+    return v;
+}
+
+template <typename A>
+static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
+    const bool bulk = (sizeof(A) << f.lowrun) >= 512 && f.ntiles >= 2;
+    const int v = fused_variant();
+    if (bulk) {
+        if (v == 0) return launch_fused_v<A, true, 0>(ctx, state, f);
+        if (v == 2) return launch_fused_v<A, true, 2>(ctx, state, f);
+        return launch_fused_v<A, true, 1>(ctx, state, f);
+    }
+    if (v == 0) return launch_fused_v<A, false, 0>(ctx, state, f);
+    if (v == 2) return launch_fused_v<A, false, 2>(ctx, state, f);
+    return launch_fused_v<A, false, 1>(ctx, state, f);
+}
+
+
+// ---- host side: folding runs of diagonal gates into stages -------------------------------------
+typedef std::complex<double> cplx;
+
+struct Op {
+    bool stage;
+    int gate;                 // !stage: index into the caller's gate list
+    u64 common;               // stage: control bits shared by every gate of the stage
+    u32 tab_off;              // stage: offset of its tables in the table buffer
+    int nout;
+    std::vector<int> cells[FUSED_OUT_CELLS];
+};
+
+static bool stages_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("QIPB_FUSED_STAGES");          // tuning knob for profiling runs
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
+// cell of a state bit: 0 = tile-lo, 1 = tile-hi, 2.. = groups of 7 outside bits (ascending)
+struct CellMap {
+    int cell_of[64];
+    int idx_in_cell[64];
+    std::vector<int> bits[2 + FUSED_OUT_CELLS];
+    int ncells;
+};
+
+static int residual_cell(const qipb_gate &g, u64 common, const CellMap &cm) {
+    // -1: no residual bits; -2: spans several cells; else the cell id
+    int cell = -1;
+    u64 rest = g.ctrl_mask & ~common;
+    for (int j = 0; j < g.k; ++j) rest |= 1ull << g.bits[j];
+    for (int b = 0; b < 64; ++b)
+        if ((rest >> b) & 1ull) {
+            const int c = cm.cell_of[b];
+            if (c < 0) return -2;
+            if (cell == -1) cell = c;
+            else if (cell != c) return -2;
+        }
+    return cell;
+}
+
+static void build_stages(const qipb_gate *gates, const std::vector<int> &run, int nbits, int tb, const int *local_of,
+                         u64 tmask, std::vector<Op> &ops, std::vector<cplx> &tables) {
+    CellMap cm;
+    for (int b = 0; b < 64; ++b) { cm.cell_of[b] = -1; cm.idx_in_cell[b] = 0; }
+    const int lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
+    int nout_bits = 0;
+    for (int b = 0; b < nbits; ++b) {
+        int c;
+        if (local_of[b] >= 0) c = local_of[b] < lo ? 0 : 1;
+        else c = 2 + nout_bits++ / 7;
+        if (c >= 2 + FUSED_OUT_CELLS) continue;               // beyond the supported outside cells: not table-izable
+        cm.cell_of[b] = c;
+        cm.idx_in_cell[b] = (int)cm.bits[c].size();
+        cm.bits[c].push_back(b);
+    }
+    // tile cells are indexed by tile-local position (lo: e & 63, hi: e >> 6)
+    for (int b = 0; b < nbits; ++b)
+        if (local_of[b] >= 0) cm.idx_in_cell[b] = local_of[b] < lo ? local_of[b] : local_of[b] - lo;
+    cm.ncells = 2 + (nout_bits + 6) / 7;
+    if (cm.ncells > 2 + FUSED_OUT_CELLS) cm.ncells = 2 + FUSED_OUT_CELLS;
+
+    size_t pos = 0;
+    while (pos < run.size()) {
+        // grow a stage greedily: the common control set may only shrink, every member must stay single-cell
+        u64 common = gates[run[pos]].ctrl_mask;
+        size_t end = pos + 1;
+        {
+            // a single gate is "single-cell" w.r.t. its own controls iff its targets are
+            if (residual_cell(gates[run[pos]], common, cm) == -2) common = 0;
+        }
+        while (end < run.size()) {
+            const u64 nc = common & gates[run[end]].ctrl_mask;
+            bool ok = true;
+            for (size_t t = pos; t <= end && ok; ++t) ok = residual_cell(gates[run[t]], nc, cm) != -2;
+            if (!ok) break;
+            common = nc;
+            ++end;
+        }
+        if (end - pos < 3 || residual_cell(gates[run[pos]], common, cm) == -2) {
+            // too short to pay for tables (or not table-izable at all): keep the gate as it is
+            Op o;
+            o.stage = false;
+            o.gate = run[pos];
+            ops.push_back(o);
+            ++pos;
+            continue;
+        }
+        // tables: T_lo, T_hi, then the outside cells that are actually used
+        std::vector<std::vector<cplx>> T(cm.ncells);
+        std::vector<bool> used(cm.ncells, false);
+        used[0] = used[1] = true;
+        for (int c = 0; c < cm.ncells; ++c) T[c].assign((size_t)1 << (c == 0 ? lo : c == 1 ? tb - lo : (int)cm.bits[c].size()), cplx(1.0, 0.0));
+        for (size_t t = pos; t < end; ++t) {
+            const qipb_gate &g = gates[run[t]];
+            int c = residual_cell(g, common, cm);
+            if (c == -1) c = 0;
+            used[c] = true;
+            const int D = 1 << g.k;
+            const u64 rc = g.ctrl_mask & ~common;
+            for (size_t v = 0; v < T[c].size(); ++v) {
+                bool on = true;
+                for (int b = 0; b < nbits && on; ++b)
+                    if ((rc >> b) & 1ull) on = (v >> cm.idx_in_cell[b]) & 1u;
+                if (!on) continue;
+                int sel = 0;
+                for (int j = 0; j < g.k; ++j)
+                    if ((v >> cm.idx_in_cell[g.bits[j]]) & 1u) sel |= 1 << (g.k - 1 - j);
+                T[c][v] *= cplx(g.mat[2 * (sel * D + sel)], g.mat[2 * (sel * D + sel) + 1]);
+            }
+        }
+        Op o;
+        o.stage = true;
+        o.gate = -1;
+        o.common = common;
+        o.tab_off = (u32)tables.size();
+        o.nout = 0;
+        tables.insert(tables.end(), T[0].begin(), T[0].end());
+        tables.insert(tables.end(), T[1].begin(), T[1].end());
+        for (int c = 2; c < cm.ncells; ++c)
+            if (used[c]) {
+                o.cells[o.nout] = cm.bits[c];
+                tables.insert(tables.end(), T[c].begin(), T[c].end());
+                o.nout++;
+            }
+        ops.push_back(o);
+        pos = end;
+    }
 }
 
 }  // namespace qipb
@@ -324,14 +543,13 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     QIPB_REQUIRE(ctx && state && gates && tile_bits, "null argument");
     QIPB_REQUIRE(nbits >= 0 && nbits <= 40, "nbits %d unsupported", nbits);
     QIPB_REQUIRE(ntile_bits >= 0 && ntile_bits <= QIPB_MAX_TILE_BITS && ntile_bits <= nbits, "tile bits %d unsupported", ntile_bits);
-    QIPB_REQUIRE(ngates >= 1 && ngates <= FUSED_MAX_GATES, "ngates %d unsupported (1..%d)", ngates, FUSED_MAX_GATES);
+    QIPB_REQUIRE(ngates >= 1 && ngates <= QIPB_MAX_FUSED_GATES, "ngates %d unsupported (1..%d)", ngates, QIPB_MAX_FUSED_GATES);
     QIPB_CUDA(cudaSetDevice(ctx->device));
     static thread_local FusedArgs f;    // ~30 KiB: keep it off the stack
     memset(&f, 0, sizeof(f));
     u32 pool_used = 0;
     f.nbits = nbits;
     f.tb = ntile_bits;
-    f.ngates = ngates;
     f.ntiles = 1ull << (nbits - ntile_bits);
     int local_of[64];
     for (int b = 0; b < 64; ++b) local_of[b] = -1;
@@ -347,36 +565,91 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     while (f.lowrun < ntile_bits && tile_bits[f.lowrun] == f.lowrun) f.lowrun++;
     f.wb = ntile_bits - 5 < 0 ? 0 : (ntile_bits - 5 > 3 ? 3 : ntile_bits - 5);   // 2^wb of the 8 warps, >= 32 elements each
     f.sb = ntile_bits - f.wb;
-    for (int gi = 0; gi < ngates; ++gi) {
-        const qipb_gate &s = gates[gi];
-        DevGate &d = f.g[gi];
-        QIPB_REQUIRE(s.k >= 0 && s.k <= 2, "fused gate %d: k=%d unsupported", gi, s.k);
-        d.k = (unsigned char)s.k;
-        d.diag = (unsigned char)(s.diagonal != 0 || s.k == 0);
-        u64 tgt = 0, fixed_local = 0;
-        d.kin = 0;
-        for (int j = 0; j < s.k; ++j) {
-            const int b = s.bits[j];
-            QIPB_REQUIRE(b >= 0 && b < nbits && !((tgt >> b) & 1ull), "fused gate %d: bad target bit %d", gi, b);
-            tgt |= 1ull << b;
-            d.tg[j] = (unsigned char)b;
-            if (local_of[b] >= 0) {
-                d.tl[j] = (unsigned char)local_of[b];
-                fixed_local |= 1ull << local_of[b];
-                d.kin++;
+    // ---- pass 1: validate, and fold runs of diagonal gates into stages ----
+    std::vector<Op> ops;
+    std::vector<cplx> tables;
+    {
+        std::vector<int> run;
+        auto flush_run = [&]() {
+            if (!run.empty()) build_stages(gates, run, nbits, ntile_bits, local_of, tmask, ops, tables);
+            run.clear();
+        };
+        for (int gi = 0; gi < ngates; ++gi) {
+            const qipb_gate &s = gates[gi];
+            QIPB_REQUIRE(s.k >= 0 && s.k <= 2, "fused gate %d: k=%d unsupported", gi, s.k);
+            u64 tgt = 0;
+            const bool diag = s.diagonal != 0 || s.k == 0;
+            for (int j = 0; j < s.k; ++j) {
+                const int b = s.bits[j];
+                QIPB_REQUIRE(b >= 0 && b < nbits && !((tgt >> b) & 1ull), "fused gate %d: bad target bit %d", gi, b);
+                tgt |= 1ull << b;
+                QIPB_REQUIRE(diag || local_of[b] >= 0, "fused gate %d: non-diagonal target bit %d is not a tile bit", gi, b);
+            }
+            QIPB_REQUIRE((s.ctrl_mask & tgt) == 0, "fused gate %d: control mask overlaps targets", gi);
+            QIPB_REQUIRE(nbits == 64 || (s.ctrl_mask >> nbits) == 0, "fused gate %d: control outside local bits", gi);
+            if (diag && stages_enabled()) {
+                run.push_back(gi);
             } else {
-                QIPB_REQUIRE(d.diag, "fused gate %d: non-diagonal target bit %d is not a tile bit", gi, b);
-                d.tl[j] = 0xFF;
+                flush_run();
+                Op o;
+                o.gate = gi;
+                o.stage = false;
+                ops.push_back(o);
             }
         }
-        QIPB_REQUIRE((s.ctrl_mask & tgt) == 0, "fused gate %d: control mask overlaps targets", gi);
-        QIPB_REQUIRE(nbits == 64 || (s.ctrl_mask >> nbits) == 0, "fused gate %d: control outside local bits", gi);
-        d.out_ctrl = s.ctrl_mask & ~tmask;
+        flush_run();
+    }
+    QIPB_REQUIRE((int)ops.size() <= FUSED_MAX_GATES, "fused pass needs %d device ops (max %d)", (int)ops.size(), FUSED_MAX_GATES);
+
+    // ---- pass 2: device descriptors ----
+    f.ngates = (int)ops.size();
+    for (size_t oi = 0; oi < ops.size(); ++oi) {
+        const Op &o = ops[oi];
+        DevGate &d = f.g[oi];
+        const u64 ctrl_mask = o.stage ? o.common : gates[o.gate].ctrl_mask;
+        u64 fixed_local = 0;
+        if (o.stage) {
+            d.k = 0;
+            d.kin = 0;
+            d.diag = 2;
+            d.coef = o.tab_off;
+            d.nout = (unsigned char)o.nout;
+            for (int c = 0; c < o.nout; ++c) {
+                d.cn[c] = (unsigned char)o.cells[c].size();
+                for (size_t j = 0; j < o.cells[c].size(); ++j) d.cb[c][j] = (unsigned char)o.cells[c][j];
+            }
+        } else {
+            const qipb_gate &s = gates[o.gate];
+            d.k = (unsigned char)s.k;
+            d.diag = (unsigned char)(s.diagonal != 0 || s.k == 0);
+            d.kin = 0;
+            for (int j = 0; j < s.k; ++j) {
+                const int b = s.bits[j];
+                d.tg[j] = (unsigned char)b;
+                if (local_of[b] >= 0) {
+                    d.tl[j] = (unsigned char)local_of[b];
+                    fixed_local |= 1ull << local_of[b];
+                    d.kin++;
+                } else {
+                    d.tl[j] = 0xFF;
+                }
+            }
+            const int D = 1 << s.k;
+            const int ncoef = d.diag ? D : D * D;
+            QIPB_REQUIRE(pool_used + ncoef <= FUSED_POOL, "fused pass needs more than %d matrix coefficients", FUSED_POOL);
+            d.coef = pool_used;
+            for (int e = 0; e < ncoef; ++e) {
+                const int src = d.diag ? e * D + e : e;
+                f.pool[pool_used + e] = make_double2(s.mat[2 * src], s.mat[2 * src + 1]);
+            }
+            pool_used += ncoef;
+        }
+        d.out_ctrl = ctrl_mask & ~tmask;
         d.in_or = 0;
         d.hi_need = 0;
         if (d.diag) fixed_local = 0;      // diagonal gates enumerate elements: only controls are fixed
         for (int b = 0; b < nbits; ++b)
-            if (((s.ctrl_mask & tmask) >> b) & 1ull) {
+            if (((ctrl_mask & tmask) >> b) & 1ull) {
                 const int lb = local_of[b];
                 if (d.diag && lb >= f.sb) {
                     d.hi_need |= 1u << (lb - f.sb);
@@ -388,15 +661,35 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
         d.nins = 0;
         for (int j = 0; j < ntile_bits; ++j)
             if ((fixed_local >> j) & 1ull) d.ins[d.nins++] = (unsigned char)j;
-        const int D = 1 << s.k;
-        const int ncoef = d.diag ? D : D * D;
-        QIPB_REQUIRE(pool_used + ncoef <= FUSED_POOL, "fused pass needs more than %d matrix coefficients", FUSED_POOL);
-        d.coef = pool_used;
-        for (int e = 0; e < ncoef; ++e) {
-            const int src = d.diag ? e * D + e : e;
-            f.pool[pool_used + e] = make_double2(s.mat[2 * src], s.mat[2 * src + 1]);
+    }
+    f.npool = (int)pool_used;
+
+    // ---- stage tables: pinned staging ring -> device buffer, stream ordered ----
+    f.tables = nullptr;
+    if (!tables.empty()) {
+        const size_t need = tables.size();
+        if (ctx->tab_cap < need) {
+            QIPB_CUDA(cudaStreamSynchronize(ctx->stream));
+            size_t cap = 1u << 16;
+            while (cap < need) cap <<= 1;
+            if (ctx->tab_dev) QIPB_CUDA(cudaFree(ctx->tab_dev));
+            ctx->tab_dev = nullptr;
+            QIPB_CUDA(cudaMalloc(&ctx->tab_dev, cap * sizeof(double2)));
+            for (int i = 0; i < 4; ++i) {
+                if (ctx->tab_host[i]) QIPB_CUDA(cudaFreeHost(ctx->tab_host[i]));
+                ctx->tab_host[i] = nullptr;
+                QIPB_CUDA(cudaMallocHost(&ctx->tab_host[i], cap * sizeof(double2)));
+                if (!ctx->tab_ev[i]) QIPB_CUDA(cudaEventCreateWithFlags(&ctx->tab_ev[i], cudaEventDisableTiming));
+            }
+            ctx->tab_cap = cap;
         }
-        pool_used += ncoef;
+        const int slot = ctx->tab_slot;
+        ctx->tab_slot = (slot + 1) & 3;
+        QIPB_CUDA(cudaEventSynchronize(ctx->tab_ev[slot]));      // the copy that last used this slot is done
+        memcpy(ctx->tab_host[slot], tables.data(), need * sizeof(double2));
+        QIPB_CUDA(cudaMemcpyAsync(ctx->tab_dev, ctx->tab_host[slot], need * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        QIPB_CUDA(cudaEventRecord(ctx->tab_ev[slot], ctx->stream));
+        f.tables = ctx->tab_dev;
     }
     if (dtype == QIPB_C128) return launch_fused<double2>(ctx, (double2 *)state, f);
     if (dtype == QIPB_C64) return launch_fused<float2>(ctx, (float2 *)state, f);

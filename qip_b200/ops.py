@@ -388,7 +388,7 @@ def _ncoef(g: BitGate) -> int:
 
 
 def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_bits: int = 12,
-                min_low_bits: int = 6, max_gates: int = 400, enable: bool = True, max_coefs: int = 800) -> List[Pass]:
+                min_low_bits: int = 6, max_gates: int = 280, enable: bool = True, max_coefs: int = 600) -> List[Pass]:
     """Greedy, order-preserving fusion.  A group grows while the union of the bits its non-diagonal
     gates need, together with the `min_low_bits` lowest bits, still fits in a tile; a group is run
     fused only when that moves fewer bytes than launching its gates one by one."""
@@ -457,7 +457,9 @@ def plan(gates: Sequence[Gate], n: int, amp_bytes: int = 16, fuse: bool = True, 
         return [Pass(False, [lower(g, n)]) for g in gates], "unfused"
     out = {}
     if strategy in ("auto", "tile"):
-        a = plan_passes([lower(g, n) for g in merge_blocks(gates, 2, cost_aware=True)], n, amp_bytes,
+        import os
+        ca = os.environ.get("QIPB_COST_AWARE", "1") != "0"         # tuning knob for profiling runs
+        a = plan_passes([lower(g, n) for g in merge_blocks(gates, 2, cost_aware=ca)], n, amp_bytes,
                         tile_bits=tile_bits, min_low_bits=min_low_bits)
         out["tile"] = (sum(pass_cost(p, n, amp_bytes) for p in a), a)
     if strategy in ("auto", "dense4"):
