@@ -41,7 +41,8 @@ struct DevGate {
     unsigned char nout;     // number of cells made of bits outside the tile
     unsigned char cn[FUSED_OUT_CELLS];        // bits per outside cell
     unsigned char cb[FUSED_OUT_CELLS][7];     // their state-index positions, ascending
-    unsigned char pad2[3];
+    unsigned char blockwide; // diagonal op that is alone between two block syncs: spread over all 256 threads
+    unsigned char pad2[2];
 };
 
 #define FUSED_MAX_GATES QIPB_MAX_FUSED_GATES
@@ -108,6 +109,25 @@ __device__ __forceinline__ LocalIns load_ins(const DevGate &g) {
     l.more = g.nins > 4;
     return l;
 }
+// Block-wide variant for diagonal ops: the control bits at or above the warp-slice bits are fixed
+// positions too (they are masks over the warp id in the warp-sliced mode).
+__device__ __forceinline__ LocalIns load_ins_block(const DevGate &g, int sb) {
+    u32 m[8];
+    int n = 0;
+    for (int q = 0; q < g.nins && n < 8; ++q) m[n++] = ~((1u << g.ins[q]) - 1u);
+    for (int b = 0; b < 3; ++b)
+        if ((g.hi_need >> b) & 1u) m[n++] = ~((1u << (sb + b)) - 1u);
+    LocalIns l;
+    l.m0 = n > 0 ? m[0] : 0u;
+    l.m1 = n > 1 ? m[1] : 0u;
+    l.m2 = n > 2 ? m[2] : 0u;
+    l.m3 = n > 3 ? m[3] : 0u;
+    l.orv = g.in_or | (g.hi_need << sb);
+    l.more = 0;
+    return l;
+}
+__device__ __forceinline__ int popc3(u32 v) { return __popc(v & 7u); }
+
 __device__ __forceinline__ u32 expand_fast(u32 w, const LocalIns &l, const DevGate &g) {
     w += (w & l.m0);
     w += (w & l.m1);
@@ -152,12 +172,29 @@ __device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double
         double2 m[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) m[i] = NOPIN ? M[i] : pin(M[i]);   // NOPIN: ptxas may re-load them inside the loop
-        for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
+        // software pipeline: the next group's four LDS are issued before this group's 64 DFMA, so the
+        // shared-memory latency hides behind the FP64 work (the compiler cannot hoist them itself:
+        // the stores of this iteration may alias the loads of the next as far as it can tell)
+        u32 w = tid;
+        A a[4];
+        u32 idx[4];
+        if (w < ngroups) {
             const u32 e = expand_fast(w, li, g);
-            const u32 idx[4] = {e, e | ol, e | oh, e | oh | ol};
-            A a[4], r[4];
+            idx[0] = e; idx[1] = e | ol; idx[2] = e | oh; idx[3] = e | oh | ol;
 #pragma unroll
             for (int j = 0; j < 4; ++j) a[j] = tile[idx[j]];
+        }
+        while (w < ngroups) {
+            const u32 wn = w + FUSED_THREADS;
+            A an[4];
+            u32 idn[4];
+            if (wn < ngroups) {
+                const u32 e = expand_fast(wn, li, g);
+                idn[0] = e; idn[1] = e | ol; idn[2] = e | oh; idn[3] = e | oh | ol;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) an[j] = tile[idn[j]];
+            }
+            A r[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 r[i] = cmul<A>(m[i * 4], a[0]);
@@ -166,6 +203,9 @@ __device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) tile[idx[i]] = r[i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] = an[j]; idx[j] = idn[j]; }
+            w = wn;
         }
     }
 }
@@ -188,7 +228,16 @@ __device__ __forceinline__ void run_diag(A *tile, const DevGate &g, const double
     if (g.kin == 0) {
         const double2 d = pin(M[sel_out]);
         if (d.x == 1.0 && d.y == 0.0) return;
-        for (u32 x = lane; x < n; x += 32) {
+        u32 x = lane;
+        for (; x + 96 < n; x += 128) {          // four independent elements per iteration
+            u32 e[4];
+            A v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { e[q] = wbase | expand_fast(x + 32 * q, li, g); v[q] = tile[e[q]]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tile[e[q]] = cmul<A>(d, v[q]);
+        }
+        for (; x < n; x += 32) {
             const u32 e = wbase | expand_fast(x, li, g);
             tile[e] = cmul<A>(d, tile[e]);
         }
@@ -226,7 +275,8 @@ template <typename A>
 __device__ __forceinline__ void run_stage(A *tile, const DevGate &g, const double2 *T, u64 base, int tb, int sb, int wb,
                                           int wid, int lane) {
     if ((base & g.out_ctrl) != g.out_ctrl) return;
-    if (wid >= (1 << wb) || ((u32)wid & g.hi_need) != g.hi_need) return;
+    const bool bw = g.blockwide && g.nins + popc3(g.hi_need) <= 4;
+    if (!bw && (wid >= (1 << wb) || ((u32)wid & g.hi_need) != g.hi_need)) return;
     const int lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
     const u32 nlo = 1u << lo, nhi = 1u << (tb - lo);
     double2 S = make_double2(1.0, 0.0);
@@ -237,10 +287,30 @@ __device__ __forceinline__ void run_stage(A *tile, const DevGate &g, const doubl
         S = cmul<double2>(S, To[idx]);
         To += 1u << g.cn[c];
     }
-    const LocalIns li = load_ins(g);
-    const u32 n = (1u << sb) >> g.nins;
-    const u32 wbase = (u32)wid << sb;
-    for (u32 x = lane; x < n; x += 32) {
+    const LocalIns li = bw ? load_ins_block(g, sb) : load_ins(g);
+    const u32 n = bw ? ((1u << tb) >> (g.nins + popc3(g.hi_need))) : ((1u << sb) >> g.nins);
+    const u32 wbase = bw ? 0u : ((u32)wid << sb);
+    const u32 step = bw ? FUSED_THREADS : 32u;
+    u32 x = bw ? (u32)(wid * 32 + lane) : (u32)lane;
+    for (; x + 3 * step < n; x += 4 * step) {   // four independent elements per iteration
+        u32 e[4];
+        A v[4];
+        double2 th[4], tl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            e[q] = wbase | expand_fast(x + step * q, li, g);
+            v[q] = tile[e[q]];
+            th[q] = T[nlo + (e[q] >> lo)];
+            tl[q] = T[e[q] & (nlo - 1u)];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double2 ph = cmul<double2>(S, th[q]);
+            ph = cmul<double2>(ph, tl[q]);
+            tile[e[q]] = cmul<A>(ph, v[q]);
+        }
+    }
+    for (; x < n; x += step) {
         const u32 e = wbase | expand_fast(x, li, g);
         double2 ph = cmul<double2>(S, T[nlo + (e >> lo)]);
         ph = cmul<double2>(ph, T[e & (nlo - 1u)]);
@@ -319,9 +389,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, (VAR == 2 ? 2 : 3)) fused_kerne
         for (int gi = 0; gi < f.ngates; ++gi) {
             const DevGate &g = gates[gi];
             if (g.diag == 2) {
+                if (g.blockwide && prev_diag) __syncthreads();
                 run_stage<A>(tile, g, f.tables + g.coef, base, f.tb, f.sb, f.wb, tid >> 5, tid & 31);
-                __syncwarp();
-                prev_diag = true;
+                if (g.blockwide) {
+                    __syncthreads();
+                    prev_diag = false;
+                } else {
+                    __syncwarp();
+                    prev_diag = true;
+                }
             } else if (g.diag) {
                 run_diag<A>(tile, g, pool + g.coef, base, f.sb, f.wb, tid >> 5, tid & 31);
                 __syncwarp();
@@ -663,6 +739,12 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
             if ((fixed_local >> j) & 1ull) d.ins[d.nins++] = (unsigned char)j;
     }
     f.npool = (int)pool_used;
+    for (int oi = 0; oi < f.ngates; ++oi)
+        if (f.g[oi].diag == 2) {
+            const bool prev_dense = oi == 0 || f.g[oi - 1].diag == 0;
+            const bool next_dense = oi + 1 == f.ngates || f.g[oi + 1].diag == 0;
+            f.g[oi].blockwide = (prev_dense && next_dense) ? 1 : 0;
+        }
 
     // ---- stage tables: pinned staging ring -> device buffer, stream ordered ----
     f.tables = nullptr;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU-side sweep of fused-kernel variants (run under gpurun): prints one line per configuration.
 for wl in layered qft; do
- for v in 0 1 2; do
+ for v in 0 2; do
   for ca in 0 1; do
    QIPB_FUSED_VARIANT=$v QIPB_COST_AWARE=$ca timeout 300 python bench.py --workload $wl --steps 2 --warmup 1 --no-micro --no-cpu --strategy tile > gpurun_out/sw_${wl}_${v}_${ca}.json 2> gpurun_out/sw.err
    python - <<PY
