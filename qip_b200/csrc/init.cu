@@ -19,32 +19,58 @@ struct KronArgs {
     u64 shard_base;       // shard_index << nbits
     u64 zero_mask;        // global bits that must be 0 (un-fed qubits)
     int ngroups;
+    int vb;               // a thread writes 2^vb amplitudes: index bits 8 .. 8+vb-1 vary inside a thread
     int run_begin[QIPB_MAX_GROUPS + 1];
     u64 feed_off[QIPB_MAX_GROUPS];
+    unsigned char varies[QIPB_MAX_GROUPS];   // group reads one of the bits that vary inside a thread
     BitRuns runs;         // all groups' gathers, concatenated
 };
 
+__device__ __forceinline__ double2 kron_factor(const KronArgs &k, const double2 *__restrict__ feeds, int g, u64 G) {
+    u64 sub = 0;
+    for (int r = k.run_begin[g]; r < k.run_begin[g + 1]; ++r)
+        sub |= ((G >> k.runs.src[r]) & ((1ull << k.runs.len[r]) - 1ull)) << k.runs.dst[r];
+    return feeds[k.feed_off[g] + sub];
+}
+
+// A block of 256 threads writes 256 * 2^vb consecutive amplitudes; thread t owns t, t+256, t+512, ...
+// (every store instruction of a warp is 512 contiguous bytes).  The factors of the groups that do
+// not depend on the bits varying inside a thread are multiplied once per thread (left to right, like
+// qip/backend.py:98-101), the others once per amplitude -- for n one-qubit feeds that is n/2^vb + vb
+// complex multiplies per amplitude instead of n.
 template <typename A>
 __global__ void __launch_bounds__(256) init_kron_kernel(A *__restrict__ state, const double2 *__restrict__ feeds,
                                                         const __grid_constant__ KronArgs k) {
     typedef typename amp_traits<A>::real R;
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k.n) return;
-    const u64 G = k.shard_base | i;
-    double2 v = make_double2(0.0, 0.0);
-    if ((G & k.zero_mask) == 0) {
-        v = make_double2(1.0, 0.0);
-        for (int g = 0; g < k.ngroups; ++g) {
-            u64 sub = 0;
-            for (int r = k.run_begin[g]; r < k.run_begin[g + 1]; ++r)
-                sub |= ((G >> k.runs.src[r]) & ((1ull << k.runs.len[r]) - 1ull)) << k.runs.dst[r];
-            const double2 f = feeds[k.feed_off[g] + sub];
-            const double2 t = v;
-            v.x = t.x * f.x - t.y * f.y;
-            v.y = t.x * f.y + t.y * f.x;
+    const int vec = 1 << k.vb;
+    const u64 i0 = ((u64)blockIdx.x << (8 + k.vb)) + threadIdx.x;
+    if (i0 >= k.n) return;
+    const u64 G0 = k.shard_base | i0;
+    double2 P = make_double2(1.0, 0.0);
+    for (int g = 0; g < k.ngroups; ++g)
+        if (!k.varies[g]) {
+            const double2 f = kron_factor(k, feeds, g, G0);
+            const double2 t = P;
+            P.x = t.x * f.x - t.y * f.y;
+            P.y = t.x * f.y + t.y * f.x;
         }
+    for (int j = 0; j < vec; ++j) {
+        const u64 i = i0 + ((u64)j << 8);
+        if (i >= k.n) break;
+        const u64 G = k.shard_base | i;
+        double2 v = make_double2(0.0, 0.0);
+        if ((G & k.zero_mask) == 0) {
+            v = P;
+            for (int g = 0; g < k.ngroups; ++g)
+                if (k.varies[g]) {
+                    const double2 f = kron_factor(k, feeds, g, G);
+                    const double2 t = v;
+                    v.x = t.x * f.x - t.y * f.y;
+                    v.y = t.x * f.y + t.y * f.x;
+                }
+        }
+        state[i] = make_amp<A>((R)v.x, (R)v.y);
     }
-    state[i] = make_amp<A>((R)v.x, (R)v.y);
 }
 
 template <typename A>
@@ -108,6 +134,8 @@ extern "C" int qipb_init_kron(qipb_ctx *ctx, void *state, int nbits, int dtype, 
     k.shard_base = (u64)shard_index << nbits;
     k.zero_mask = zero_mask;
     k.ngroups = ngroups;
+    k.vb = nbits >= 11 ? 3 : (nbits > 8 ? nbits - 8 : 0);
+    const u64 vmask = ((1ull << k.vb) - 1ull) << 8;
     u64 foff = 0, seen = 0;
     const int *gb = group_bits;
     for (int g = 0; g < ngroups; ++g) {
@@ -120,6 +148,7 @@ extern "C" int qipb_init_kron(qipb_ctx *ctx, void *state, int nbits, int dtype, 
             seen |= 1ull << gb[t];
             src[t] = gb[t];
             dst[t] = L - 1 - t;      // first listed qubit = most significant sub-index bit
+            if ((vmask >> gb[t]) & 1ull) k.varies[g] = 1;
         }
         BitRuns one;
         memset(&one, 0, sizeof(one));
@@ -139,7 +168,8 @@ extern "C" int qipb_init_kron(qipb_ctx *ctx, void *state, int nbits, int dtype, 
     }
     k.run_begin[ngroups] = k.runs.nruns;
     QIPB_REQUIRE((seen & zero_mask) == 0, "zero_mask overlaps fed bits");
-    const u64 blocks = (k.n + 255) / 256;
+    const u64 per_block = 256ull << k.vb;
+    const u64 blocks = (k.n + per_block - 1) / per_block;
     if (dtype == QIPB_C128) init_kron_kernel<double2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)state, (const double2 *)feeds_dev, k);
     else if (dtype == QIPB_C64) init_kron_kernel<float2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)state, (const double2 *)feeds_dev, k);
     else QIPB_REQUIRE(false, "unknown dtype %d", dtype);

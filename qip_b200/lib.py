@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libqipb200.so")
 
 C128, C64 = 0, 1
-MAX_DENSE_K, MAX_BIG_K, MAX_TILE_BITS, MAX_FUSED_GATES, MAX_FUSED_COEFS = 4, 10, 12, 280, 600
+MAX_DENSE_K, MAX_BIG_K, MAX_TILE_BITS, MAX_FUSED_GATES = 4, 10, 12, 280
 
 EXPORTS = [
     "qipb_version", "qipb_last_error", "qipb_create", "qipb_destroy", "qipb_set_stream", "qipb_sync",

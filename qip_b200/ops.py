@@ -179,17 +179,19 @@ def _apply_to_block(block_mat, block_qubits, u, u_qubits):
 
 
 def tile_cost(g: Optional[Gate]) -> float:
-    """Relative cost of a gate inside a fused tile pass (FP64 work + shared-memory traffic per
-    amplitude of the state, in units of one complex multiply): used to refuse merges that would turn
-    cheap controlled / diagonal gates into a more expensive dense block (e.g. H followed by a C-phase)."""
+    """Relative cost of a gate inside a fused tile pass, calibrated on B200 (profiles/): a dense gate
+    costs one shared-memory sweep whose length hardly depends on k (1q ~ 4, 2q ~ 5 units, scaled by
+    the fraction of the state its controls select); a diagonal gate is nearly free because runs of
+    diagonal gates are folded into one table sweep by the kernel (fused.cu, "stage").  Used to refuse
+    merges that would turn cheap diagonal gates into a dense block (H followed by a C-phase in a QFT)."""
     if g is None:
         return 0.0
     frac = 2.0 ** (-len(g.controls))
     if g.kind == "swap":
-        return 0.5 * frac
+        return 1.0 * frac
     if g.diagonal or g.k == 0:
-        return 2.0 * frac
-    return (2.0 ** g.k + 1.0) * frac
+        return 0.3
+    return (3.0 + g.k) * frac
 
 
 def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True, cost_aware: bool = False) -> List[Gate]:
@@ -216,7 +218,7 @@ def merge_blocks(gates: Sequence[Gate], max_k: int = 4, pack: bool = True, cost_
             return True
         trial = [list(block[0]), block[1]]
         _absorb(trial, qs, u)
-        return cost_of(trial[0], trial[1]) <= cost_of(block[0], block[1]) + cost_of(list(qs), u) + 1.0
+        return cost_of(trial[0], trial[1]) <= cost_of(block[0], block[1]) + cost_of(list(qs), u) + 0.5
 
     for g in gates:
         if len(g.qubits()) > max_k:
@@ -388,7 +390,7 @@ def _ncoef(g: BitGate) -> int:
 
 
 def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_bits: int = 12,
-                min_low_bits: int = 6, max_gates: int = 280, enable: bool = True, max_coefs: int = 600) -> List[Pass]:
+                min_low_bits: int = 6, max_gates: int = 280, enable: bool = True, max_coefs: int = 1 << 30) -> List[Pass]:
     """Greedy, order-preserving fusion.  A group grows while the union of the bits its non-diagonal
     gates need, together with the `min_low_bits` lowest bits, still fits in a tile; a group is run
     fused only when that moves fewer bytes than launching its gates one by one."""

@@ -71,7 +71,7 @@ def main():
     feeds2 = [rng.normal(size=8) + 1j * rng.normal(size=8), [0.6, 0.8j], rng.normal(size=4)]
     g = ShardedB200Backend.make_state(n, groups2, feeds2)
     c = orc.OracleBackend.make_state(n, groups2, feeds2)
-    assert np.array_equal(g.get_state(), c.get_state())
+    check("kron init", g.get_state(), c.get_state(), 1e-15)
     g.close()
     g = ShardedB200Backend.make_state(n, [], [])
     want = np.zeros(2 ** n)

@@ -205,7 +205,7 @@ def test_kron_init_shuffled_groups_and_one_hot():
     feeds = [rng.normal(size=8) + 1j * rng.normal(size=8), [0.6, 0.8j], rng.normal(size=4), [0.0, 1.0]]
     g = _backend().make_state(n, groups, feeds)
     c = orc.OracleBackend.make_state(n, groups, feeds)
-    assert np.array_equal(np.asarray(g.get_state()), c.get_state())      # same product order -> identical
+    _agree(g, c, 1e-15)            # same factors; association differs only where a thread shares a partial product
     g = _backend().make_state(3, [], [])
     assert np.array_equal(np.asarray(g.get_state()), np.eye(8)[0])
     g = _backend().make_state(4, [[1, 2]], [3])                           # one-hot int feed
