@@ -60,7 +60,7 @@ class B200Backend(object):
     """StateType implementation on one B200 (see module docstring)."""
 
     def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6,
-                 strategy: str = "auto"):
+                 strategy: str = "auto", relabel_swaps: bool = True):
         torch = _torch()
         self.L = _lib.load()
         if not torch.cuda.is_available():
@@ -78,6 +78,10 @@ class B200Backend(object):
         self.tile_bits = tile_bits
         self.min_low_bits = min_low_bits
         self.strategy = strategy
+        # logical qubit -> index bit.  Canonical is n-1-q; an un-controlled Swap only permutes this map
+        # (free) and the state is brought back to canonical order when it is read out in index order.
+        self.relabel_swaps = relabel_swaps and fuse
+        self.pos = [self.n - 1 - q for q in range(self.n)]
         ctx = ctypes.c_void_p()
         _lib.check(self.L.qipb_create(self.device.index or 0, ctypes.byref(ctx)))
         self.ctx = ctx
@@ -192,10 +196,53 @@ class B200Backend(object):
         if not self.queue:
             return
         torch = _torch()
-        passes, chosen = plan(self.queue, self.n, self.amp_bytes, fuse=self.fuse, tile_bits=self.tile_bits,
+        gates = self._relabel(self.queue)
+        self.queue = []
+        if not gates:
+            return
+        passes, chosen = plan(gates, self.n, self.amp_bytes, fuse=self.fuse, tile_bits=self.tile_bits,
                               min_low_bits=self.min_low_bits, strategy=self.strategy)
         self.stats["strategy_" + chosen] = self.stats.get("strategy_" + chosen, 0) + 1
-        self.queue = []
+        self._run_passes(passes)
+        self.stats["flushes"] += 1
+
+    def _relabel(self, gates):
+        """Un-controlled swaps become permutations of self.pos; every other gate is rewritten onto the
+        pseudo-qubits n-1-pos[q] so that the planner's canonical lowering lands on the right bits."""
+        n = self.n
+        out = []
+        for g in gates:
+            if self.relabel_swaps and g.kind == "swap" and not g.controls:
+                a, b = g.targets
+                self.pos[a], self.pos[b] = self.pos[b], self.pos[a]
+                self.stats["relabels"] = self.stats.get("relabels", 0) + 1
+                continue
+            if all(self.pos[q] == n - 1 - q for q in g.qubits()):
+                out.append(g)
+            else:
+                out.append(Gate(g.kind, tuple(n - 1 - self.pos[q] for q in g.targets),
+                                tuple(n - 1 - self.pos[q] for q in g.controls), g.mat, g.diagonal))
+        return out
+
+    def _canonicalise(self):
+        """Physically undo the relabels (bit swaps, fused like any other gates)."""
+        n = self.n
+        if all(self.pos[q] == n - 1 - q for q in range(n)):
+            return
+        swaps = []
+        pos = self.pos
+        for q in range(n):
+            want = n - 1 - q
+            if pos[q] != want:
+                other = pos.index(want)
+                swaps.append(Gate("swap", (n - 1 - pos[q], n - 1 - want)))     # pseudo-qubits of the two bits
+                pos[other], pos[q] = pos[q], want
+        passes, _ = plan(swaps, n, self.amp_bytes, fuse=self.fuse, tile_bits=self.tile_bits,
+                         min_low_bits=self.min_low_bits, strategy="tile")
+        self._run_passes(passes)
+
+    def _run_passes(self, passes):
+        torch = _torch()
         with torch.cuda.device(self.device):
             self._stream()
             for p in passes:
@@ -212,7 +259,6 @@ class B200Backend(object):
                     e1.record()
                     self.profile.append(kernel_label(p, self.n, self.amp_bytes) + (e0, e1))
                 self.stats["passes"] += 1
-        self.stats["flushes"] += 1
 
     def func_apply(self, reg1_indices, reg2_indices, func: Callable[[int], int],
                    input_offset: int = 0, output_offset: int = 0) -> None:
@@ -231,8 +277,8 @@ class B200Backend(object):
             self._stream()
             dev_table = torch.from_numpy(table).to(self.device)
             _lib.check(self.L.qipb_func_xor(self.ctx, self._ptr(), n, self.code, len(reg1),
-                                            _lib.int_array([n - 1 - q for q in reg1]), len(reg2),
-                                            _lib.int_array([n - 1 - q for q in reg2]),
+                                            _lib.int_array([self.pos[q] for q in reg1]), len(reg2),
+                                            _lib.int_array([self.pos[q] for q in reg2]),
                                             ctypes.c_void_p(dev_table.data_ptr()), 0))
             self._keepalive = dev_table
 
@@ -247,14 +293,14 @@ class B200Backend(object):
         k = len(idx)
         if len(set(idx)) != k or any(not (0 <= q < n) for q in idx):
             raise ValueError("measured indices must be distinct qubit indices in [0, n)")
+        self.flush()
         if order == "given-le":
-            bits = [n - 1 - q for q in idx]
+            bits = [self.pos[q] for q in idx]
             outb = list(range(k))
         else:
             srt = sorted(idx)
-            bits = [n - 1 - q for q in srt]
+            bits = [self.pos[q] for q in srt]
             outb = [k - 1 - j for j in range(k)]
-        self.flush()
         with torch.cuda.device(self.device):
             self._stream()
             out = torch.empty(2 ** k, dtype=torch.float64, device=self.device)
@@ -271,7 +317,7 @@ class B200Backend(object):
         k = len(srt)
         mask = want = 0
         for j, q in enumerate(srt):
-            bit = 1 << (n - 1 - q)
+            bit = 1 << self.pos[q]
             mask |= bit
             if (m >> (k - 1 - j)) & 1:
                 want |= bit
@@ -288,6 +334,7 @@ class B200Backend(object):
             raise ValueError("B200Backend holds the whole state; offset windows are not supported")
         k = len(indices)
         r = random.random()
+        self.flush()
         if measured is not None:
             mask, want = self._mask_value(indices, int(measured))
             p = float(self._probabilities([], "sorted-be", mask, want)[0])
@@ -307,8 +354,8 @@ class B200Backend(object):
             m, p = self.soft_measure(indices, measured=measured)
         else:
             m, p = int(measured), float(measured_prob)
-        mask, want = self._mask_value(indices, m)
         self.flush()
+        mask, want = self._mask_value(indices, m)
         with torch.cuda.device(self.device):
             self._stream()
             _lib.check(self.L.qipb_collapse(self.ctx, self._ptr(), self.n, self.code, mask, want, math.sqrt(1.0 / p)))
@@ -325,8 +372,9 @@ class B200Backend(object):
             m, p = self.soft_measure(indices, measured=measured)
         else:
             m, p = int(measured), float(measured_prob)
-        mask, want = self._mask_value(indices, m)
         self.flush()
+        self._canonicalise()
+        mask, want = self._mask_value(indices, m)
         with torch.cuda.device(self.device):
             self._stream()
             dst = torch.empty(2 ** (self.n - k), dtype=self.tdtype, device=self.device)
@@ -335,6 +383,7 @@ class B200Backend(object):
             torch.cuda.current_stream(self.device).synchronize()
             self.state = dst
             self.n -= k
+            self.pos = [self.n - 1 - q for q in range(self.n)]
         return m, p
 
     def measure_probabilities(self, indices, top_k: int = 0):
@@ -349,6 +398,7 @@ class B200Backend(object):
         """qip/backend.py:106-107.  Host ndarray for n <= 28, DeviceState handle beyond."""
         torch = _torch()
         self.flush()
+        self._canonicalise()
         with torch.cuda.device(self.device):
             torch.cuda.current_stream(self.device).synchronize()
             if self.n <= _HOST_STATE_MAX_QUBITS:
@@ -360,17 +410,20 @@ class B200Backend(object):
 
     def get_relative_range(self, start: int, end: int):
         self.flush()
+        self._canonicalise()
         return self.state[start:end].cpu().numpy()
 
     def overwrite_relative_range(self, start: int, end: int, data):
         torch = _torch()
         self.flush()
+        self._canonicalise()
         src = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=self.np_dtype)))
         self.state[start:end].copy_(src)
 
     def addto_relative_range(self, start: int, end: int, data):
         torch = _torch()
         self.flush()
+        self._canonicalise()
         with torch.cuda.device(self.device):
             self._stream()
             src = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=self.np_dtype))).to(self.device)

@@ -171,25 +171,58 @@ __device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double
             const u32 nlo = 1u << lo, nhi = 1u << (tb - lo);
             const double2 S = stage_scalar(si, T, base, nlo, nhi);
             const u32 sor = st.in_or;
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g), e1 = e | o1;
-                const A a0 = tile[e], a1 = tile[e1];
-                A r0 = cmul<A>(g.m[0], a0);
-                cfma<A>(r0, g.m[1], a1);
-                A r1 = cmul<A>(g.m[2], a0);
-                cfma<A>(r1, g.m[3], a1);
-                if ((e & sor) == sor) {
-                    double2 ph = cmul<double2>(S, T[nlo + (e >> lo)]);
-                    ph = cmul<double2>(ph, T[e & (nlo - 1u)]);
-                    r0 = cmul<A>(ph, r0);
+            if (sor == o1 && g.nins == 1) {
+                // the stage is controlled by exactly the gate's target bit (H_k + its controlled phases):
+                // branch-free, two pairs per iteration so that table and tile loads overlap the FP64 work
+                const u32 nm = g.nmask[0];
+                const double2 m0 = g.m[0], m1 = g.m[1], m2 = g.m[2], m3 = g.m[3];
+                const u32 lom = nlo - 1u;
+                for (u32 w = tid; w < ngroups; w += 2 * FUSED_THREADS) {
+                    const u32 w2 = w + FUSED_THREADS;
+                    const bool two = w2 < ngroups;
+                    const u32 ea = w + (w & nm), eb = two ? w2 + (w2 & nm) : ea;
+                    const u32 ea1 = ea | o1, eb1 = eb | o1;
+                    const A a0 = tile[ea], a1 = tile[ea1], b0 = tile[eb], b1 = tile[eb1];
+                    const double2 tha = T[nlo + (ea1 >> lo)], tla = T[ea1 & lom];
+                    const double2 thb = T[nlo + (eb1 >> lo)], tlb = T[eb1 & lom];
+                    A r0 = cmul<A>(m0, a0), r1 = cmul<A>(m2, a0), s0 = cmul<A>(m0, b0), s1 = cmul<A>(m2, b0);
+                    cfma<A>(r0, m1, a1);
+                    cfma<A>(r1, m3, a1);
+                    cfma<A>(s0, m1, b1);
+                    cfma<A>(s1, m3, b1);
+                    double2 pa = cmul<double2>(S, tha), pb = cmul<double2>(S, thb);
+                    pa = cmul<double2>(pa, tla);
+                    pb = cmul<double2>(pb, tlb);
+                    r1 = cmul<A>(pa, r1);
+                    s1 = cmul<A>(pb, s1);
+                    tile[ea] = r0;
+                    tile[ea1] = r1;
+                    if (two) {
+                        tile[eb] = s0;
+                        tile[eb1] = s1;
+                    }
                 }
-                if ((e1 & sor) == sor) {
-                    double2 ph = cmul<double2>(S, T[nlo + (e1 >> lo)]);
-                    ph = cmul<double2>(ph, T[e1 & (nlo - 1u)]);
-                    r1 = cmul<A>(ph, r1);
+            } else {
+                for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
+                    const u32 e = expand_local(w, g), e1 = e | o1;
+                    const A a0 = tile[e], a1 = tile[e1];
+                    A r0 = cmul<A>(g.m[0], a0);
+                    cfma<A>(r0, g.m[1], a1);
+                    A r1 = cmul<A>(g.m[2], a0);
+                    cfma<A>(r1, g.m[3], a1);
+                    if ((e & sor) == sor) {
+                        double2 ph = cmul<double2>(S, T[nlo + (e >> lo)]);
+                        ph = cmul<double2>(ph, T[e & (nlo - 1u)]);
+                        r0 = cmul<A>(ph, r0);
+                    }
+                    if ((e1 & sor) == sor) {
+                        double2 ph = cmul<double2>(S, T[nlo + (e1 >> lo)]);
+                        ph = cmul<double2>(ph, T[e1 & (nlo - 1u)]);
+                        r1 = cmul<A>(ph, r1);
+                    }
+                    tile[e] = r0;
+                    tile[e1] = r1;
                 }
-                tile[e] = r0;
-                tile[e1] = r1;
             }
         }
     } else {   // dense k == 2
@@ -648,6 +681,17 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
                     nx.diag = 3;
                 }
             }
+        if (getenv("QIPB_DEBUG")) {
+            int nst = 0, npost = 0, ndense = 0, ndiag = 0;
+            for (size_t oi = 0; oi < cnt; ++oi) {
+                nst += f.g[oi].diag >= 2;
+                npost += f.g[oi].post != 0;
+                ndense += f.g[oi].diag == 0;
+                ndiag += f.g[oi].diag == 1;
+            }
+            fprintf(stderr, "[qipb] fused launch: %d input gates -> %d ops (dense %d, lone diagonal %d, stages %d of which %d ride on a dense gate), tables %zu\n",
+                    ngates, (int)cnt, ndense, ndiag, nst, npost, tables.size());
+        }
         int rc = dtype == QIPB_C128 ? launch_fused<double2>(ctx, (double2 *)state, f)
                                     : launch_fused<float2>(ctx, (float2 *)state, f);
         if (rc) return rc;

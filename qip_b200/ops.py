@@ -436,20 +436,28 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
 # bound once the gate list is long.  plan() uses it to choose between
 #   A. blocks of <= 2 qubits -> fused tile passes (diagonal gates and controls anywhere), and
 #   B. blocks of <= 4 qubits -> one register-blocked stand-alone launch per block (HBM roofline).
-TILE_GATE_COST = 0.40
+TILE_GATE_COST = 0.45
 
 
 def pass_cost(p: Pass, nbits: int, amp_bytes: int) -> float:
+    """Estimated cost of a pass in HBM-byte equivalents, calibrated at 33 qubits complex128 on B200
+    (profiles/): a fused pass costs one full sweep of HBM traffic overlapped with ~0.45 sweep-times of
+    shared-memory work per dense gate; the register-blocked K=3/K=4 kernels are FP64-limited."""
     full = 2.0 * amp_bytes * 2.0 ** nbits
     if not p.fused:
-        return gate_bytes(p.gates[0], nbits, amp_bytes)
+        g = p.gates[0]
+        slow = 1.5 if (g.kind == "matrix" and g.k >= 4 and not g.diagonal) else 1.1 if (g.kind == "matrix" and g.k == 3 and not g.diagonal) else 1.0
+        return slow * gate_bytes(g, nbits, amp_bytes)
     work = 0.0
     for g in p.gates:
         frac = 2.0 ** (-g.nctrl())
         if g.kind == "swap":
-            frac *= 0.5
-        work += TILE_GATE_COST * max(frac, 0.05)
-    return full * max(1.0, work)
+            work += 0.5 * frac
+        elif g.diagonal or g.k == 0:
+            work += 0.1 * frac
+        else:
+            work += frac
+    return full * max(1.0, 0.5 + TILE_GATE_COST * work)
 
 
 def plan(gates: Sequence[Gate], n: int, amp_bytes: int = 16, fuse: bool = True, tile_bits: int = 12,
