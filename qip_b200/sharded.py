@@ -62,9 +62,16 @@ class ShardedB200Backend(object):
         self.fuse = fuse
         self.stats = {"gates": 0, "exchanges": 0, "peer_gates": 0, "nvlink_bytes_out": 0}
         # shard memory comes from cudaMalloc (qipb_dev_alloc) so that its IPC handle maps it exactly
-        count = 1 << self.nl
         ptr = ctypes.c_void_p()
-        _lib.check(self.L.qipb_dev_alloc(self.ctx, count * self.amp_bytes, ctypes.byref(ptr)))
+        _lib.check(self.L.qipb_dev_alloc(self.ctx, (1 << self.nl) * self.amp_bytes, ctypes.byref(ptr)))
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.peers = {}
+        self._adopt_shard(ptr)
+
+    def _adopt_shard(self, ptr):
+        """Wrap a cudaMalloc'ed shard for torch, export its IPC handle and map every peer's shard."""
+        torch = _torch()
+        count = 1 << self.nl
         self.ptr = ptr
         self.eng.state = torch.as_tensor(_RawCuda(ptr.value, count, "<c16" if self.amp_bytes == 16 else "<c8"),
                                          device=self.device)
@@ -72,15 +79,27 @@ class ShardedB200Backend(object):
         handle = ctypes.create_string_buffer(64)
         _lib.check(self.L.qipb_ipc_export(self.ctx, ptr, handle))
         handles = [None] * self.P
-        dist.all_gather_object(handles, bytes(handle.raw))
+        self.dist.all_gather_object(handles, bytes(handle.raw))
         self.peers = {}
         for r in range(self.P):
             if r != self.rank:
                 pp = ctypes.c_void_p()
                 _lib.check(self.L.qipb_ipc_open(self.ctx, handles[r], ctypes.byref(pp)))
                 self.peers[r] = pp
-        self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._sync_all()
+
+    def _release_shard(self):
+        torch = _torch()
+        torch.cuda.synchronize()
+        self._sync_all()
+        torch.cuda.synchronize()
+        for pp in self.peers.values():
+            self.L.qipb_ipc_close(self.ctx, pp)
+        self.peers = {}
+        self.dist.barrier()
+        self.eng.state = None
+        self.L.qipb_dev_free(self.ctx, self.ptr)
+        self.ptr = None
 
     # ------------------------------------------------------------------ plumbing
     def _sync_all(self):
@@ -367,8 +386,62 @@ class ShardedB200Backend(object):
                 _lib.check(self.L.qipb_init_basis(self.ctx, self.ptr, self.nl, self.code, -1))
         return m, p
 
-    def reduce_measure(self, *a, **k):
-        raise NotImplementedError("reduce_measure on a sharded state is not implemented yet (DESIGN.md, gaps)")
+    def reduce_measure(self, indices, measured: Optional[int] = None, measured_prob: Optional[float] = None,
+                       input_offset: int = 0, output_offset: int = 0):
+        """Measured qubits are first made local (bit exchanges), then every rank compacts its shard;
+        the state keeps P shards of 2^(n-k-G) amplitudes and n decreases by k."""
+        torch = _torch()
+        k = len(indices)
+        _check_measure_args(k, measured, measured_prob)
+        if self.nl - k < 1:
+            raise ValueError("reduce_measure would leave less than one local qubit per rank")
+        if measured is None or measured_prob is None:
+            m, p = self.soft_measure(indices, measured=measured)
+        else:
+            m, p = int(measured), float(measured_prob)
+        self.flush()
+        srt = sorted(int(i) for i in indices)
+        moves = []
+        for q in srt:
+            if self.layout.is_global(q):
+                for pp in range(self.nl - 1, -1, -1):
+                    v = self.layout.qubit_at(pp)
+                    if v not in srt:
+                        moves.append(sp.Exchange(self.layout.pos[q], pp))
+                        self.layout.swap_qubits(q, v)
+                        break
+        self._execute(moves)
+        mask = want = 0
+        for j, q in enumerate(srt):
+            pos = self.layout.pos[q]
+            mask |= 1 << pos
+            want |= ((m >> (k - 1 - j)) & 1) << pos
+        new_nl = self.nl - k
+        with torch.cuda.device(self.device):
+            self._stream()
+            torch.cuda.synchronize()
+            self._sync_all()
+            torch.cuda.synchronize()
+            new_ptr = ctypes.c_void_p()
+            _lib.check(self.L.qipb_dev_alloc(self.ctx, (1 << new_nl) * self.amp_bytes, ctypes.byref(new_ptr)))
+            _lib.check(self.L.qipb_reduce(self.ctx, self.ptr, new_ptr, self.nl, self.code, mask, want, math.sqrt(1.0 / p)))
+            torch.cuda.synchronize()
+            # remaining logical qubits are renumbered in ascending order; local positions are compacted
+            remaining = [q for q in range(self.n) if q not in srt]
+            old_pos = [self.layout.pos[q] for q in remaining]
+            new_layout = sp.Layout(self.n - k, self.G)
+            for newq, op in enumerate(old_pos):
+                if op >= self.nl:
+                    new_layout.pos[newq] = op - k
+                else:
+                    new_layout.pos[newq] = op - bin(mask & ((1 << op) - 1)).count("1")
+            self._release_shard()
+            self.n -= k
+            self.nl = new_nl
+            self.layout = new_layout
+            self.eng.n = new_nl
+            self._adopt_shard(new_ptr)
+        return m, p
 
     def measure_probabilities(self, indices, top_k: int = 0):
         if top_k:
@@ -390,6 +463,46 @@ class ShardedB200Backend(object):
     def get_state_size(self) -> int:
         return 2 ** self.n
 
+    def _my_overlap(self, start: int, end: int):
+        lo, hi = self.rank << self.nl, (self.rank + 1) << self.nl
+        a, b = max(start, lo), min(end, hi)
+        return (a, b, lo) if a < b else None
+
+    def get_relative_range(self, start: int, end: int):
+        """qip/backend.py:165-166 on the canonical (index-ordered) state; every rank gets the range."""
+        self.flush()
+        self._execute(sp.canonicalise(self.layout))
+        ov = self._my_overlap(start, end)
+        piece = self.eng.state[ov[0] - ov[2]:ov[1] - ov[2]].cpu().numpy() if ov else np.zeros(0, dtype=self.np_dtype)
+        parts = [None] * self.P
+        self.dist.all_gather_object(parts, piece)
+        return np.concatenate(parts)
+
+    def overwrite_relative_range(self, start: int, end: int, data):
+        torch = _torch()
+        self.flush()
+        self._execute(sp.canonicalise(self.layout))
+        ov = self._my_overlap(start, end)
+        if ov:
+            src = np.ascontiguousarray(np.asarray(data, dtype=self.np_dtype)[ov[0] - start:ov[1] - start])
+            self.eng.state[ov[0] - ov[2]:ov[1] - ov[2]].copy_(torch.from_numpy(src))
+        self._sync_all()
+
+    def addto_relative_range(self, start: int, end: int, data):
+        torch = _torch()
+        self.flush()
+        self._execute(sp.canonicalise(self.layout))
+        ov = self._my_overlap(start, end)
+        if ov:
+            src = np.ascontiguousarray(np.asarray(data, dtype=self.np_dtype)[ov[0] - start:ov[1] - start])
+            with torch.cuda.device(self.device):
+                self._stream()
+                dev = torch.from_numpy(src).to(self.device)
+                _lib.check(self.L.qipb_add_range(self.ctx, self.ptr, self.code, ov[0] - ov[2], ov[1] - ov[0],
+                                                 ctypes.c_void_p(dev.data_ptr())))
+                torch.cuda.current_stream(self.device).synchronize()
+        self._sync_all()
+
     def synchronize(self):
         self.flush()
         _torch().cuda.current_stream(self.device).synchronize()
@@ -397,15 +510,5 @@ class ShardedB200Backend(object):
     def close(self):
         if getattr(self, "ptr", None) is None:
             return
-        torch = _torch()
-        torch.cuda.synchronize()
-        self._sync_all()
-        torch.cuda.synchronize()
-        for pp in self.peers.values():
-            self.L.qipb_ipc_close(self.ctx, pp)
-        self.peers = {}
-        self.dist.barrier()
-        self.eng.state = None
-        self.L.qipb_dev_free(self.ctx, self.ptr)
-        self.ptr = None
+        self._release_shard()
         self.eng.close()

@@ -63,6 +63,21 @@ def main():
             g.func_apply([0, 5, 2], [1, 8], f)
             c.func_apply([0, 5, 2], [1, 8], f)
             check(name + " func", g.get_state(), c.get_state())
+            check(name + " range", g.get_relative_range(100, 2300), c.get_relative_range(100, 2300))
+            g.addto_relative_range(2040, 2056, np.arange(16) * (0.5 + 0.25j))
+            c.addto_relative_range(2040, 2056, np.arange(16) * (0.5 + 0.25j))
+            g.overwrite_relative_range(5, 9, np.array([1, 2, 3, 4], dtype=np.complex128))
+            c.overwrite_relative_range(5, 9, np.array([1, 2, 3, 4], dtype=np.complex128))
+            check(name + " range writes", g.get_state(), c.get_state())
+            random.seed(4)
+            mg, pg = g.reduce_measure(np.array([0, 7, 3], dtype=np.int32))
+            random.seed(4)
+            mc, pc = c.reduce_measure([0, 7, 3])
+            assert mg == mc and abs(pg - pc) < 1e-12 * max(1.0, pc) and g.n == c.n == n - 3, (mg, mc, pg, pc)
+            check(name + " reduced", g.get_state(), c.get_state())
+            g.kronselect_dot({0: H2, (1, 8): CMat(X2)})
+            c.kronselect_dot({0: H2, (1, 8): CMat(X2)})
+            check(name + " after reduce", g.get_state(), c.get_state())
             if rank == 0:
                 print("OK %-14s fuse=%-5s err=%.1e exchanges=%d peer_gates=%d" % (name, fuse, err, g.stats["exchanges"], g.stats["peer_gates"]))
             g.close()
