@@ -37,7 +37,8 @@ class _RawCuda(object):
 
 
 class ShardedB200Backend(object):
-    def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6):
+    def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6,
+                 peer_gates: bool = False, lazy_layout: bool = True):
         torch = _torch()
         import torch.distributed as dist
         if not dist.is_initialized():
@@ -60,6 +61,9 @@ class ShardedB200Backend(object):
         self.layout = sp.Layout(self.n, self.G)
         self.queue: List[Gate] = []
         self.fuse = fuse
+        self.peer_gates = peer_gates
+        self.lazy_layout = lazy_layout
+        self._pending_init = None       # (groups, feeds): the state is built at the first flush
         self.stats = {"gates": 0, "exchanges": 0, "peer_gates": 0, "nvlink_bytes_out": 0}
         # shard memory comes from cudaMalloc (qipb_dev_alloc) so that its IPC handle maps it exactly
         ptr = ctypes.c_void_p()
@@ -127,12 +131,31 @@ class ShardedB200Backend(object):
         return b
 
     def _init_state(self, index_groups, feed_list):
-        torch = _torch()
-        n, nl = self.n, self.nl
+        n = self.n
         groups = [[int(q) for q in g] for g in index_groups]
         flat = [q for g in groups for q in g]
         if len(groups) != len(feed_list) or len(set(flat)) != len(flat) or any(not (0 <= q < n) for q in flat):
             raise ValueError("bad feed groups")
+        for g, f in zip(groups, feed_list):
+            if not isinstance(f, (int, np.integer)) and np.asarray(f).reshape(-1).shape[0] != 2 ** len(g):
+                raise ValueError("feed length does not match 2**len(group)")
+        self._pending_init = (groups, list(feed_list))
+        if not self.lazy_layout:
+            self._materialise()
+
+    def _materialise(self):
+        """Build the initial state.  Deferred to the first flush so that the shard layout can be chosen
+        from the queued gates (qubits needed non-diagonally last go on the rank bits)."""
+        if self._pending_init is None:
+            return
+        torch = _torch()
+        groups, feed_list = self._pending_init
+        self._pending_init = None
+        n, nl = self.n, self.nl
+        flat = [q for g in groups for q in g]
+        if self.lazy_layout:
+            sp.choose_initial_layout(self.queue, self.layout)
+        pos = self.layout.pos
         self._stream()
         if not groups:
             _lib.check(self.L.qipb_init_basis(self.ctx, self.ptr, nl, self.code, 0 if self.rank == 0 else -1))
@@ -151,10 +174,10 @@ class ShardedB200Backend(object):
         zero_mask = 0
         for q in range(n):
             if q not in flat:
-                zero_mask |= 1 << (n - 1 - q)
+                zero_mask |= 1 << pos[q]
         _lib.check(self.L.qipb_init_kron(self.ctx, self.ptr, nl, self.code, len(groups),
                                          _lib.int_array([len(g) for g in groups]),
-                                         _lib.int_array([n - 1 - q for q in flat]),
+                                         _lib.int_array([pos[q] for q in flat]),
                                          ctypes.c_void_p(dev_feeds.data_ptr()), zero_mask, self.rank))
         self._keep = dev_feeds
 
@@ -241,11 +264,12 @@ class ShardedB200Backend(object):
             self._run_local(batch)
 
     def flush(self) -> None:
+        self._materialise()
         if not self.queue:
             return
         gates = list(self.queue)
         self.queue = []
-        self._execute(sp.schedule(gates, self.layout))
+        self._execute(sp.schedule(gates, self.layout, peer_gates=self.peer_gates))
 
     def func_apply(self, reg1_indices, reg2_indices, func, input_offset: int = 0, output_offset: int = 0) -> None:
         torch = _torch()

@@ -124,8 +124,38 @@ def lower_for_rank(pg: PhysGate, nl: int, rank: int) -> Optional[BitGate]:
     return BitGate("matrix", tuple(pg.bits[j] for j in keep), pg.ctrl_mask & lowmask, np.diag(sub), True)
 
 
-def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8) -> List[object]:
-    """Turn logical gates into rank-independent actions; `lay` is updated in place."""
+def choose_initial_layout(gates: Sequence[Gate], lay: Layout) -> None:
+    """Before the state exists, put on the rank bits the qubits whose first NON-DIAGONAL use comes
+    latest in the queued gates (diagonal gates and controls never need a qubit to be local).  A QFT then
+    runs its first n-G Hadamards without any exchange.  `lay` is permuted in place."""
+    if lay.G == 0:
+        return
+    first = {}
+    for i, g in enumerate(gates):
+        if g.kind == "swap":
+            used = list(g.targets) if g.controls else []       # un-controlled swaps are relabels
+        else:
+            used = [] if (g.diagonal or g.k == 0) else list(g.targets)
+        for q in used:
+            first.setdefault(q, i)
+    never = len(gates) + 1
+    order = sorted(range(lay.n), key=lambda q: (-first.get(q, never), q))    # latest first use first
+    want_global = order[:lay.G]
+    # keep the canonical layout unless it is strictly worse
+    canon_global = [q for q in range(lay.n) if lay.is_global(q)]
+    if sorted(first.get(q, never) for q in canon_global) == sorted(first.get(q, never) for q in want_global):
+        return
+    for q in want_global:
+        if not lay.is_global(q):
+            victim = next(v for v in canon_global if v not in want_global and lay.is_global(v))
+            lay.swap_qubits(q, victim)
+
+
+def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates: bool = False) -> List[object]:
+    """Turn logical gates into rank-independent actions; `lay` is updated in place.
+    peer_gates: run a dense 1-qubit gate on a rank bit as one fused compute+exchange kernel when its
+    qubit is never needed locally afterwards.  Off by default: the fused kernel moves one shard per
+    direction, an Exchange followed by a local gate only half a shard (measured on B200)."""
     nl = lay.nl
     actions: List[object] = []
 
@@ -149,7 +179,7 @@ def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8) -> List[ob
         need = uses[i]
         glob = [q for q in need if lay.is_global(q)]
         if glob and lay.G > 0:
-            if (g.kind == "matrix" and g.k == 1 and next_use(glob[0], i + 1) >= (1 << 30)):
+            if (peer_gates and g.kind == "matrix" and g.k == 1 and next_use(glob[0], i + 1) >= (1 << 30)):
                 cm = 0
                 for q in g.controls:
                     cm |= 1 << lay.pos[q]

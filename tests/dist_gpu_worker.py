@@ -40,8 +40,8 @@ def main():
     cases = {"layered": list(layered_stream(n, 3, 2)), "qfft": list(qfft_stream(n)), "mixed": extra,
              "layered+qfft": list(layered_stream(n, 1, 9)) + list(qfft_stream(n))}
     for name, ops_ in cases.items():
-        for fuse in (True, False):
-            g = ShardedB200Backend.make_state(n, groups, feeds, statetype=np.complex128, fuse=fuse)
+        for fuse, peer in ((True, False), (False, False), (True, True)):
+            g = ShardedB200Backend.make_state(n, groups, feeds, statetype=np.complex128, fuse=fuse, peer_gates=peer)
             c = orc.OracleBackend.make_state(n, groups, feeds)
             for mats in ops_:
                 g.kronselect_dot(mats)
@@ -79,7 +79,7 @@ def main():
             c.kronselect_dot({0: H2, (1, 8): CMat(X2)})
             check(name + " after reduce", g.get_state(), c.get_state())
             if rank == 0:
-                print("OK %-14s fuse=%-5s err=%.1e exchanges=%d peer_gates=%d" % (name, fuse, err, g.stats["exchanges"], g.stats["peer_gates"]))
+                print("OK %-14s fuse=%-5s peer=%-5s err=%.1e exchanges=%d peer_gates=%d" % (name, fuse, peer, err, g.stats["exchanges"], g.stats["peer_gates"]))
             g.close()
     # kron-product init per shard (rank bits select the top sub-indices) and empty feed
     groups2 = [[7, 0, 5], [1], [11, 10]]

@@ -64,20 +64,39 @@ def test_layered_circuit_on_virtual_shards(gbits, seed):
         assert any(isinstance(a, (sp.Exchange, sp.PeerGate1)) for a in actions)
 
 
+def _permuted(psi, lay):
+    """The state as it is laid out physically: bit lay.pos[q] of the physical index is qubit q."""
+    n = lay.n
+    idx = np.arange(2 ** n, dtype=np.int64)
+    logical = np.zeros(2 ** n, dtype=np.int64)
+    for q in range(n):
+        logical |= ((idx >> lay.pos[q]) & 1) << (n - 1 - q)
+    return psi[logical]
+
+
 @pytest.mark.parametrize("gbits", [1, 2, 3])
-def test_qft_on_virtual_shards_needs_few_exchanges(gbits):
+@pytest.mark.parametrize("mode", ["lazy_layout", "peer_gates", "plain"])
+def test_qft_on_virtual_shards_needs_few_exchanges(gbits, mode):
     n = 10
     rng = np.random.default_rng(gbits)
     psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
     psi /= np.linalg.norm(psi)
     gates = logical_gates(qfft_stream(n), n)
     lay = sp.Layout(n, gbits)
-    actions = sp.schedule(gates, lay)
+    if mode == "lazy_layout":
+        sp.choose_initial_layout(gates, lay)        # the last qubits to be Hadamard-ed go on the rank bits
+        assert sorted(q for q in range(n) if lay.is_global(q)) == list(range(n - gbits, n))
+    start = _permuted(psi, lay)
+    actions = sp.schedule(gates, lay, peer_gates=(mode == "peer_gates"))
     moves = [a for a in actions if isinstance(a, (sp.Exchange, sp.PeerGate1))]
-    # only the H gates on the gbits rank qubits move data; every C-phase is communication-free and
-    # the final bit reversal is a relabel
-    assert len(moves) == gbits and all(isinstance(a, sp.PeerGate1) for a in moves)
-    vs = shardsim.VirtualShards(psi, gbits)
+    # every C-phase is communication-free and the final bit reversal is a relabel
+    if mode == "lazy_layout":
+        assert len(moves) == gbits and all(isinstance(a, sp.Exchange) for a in moves)
+    elif mode == "peer_gates":
+        assert len(moves) == gbits and all(isinstance(a, sp.PeerGate1) for a in moves)
+    else:
+        assert len(moves) <= 2 * gbits and all(isinstance(a, sp.Exchange) for a in moves)
+    vs = shardsim.VirtualShards(start, gbits)
     vs.run(actions)
     vs.run(sp.canonicalise(lay))
     want = np.fft.ifft(psi) * np.sqrt(2 ** n)
