@@ -219,9 +219,17 @@ class ShardedB200Backend(object):
         half = 1 << (self.nl - 2) if self.nl >= 2 else 0
         total = 1 << (self.nl - 1)
         begin, count = (0, total - half) if my_g == 0 else (total - half, half)
+        torch = _torch()
         self._sync_all()
+        if self.eng.profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(self.L.qipb_peer_swap_bit(self.ctx, self.ptr, self.peers[partner], self.nl, self.code, a.lpos, my_g,
                                              begin, count))
+        if self.eng.profile is not None:
+            e1.record()
+            # NVLink bytes leaving this GPU: half a shard (reads served to the partner + writes to it)
+            self.eng.profile.append(("peer_swap_bit_kernel[nvlink]", float(self.amp_bytes * total), e0, e1))
         self._sync_all()
         self.stats["exchanges"] += 1
         self.stats["nvlink_bytes_out"] += self.amp_bytes * total
