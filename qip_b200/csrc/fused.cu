@@ -20,14 +20,13 @@
 #include <vector>
 #include "common.cuh"
 #include "../../include/qip_b200.h"
+#include "fused_shared.cuh"
 
 namespace qipb {
 
 #define FUSED_THREADS 256
 #define FUSED_MAX_INS 12
 #define FUSED_MAX_OPS 96          // device ops per launch (a pass with more is split into several launches)
-#define FUSED_OUT_CELLS 4
-#define FUSED_LO_BITS 6           // tile-local bits 0..5 form the 'lo' table cell, the rest the 'hi' cell
 
 struct DevGate {
     unsigned char k;        // target bits in total (0..2)
@@ -43,13 +42,6 @@ struct DevGate {
     double2 m[16];
 };
 
-// diag == 2: a run of diagonal gates folded into per-cell phase tables (stored over DevGate::m)
-struct StageInfo {
-    u32 tab_off;                              // offset of T_lo in the table buffer (double2 units)
-    unsigned char nout;                       // number of cells made of bits outside the tile
-    unsigned char cn[FUSED_OUT_CELLS];        // bits per outside cell
-    unsigned char cb[FUSED_OUT_CELLS][7];     // their state-index positions, ascending
-};
 static_assert(sizeof(StageInfo) <= sizeof(double2) * 16, "StageInfo must fit over DevGate::m");
 
 struct FusedArgs {
@@ -61,52 +53,9 @@ struct FusedArgs {
 };
 static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel parameter space");
 
-// ---- mbarrier / bulk-copy (TMA 1-D) primitives ------------------------------------------------
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(void *bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void *bar, u32 parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, void *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u32 bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
 __device__ __forceinline__ u32 expand_local(u32 w, const DevGate &g) {
     for (int q = 0; q < g.nins; ++q) w += (w & g.nmask[q]);      // insert a zero bit at each fixed position
     return w | g.in_or;
-}
-
-// Product of a stage's outside-cell tables at this tile's base index (uniform per tile).
-__device__ __forceinline__ double2 stage_scalar(const StageInfo &si, const double2 *__restrict__ T, u64 base, u32 nlo, u32 nhi) {
-    double2 S = make_double2(1.0, 0.0);
-    const double2 *To = T + nlo + nhi;
-    for (int c = 0; c < si.nout; ++c) {
-        u32 idx = 0;
-        for (int j = 0; j < si.cn[c]; ++j) idx |= (u32)((base >> si.cb[c][j]) & 1ull) << j;
-        S = cmul<double2>(S, To[idx]);
-        To += 1u << si.cn[c];
-    }
-    return S;
 }
 
 template <typename A>
@@ -389,18 +338,8 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
 }
 
 
+
 // ---- host side: folding runs of diagonal gates into stages -------------------------------------
-typedef std::complex<double> cplx;
-
-struct Op {
-    bool stage;
-    int gate;                 // !stage: index into the caller's gate list
-    u64 common;               // stage: control bits shared by every gate of the stage
-    u32 tab_off;              // stage: offset of its tables in the table buffer
-    int nout;
-    std::vector<int> cells[FUSED_OUT_CELLS];
-};
-
 static bool post_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -410,7 +349,7 @@ static bool post_enabled() {
     return v != 0;
 }
 
-static bool stages_enabled() {
+bool stages_enabled() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("QIPB_FUSED_STAGES");          // tuning knob for profiling runs
@@ -442,8 +381,8 @@ static int residual_cell(const qipb_gate &g, u64 common, const CellMap &cm) {
     return cell;
 }
 
-static void build_stages(const qipb_gate *gates, const std::vector<int> &run, int nbits, int tb, const int *local_of,
-                         u64 tmask, std::vector<Op> &ops, std::vector<cplx> &tables) {
+void build_stages(const qipb_gate *gates, const std::vector<int> &run, int nbits, int tb, const int *local_of,
+                  u64 tmask, std::vector<Op> &ops, std::vector<cplx> &tables, int min_run) {
     CellMap cm;
     for (int b = 0; b < 64; ++b) { cm.cell_of[b] = -1; cm.idx_in_cell[b] = 0; }
     const int lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
@@ -480,7 +419,7 @@ static void build_stages(const qipb_gate *gates, const std::vector<int> &run, in
             common = nc;
             ++end;
         }
-        if (end - pos < 3 || residual_cell(gates[run[pos]], common, cm) == -2) {
+        if ((int)(end - pos) < min_run || residual_cell(gates[run[pos]], common, cm) == -2) {
             // too short to pay for tables (or not table-izable at all): keep the gate as it is
             Op o;
             o.stage = false;
@@ -531,6 +470,36 @@ static void build_stages(const qipb_gate *gates, const std::vector<int> &run, in
     }
 }
 
+// Stage tables: pinned staging ring -> device buffer, stream ordered.
+int upload_tables(qipb_ctx *ctx, const std::vector<cplx> &tables, const double2 **out) {
+    *out = nullptr;
+    if (tables.empty()) return QIPB_OK;
+    const size_t need = tables.size();
+    if (ctx->tab_cap < need) {
+        QIPB_CUDA(cudaStreamSynchronize(ctx->stream));
+        size_t cap = 1u << 16;
+        while (cap < need) cap <<= 1;
+        if (ctx->tab_dev) QIPB_CUDA(cudaFree(ctx->tab_dev));
+        ctx->tab_dev = nullptr;
+        QIPB_CUDA(cudaMalloc(&ctx->tab_dev, cap * sizeof(double2)));
+        for (int i = 0; i < 4; ++i) {
+            if (ctx->tab_host[i]) QIPB_CUDA(cudaFreeHost(ctx->tab_host[i]));
+            ctx->tab_host[i] = nullptr;
+            QIPB_CUDA(cudaMallocHost(&ctx->tab_host[i], cap * sizeof(double2)));
+            if (!ctx->tab_ev[i]) QIPB_CUDA(cudaEventCreateWithFlags(&ctx->tab_ev[i], cudaEventDisableTiming));
+        }
+        ctx->tab_cap = cap;
+    }
+    const int slot = ctx->tab_slot;
+    ctx->tab_slot = (slot + 1) & 3;
+    QIPB_CUDA(cudaEventSynchronize(ctx->tab_ev[slot]));      // the copy that last used this slot is done
+    memcpy(ctx->tab_host[slot], tables.data(), need * sizeof(double2));
+    QIPB_CUDA(cudaMemcpyAsync(ctx->tab_dev, ctx->tab_host[slot], need * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    QIPB_CUDA(cudaEventRecord(ctx->tab_ev[slot], ctx->stream));
+    *out = ctx->tab_dev;
+    return QIPB_OK;
+}
+
 }  // namespace qipb
 
 using namespace qipb;
@@ -560,13 +529,22 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     }
     f.lowrun = 0;
     while (f.lowrun < ntile_bits && tile_bits[f.lowrun] == f.lowrun) f.lowrun++;
+    if (fused3_enabled()) {                 // register-resident kernel (fused3.cu); -1 = not eligible
+        for (int gi = 0; gi < ngates; ++gi) {
+            const qipb_gate &s = gates[gi];
+            QIPB_REQUIRE(s.k >= 0 && s.k <= 2, "fused gate %d: k=%d unsupported", gi, s.k);
+            for (int j = 0; j < s.k; ++j) QIPB_REQUIRE(s.bits[j] >= 0 && s.bits[j] < nbits, "fused gate %d: bad target bit", gi);
+        }
+        const int rc3 = fused3_apply(ctx, state, nbits, dtype, ntile_bits, tile_bits, local_of, tmask, ngates, gates);
+        if (rc3 >= 0) return rc3;
+    }
     // ---- pass 1: validate, and fold runs of diagonal gates into stages ----
     std::vector<Op> ops;
     std::vector<cplx> tables;
     {
         std::vector<int> run;
         auto flush_run = [&]() {
-            if (!run.empty()) build_stages(gates, run, nbits, ntile_bits, local_of, tmask, ops, tables);
+            if (!run.empty()) build_stages(gates, run, nbits, ntile_bits, local_of, tmask, ops, tables, 3);
             run.clear();
         };
         for (int gi = 0; gi < ngates; ++gi) {
@@ -594,32 +572,9 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
         }
         flush_run();
     }
-    // ---- stage tables: pinned staging ring -> device buffer, stream ordered ----
-    f.tables = nullptr;
-    if (!tables.empty()) {
-        const size_t need = tables.size();
-        if (ctx->tab_cap < need) {
-            QIPB_CUDA(cudaStreamSynchronize(ctx->stream));
-            size_t cap = 1u << 16;
-            while (cap < need) cap <<= 1;
-            if (ctx->tab_dev) QIPB_CUDA(cudaFree(ctx->tab_dev));
-            ctx->tab_dev = nullptr;
-            QIPB_CUDA(cudaMalloc(&ctx->tab_dev, cap * sizeof(double2)));
-            for (int i = 0; i < 4; ++i) {
-                if (ctx->tab_host[i]) QIPB_CUDA(cudaFreeHost(ctx->tab_host[i]));
-                ctx->tab_host[i] = nullptr;
-                QIPB_CUDA(cudaMallocHost(&ctx->tab_host[i], cap * sizeof(double2)));
-                if (!ctx->tab_ev[i]) QIPB_CUDA(cudaEventCreateWithFlags(&ctx->tab_ev[i], cudaEventDisableTiming));
-            }
-            ctx->tab_cap = cap;
-        }
-        const int slot = ctx->tab_slot;
-        ctx->tab_slot = (slot + 1) & 3;
-        QIPB_CUDA(cudaEventSynchronize(ctx->tab_ev[slot]));      // the copy that last used this slot is done
-        memcpy(ctx->tab_host[slot], tables.data(), need * sizeof(double2));
-        QIPB_CUDA(cudaMemcpyAsync(ctx->tab_dev, ctx->tab_host[slot], need * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
-        QIPB_CUDA(cudaEventRecord(ctx->tab_ev[slot], ctx->stream));
-        f.tables = ctx->tab_dev;
+    {
+        int rc = upload_tables(ctx, tables, &f.tables);
+        if (rc) return rc;
     }
 
     // ---- pass 2: device descriptors, FUSED_MAX_OPS per launch ----
