@@ -59,7 +59,7 @@ class DeviceState(object):
 class B200Backend(object):
     """StateType implementation on one B200 (see module docstring)."""
 
-    def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6,
+    def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
                  strategy: str = "auto", relabel_swaps: bool = True):
         torch = _torch()
         self.L = _lib.load()
@@ -75,8 +75,9 @@ class B200Backend(object):
         self.np_dtype = np.dtype(dtype)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.fuse = fuse
+        import os
         self.tile_bits = tile_bits
-        self.min_low_bits = min_low_bits
+        self.min_low_bits = int(os.environ.get("QIPB_MIN_LOW_BITS", min_low_bits))     # tuning knob for profiling runs
         self.strategy = strategy
         # logical qubit -> index bit.  Canonical is n-1-q; an un-controlled Swap only permutes this map
         # (free) and the state is brought back to canonical order when it is read out in index order.

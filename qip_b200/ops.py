@@ -390,7 +390,7 @@ def _ncoef(g: BitGate) -> int:
 
 
 def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_bits: int = 12,
-                min_low_bits: int = 6, max_gates: int = 280, enable: bool = True, max_coefs: int = 1 << 30) -> List[Pass]:
+                min_low_bits: int = 7, max_gates: int = 280, enable: bool = True, max_coefs: int = 1 << 30) -> List[Pass]:
     """Greedy, order-preserving fusion.  A group grows while the union of the bits its non-diagonal
     gates need, together with the `min_low_bits` lowest bits, still fits in a tile; a group is run
     fused only when that moves fewer bytes than launching its gates one by one."""
@@ -461,7 +461,7 @@ def pass_cost(p: Pass, nbits: int, amp_bytes: int) -> float:
 
 
 def plan(gates: Sequence[Gate], n: int, amp_bytes: int = 16, fuse: bool = True, tile_bits: int = 12,
-         min_low_bits: int = 6, strategy: str = "auto"):
+         min_low_bits: int = 7, strategy: str = "auto"):
     """Logical gates -> (list[Pass], name of the chosen strategy)."""
     if not fuse:
         return [Pass(False, [lower(g, n)]) for g in gates], "unfused"

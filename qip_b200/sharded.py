@@ -37,7 +37,7 @@ class _RawCuda(object):
 
 
 class ShardedB200Backend(object):
-    def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 6,
+    def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
                  peer_gates: bool = False, lazy_layout: bool = True):
         torch = _torch()
         import torch.distributed as dist
