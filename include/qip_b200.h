@@ -157,6 +157,9 @@ int qipb_add_range(qipb_ctx *ctx, void *state, int dtype, uint64_t start, uint64
  *   amplitudes whose bit lbit != my_gbit trade places with the partner's amplitudes whose bit lbit
  *   == my_gbit.  The 2^(nbits-1) pairs are indexed by w (the local index with bit lbit removed);
  *   the two ranks of a pair each process a disjoint [w_begin, w_begin+count) half.
+ * qipb_peer_remap: g (1..3) rank bits <-> g local bits in ONE kernel over up to 7 peers: peers[b] is the
+ *   mapped shard of the rank whose g rank bits have value b (entry my_value is ignored), lbits[t] the
+ *   local bit paired with value bit t.  Moves (1 - 2^-g) of a shard per direction.
  * qipb_peer_gate1: the fused compute+exchange kernel for a 1-qubit gate whose target is a GLOBAL
  *   (rank) bit: for count amplitudes, (lo, hi) <- mat * (lo, hi) where `lo` lives on the shard
  *   whose rank bit is 0 and `hi` on its partner.  The caller that owns `local` passes
@@ -168,6 +171,8 @@ int qipb_peer_swap(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t l
                    uint64_t peer_off, uint64_t count);
 int qipb_peer_swap_bit(qipb_ctx *ctx, void *local, void *peer, int nbits, int dtype, int lbit,
                        int my_gbit, uint64_t w_begin, uint64_t count);
+int qipb_peer_remap(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g,
+                    const int *lbits, int my_value);
 int qipb_peer_gate1(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t off,
                     uint64_t count, const double *mat, int local_is_hi, uint64_t ctrl_mask);
 

@@ -53,6 +53,49 @@ __global__ void __launch_bounds__(256) peer_swap_bit_kernel(A *__restrict__ loca
         if (live[u]) { local[li[u]] = b[u]; peer[pi[u]] = a[u]; }
 }
 
+// g rank bits <-> g local bits in ONE kernel.  `a` = this rank's value on the g rank bits; for every
+// other value b the sub-block of local indices whose g local bits equal b trades places with the
+// sub-block "local bits == a" of the rank whose rank bits equal b.  The 2^(nbits-g) pairs of a
+// sub-block pair are indexed by w; the rank with the smaller value handles the first half of w, the
+// other one the second half, so every link direction and every GPU carries the same load:
+// (1 - 2^-g) of a shard per direction in total, against g/2 shards for g pairwise swaps.
+struct RemapArgs {
+    void *peers[8];               // indexed by b
+    u64 half;                     // 2^(nbits - g - 1)
+    int g, a;
+    unsigned char lbit[4];        // the local bit positions, lbit[t] pairs with value bit t
+    unsigned char ins[4];         // the same positions ascending (for zero insertion)
+};
+
+template <typename A, int U>
+__global__ void __launch_bounds__(256) peer_remap_kernel(A *__restrict__ local, const __grid_constant__ RemapArgs r) {
+    const int slot = blockIdx.y;
+    const int b = slot < r.a ? slot : slot + 1;
+    A *__restrict__ peer = reinterpret_cast<A *>(r.peers[b]);
+    u64 lsel = 0, psel = 0;
+    for (int t = 0; t < r.g; ++t) {
+        lsel |= (u64)((b >> t) & 1) << r.lbit[t];
+        psel |= (u64)((r.a >> t) & 1) << r.lbit[t];
+    }
+    const u64 w0 = r.a < b ? 0 : r.half;
+    A x[U], y[U];
+    u64 li[U], pi[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const u64 t = ((u64)blockIdx.x * U + u) * blockDim.x + threadIdx.x;
+        live[u] = t < r.half;
+        u64 base = w0 + t;
+        for (int q = 0; q < r.g; ++q) base = insert_zero(base, r.ins[q]);
+        li[u] = base | lsel;
+        pi[u] = base | psel;
+        if (live[u]) { x[u] = local[li[u]]; y[u] = peer[pi[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (live[u]) { local[li[u]] = y[u]; peer[pi[u]] = x[u]; }
+}
+
 struct PeerGateArgs {
     u64 count;
     u64 ctrl_mask;        // local-index bits that must be 1
@@ -142,6 +185,40 @@ extern "C" int qipb_peer_swap_bit(qipb_ctx *ctx, void *local, void *peer, int nb
     QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
     if (dtype == QIPB_C128) peer_swap_bit_kernel<double2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)local, (double2 *)peer, lbit, my_gbit, w_begin, count);
     else if (dtype == QIPB_C64) peer_swap_bit_kernel<float2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)local, (float2 *)peer, lbit, my_gbit, w_begin, count);
+    else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
+    ctx->launches++;
+    QIPB_CUDA(cudaGetLastError());
+    return QIPB_OK;
+}
+
+extern "C" int qipb_peer_remap(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g,
+                               const int *lbits, int my_value) {
+    QIPB_REQUIRE(ctx && local && peers && lbits, "null argument");
+    QIPB_REQUIRE(g >= 1 && g <= 3 && nbits > g && nbits <= 40 && my_value >= 0 && my_value < (1 << g), "bad peer_remap arguments");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    RemapArgs r;
+    memset(&r, 0, sizeof(r));
+    r.g = g;
+    r.a = my_value;
+    r.half = 1ull << (nbits - g - 1);
+    u64 seen = 0;
+    for (int t = 0; t < g; ++t) {
+        QIPB_REQUIRE(lbits[t] >= 0 && lbits[t] < nbits && !((seen >> lbits[t]) & 1ull), "bad local bit %d", lbits[t]);
+        seen |= 1ull << lbits[t];
+        r.lbit[t] = (unsigned char)lbits[t];
+    }
+    int n = 0;
+    for (int b = 0; b < nbits; ++b)
+        if ((seen >> b) & 1ull) r.ins[n++] = (unsigned char)b;
+    for (int b = 0; b < (1 << g); ++b) {
+        QIPB_REQUIRE(b == my_value || peers[b], "missing peer pointer for value %d", b);
+        r.peers[b] = peers[b];
+    }
+    const u64 bx = (r.half + 256ull * 4 - 1) / (256ull * 4);
+    QIPB_REQUIRE(bx <= 0x7fffffffull, "grid too large");
+    dim3 grid((unsigned)bx, (unsigned)((1 << g) - 1));
+    if (dtype == QIPB_C128) peer_remap_kernel<double2, 4><<<grid, 256, 0, ctx->stream>>>((double2 *)local, r);
+    else if (dtype == QIPB_C64) peer_remap_kernel<float2, 4><<<grid, 256, 0, ctx->stream>>>((float2 *)local, r);
     else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());

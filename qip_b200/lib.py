@@ -20,7 +20,7 @@ EXPORTS = [
     "qipb_launch_count", "qipb_dev_alloc", "qipb_dev_free", "qipb_memcpy_h2d", "qipb_memcpy_d2h",
     "qipb_init_basis", "qipb_init_kron", "qipb_apply_matrix", "qipb_apply_swap", "qipb_apply_fused",
     "qipb_func_xor", "qipb_probabilities", "qipb_collapse", "qipb_reduce", "qipb_add_range",
-    "qipb_ipc_export", "qipb_ipc_open", "qipb_ipc_close", "qipb_peer_swap", "qipb_peer_swap_bit", "qipb_peer_gate1",
+    "qipb_ipc_export", "qipb_ipc_open", "qipb_ipc_close", "qipb_peer_swap", "qipb_peer_swap_bit", "qipb_peer_remap", "qipb_peer_gate1",
 ]
 
 
@@ -86,6 +86,7 @@ def load():
     L.qipb_ipc_close.argtypes = [vp, vp]
     L.qipb_peer_swap.argtypes = [vp, vp, vp, ci, u64, u64, u64]
     L.qipb_peer_swap_bit.argtypes = [vp, vp, vp, ci, ci, ci, ci, u64, u64]
+    L.qipb_peer_remap.argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, i32p, ci]
     L.qipb_peer_gate1.argtypes = [vp, vp, vp, ci, u64, u64, dblp, ci, u64]
     for name in EXPORTS:
         fn = getattr(L, name)

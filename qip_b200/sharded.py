@@ -234,6 +234,36 @@ class ShardedB200Backend(object):
         self.stats["exchanges"] += 1
         self.stats["nvlink_bytes_out"] += self.amp_bytes * total
 
+    def _multi_exchange(self, a: sp.MultiExchange):
+        torch = _torch()
+        g = len(a.pairs)
+        value = 0
+        for t, (gpos, _) in enumerate(a.pairs):
+            value |= ((self.rank >> (gpos - self.nl)) & 1) << t
+        peers = (ctypes.c_void_p * 8)()
+        for b in range(1 << g):
+            if b == value:
+                continue
+            r = self.rank
+            for t, (gpos, _) in enumerate(a.pairs):
+                bit = 1 << (gpos - self.nl)
+                r = (r | bit) if (b >> t) & 1 else (r & ~bit)
+            peers[b] = self.peers[r]
+        self._sync_all()
+        if self.eng.profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(self.L.qipb_peer_remap(self.ctx, self.ptr, peers, self.nl, self.code, g,
+                                          _lib.int_array([l for _, l in a.pairs]), value))
+        nbytes = self.amp_bytes * ((1 << self.nl) - (1 << (self.nl - g)))
+        if self.eng.profile is not None:
+            e1.record()
+            self.eng.profile.append(("peer_remap_kernel[nvlink]", float(nbytes), e0, e1))
+        self._sync_all()
+        self.stats["exchanges"] += 1
+        self.stats["multi_exchanges"] = self.stats.get("multi_exchanges", 0) + 1
+        self.stats["nvlink_bytes_out"] += nbytes
+
     def _peer_gate(self, a: sp.PeerGate1):
         gb = a.gpos - self.nl
         my_g = (self.rank >> gb) & 1
@@ -267,6 +297,8 @@ class ShardedB200Backend(object):
                     batch = []
                     if isinstance(a, sp.Exchange):
                         self._exchange(a)
+                    elif isinstance(a, sp.MultiExchange):
+                        self._multi_exchange(a)
                     else:
                         self._peer_gate(a)
             self._run_local(batch)

@@ -74,6 +74,13 @@ class Exchange:
 
 
 @dataclass
+class MultiExchange:
+    """Several (rank bit, local bit) swaps at once: one all-to-all-class kernel moves (1 - 2^-g) of a
+    shard per direction instead of g/2 shards for g pairwise exchanges."""
+    pairs: List[Tuple[int, int]]     # (gpos, lpos), all positions distinct
+
+
+@dataclass
 class PeerGate1:
     gpos: int
     mat: np.ndarray
@@ -206,7 +213,32 @@ def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates
                 actions.append(Exchange(lay.pos[q], lay.pos[victim]))
                 lay.swap_qubits(q, victim)
         actions.append(Apply(to_phys(g, lay)))
-    return actions
+    return coalesce_exchanges(actions)
+
+
+def coalesce_exchanges(actions: List[object], max_pairs: int = 3) -> List[object]:
+    """Merge runs of consecutive Exchange actions on pairwise distinct positions into MultiExchange."""
+    out: List[object] = []
+    run: List[Exchange] = []
+
+    def flush():
+        if len(run) == 1:
+            out.append(run[0])
+        elif run:
+            out.append(MultiExchange([(e.gpos, e.lpos) for e in run]))
+        run.clear()
+
+    for a in actions:
+        if isinstance(a, Exchange) and len(run) < max_pairs and all(a.gpos != e.gpos and a.lpos != e.lpos for e in run):
+            run.append(a)
+            continue
+        flush()
+        if isinstance(a, Exchange):
+            run.append(a)
+        else:
+            out.append(a)
+    flush()
+    return out
 
 
 def canonicalise(lay: Layout) -> List[object]:
@@ -235,4 +267,4 @@ def canonicalise(lay: Layout) -> List[object]:
         want = lay.n - 1 - q
         if lay.pos[q] != want:
             swap_positions(lay.pos[q], want)
-    return actions
+    return coalesce_exchanges(actions)

@@ -42,7 +42,13 @@ def main(out_path):
             dist.send(snd, partner)
         return recv.numpy()
 
+    expanded = []
     for a in actions:
+        if isinstance(a, sp.MultiExchange):
+            expanded.extend(sp.Exchange(g, l) for g, l in a.pairs)
+        else:
+            expanded.append(a)
+    for a in expanded:
         if isinstance(a, sp.Exchange):
             gb = a.gpos - nl
             my_g = (rank >> gb) & 1

@@ -43,7 +43,14 @@ class VirtualShards(object):
 
     def run(self, actions):
         nl = self.nl
+        expanded = []
         for a in actions:
+            if isinstance(a, sp.MultiExchange):       # same permutation as its pairwise exchanges in sequence
+                expanded.extend(sp.Exchange(g, l) for g, l in a.pairs)
+                self.multi_exchanges = getattr(self, "multi_exchanges", 0) + 1
+            else:
+                expanded.append(a)
+        for a in expanded:
             if isinstance(a, sp.Exchange):
                 gb = a.gpos - nl
                 for r in range(self.P):

@@ -61,7 +61,7 @@ def test_layered_circuit_on_virtual_shards(gbits, seed):
     vs, actions = run_sharded(psi, gates, n, gbits)
     assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-13
     if gbits >= 2:
-        assert any(isinstance(a, (sp.Exchange, sp.PeerGate1)) for a in actions)
+        assert any(isinstance(a, (sp.Exchange, sp.MultiExchange, sp.PeerGate1)) for a in actions)
 
 
 def _permuted(psi, lay):
@@ -88,7 +88,12 @@ def test_qft_on_virtual_shards_needs_few_exchanges(gbits, mode):
         assert sorted(q for q in range(n) if lay.is_global(q)) == list(range(n - gbits, n))
     start = _permuted(psi, lay)
     actions = sp.schedule(gates, lay, peer_gates=(mode == "peer_gates"))
-    moves = [a for a in actions if isinstance(a, (sp.Exchange, sp.PeerGate1))]
+    moves = []
+    for a in actions:
+        if isinstance(a, sp.MultiExchange):
+            moves.extend(sp.Exchange(g, l) for g, l in a.pairs)
+        elif isinstance(a, (sp.Exchange, sp.PeerGate1)):
+            moves.append(a)
     # every C-phase is communication-free and the final bit reversal is a relabel
     if mode == "lazy_layout":
         assert len(moves) == gbits and all(isinstance(a, sp.Exchange) for a in moves)
@@ -114,12 +119,12 @@ def test_rank_resolved_controls_diagonals_and_relabels_need_no_exchange():
     gates = logical_gates(stream, n)
     lay = sp.Layout(n, gbits)
     actions = sp.schedule(gates, lay)
-    assert not any(isinstance(a, (sp.Exchange, sp.PeerGate1)) for a in actions)
+    assert not any(isinstance(a, (sp.Exchange, sp.MultiExchange, sp.PeerGate1)) for a in actions)
     psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
     vs = shardsim.VirtualShards(psi, gbits)
     vs.run(actions)
     fix = sp.canonicalise(lay)
-    assert any(isinstance(a, sp.Exchange) for a in fix)          # the relabels are paid for at read-out only
+    assert any(isinstance(a, (sp.Exchange, sp.MultiExchange)) for a in fix)   # the relabels are paid for at read-out only
     vs.run(fix)
     assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-13
 
@@ -167,3 +172,16 @@ def test_two_process_gloo_shards_match_oracle(tmp_path):
     for mats in list(layered_stream(n, 2, 7)) + list(qfft_stream(n)):
         c.kronselect_dot(mats)
     assert float(np.max(np.abs(got - c.get_state()))) <= 1e-12
+
+
+def test_consecutive_exchanges_coalesce_into_one_remap():
+    acts = [sp.Exchange(9, 3), sp.Exchange(8, 5), sp.Exchange(10, 6), sp.Exchange(9, 2), sp.LocalSwap(0, 1), sp.Exchange(8, 4)]
+    out = sp.coalesce_exchanges(acts)
+    assert isinstance(out[0], sp.MultiExchange) and out[0].pairs == [(9, 3), (8, 5), (10, 6)]
+    assert isinstance(out[1], sp.Exchange) and isinstance(out[2], sp.LocalSwap) and isinstance(out[3], sp.Exchange)
+    # a batch of rank qubits needed at once (layered circuit on 8 shards) is ONE remap
+    n, gbits = 10, 3
+    gates = logical_gates(layered_stream(n, 2, 5), n)
+    lay = sp.Layout(n, gbits)
+    actions = sp.schedule(gates, lay)
+    assert any(isinstance(a, sp.MultiExchange) and len(a.pairs) >= 2 for a in actions)
