@@ -53,193 +53,285 @@ struct FusedArgs {
 };
 static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel parameter space");
 
-__device__ __forceinline__ u32 expand_local(u32 w, const DevGate &g) {
-    for (int q = 0; q < g.nins; ++q) w += (w & g.nmask[q]);      // insert a zero bit at each fixed position
-    return w | g.in_or;
+// ---- device side --------------------------------------------------------------------------------
+// Every gate is one sweep over the tile in shared memory.  The sweeps are specialised on the number
+// of fixed tile-local positions (NINS: in-tile targets + in-tile controls), so that the index
+// expansion is a handful of ALU instructions on masks held in (uniform) registers, and the matrix
+// coefficients are read from the kernel-parameter bank with warp-uniform addresses: the compiler
+// keeps them in uniform registers / feeds them to DFMA directly, so the inner loops are
+// LDS + DFMA + STS and nothing else (the first version re-loaded 24 coefficients per group with
+// indexed LDC and was issue bound at ~0.37 of the FP64 / shared-memory limit).
+
+// Sweep loops: `count` work items over the CTA's threads.  UNI (count is a multiple of the CTA size)
+// gives the loop a warp-uniform trip count; with a possibly divergent exit condition ptxas stops
+// treating the descriptor index as uniform and falls back to indexed LDC loads inside the loops.
+#define QIPB_SWEEP(var, count) \
+    for (u32 it_ = 0, nit_ = UNI ? (count) / FUSED_THREADS : ((count) + FUSED_THREADS - 1) / FUSED_THREADS, var = tid; \
+         it_ < nit_ && (UNI || var < (count)); ++it_, var += FUSED_THREADS)
+
+// matrix coefficient in the amplitude's precision
+template <typename A> struct Cf { typename amp_traits<A>::real x, y; };
+template <typename A> __device__ __forceinline__ Cf<A> cf(const double2 m) {
+    typedef typename amp_traits<A>::real R;
+    Cf<A> c;
+    c.x = (R)m.x;
+    c.y = (R)m.y;
+    return c;
+}
+template <typename A> __device__ __forceinline__ A cmulc(const Cf<A> m, const A a) {
+    A r;
+    r.x = m.x * a.x - m.y * a.y;
+    r.y = m.x * a.y + m.y * a.x;
+    return r;
+}
+template <typename A> __device__ __forceinline__ void cfmac(A &acc, const Cf<A> m, const A a) {
+    acc.x = fma(m.x, a.x, acc.x);
+    acc.x = fma(-m.y, a.y, acc.x);
+    acc.y = fma(m.x, a.y, acc.y);
+    acc.y = fma(m.y, a.x, acc.y);
 }
 
-template <typename A>
-__device__ __forceinline__ void run_gate(A *tile, const DevGate &g, const double2 *__restrict__ tables, u64 base, int tb,
-                                         u32 tsize, int tid) {
-    if ((base & g.out_ctrl) != g.out_ctrl) return;             // uniform per tile
-    const u32 ngroups = tsize >> g.nins;
-    if (g.diag) {
-        // effective diagonal over the in-tile targets; targets outside the tile are fixed by `base`
-        u32 sel_out = 0;
-        for (int j = 0; j < g.k; ++j)
-            if (g.tl[j] == 0xFF) sel_out |= (u32)((base >> g.tg[j]) & 1ull) << (g.k - 1 - j);
-        const int D = 1 << g.k;
-        if (g.kin == 0) {
-            const double2 d = g.m[sel_out * D + sel_out];
-            if (d.x == 1.0 && d.y == 0.0) return;
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g);
-                tile[e] = cmul<A>(d, tile[e]);
-            }
-        } else if (g.kin == 1) {
-            const int j = (g.tl[0] != 0xFF) ? 0 : 1;
-            const u32 o1 = 1u << g.tl[j];
-            const u32 s1 = 1u << (g.k - 1 - j);
-            const double2 d0 = g.m[sel_out * D + sel_out], d1 = g.m[(sel_out | s1) * D + (sel_out | s1)];
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g);
-                tile[e] = cmul<A>(d0, tile[e]);
-                tile[e | o1] = cmul<A>(d1, tile[e | o1]);
-            }
-        } else {
-            const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g);
-                tile[e] = cmul<A>(g.m[0], tile[e]);
-                tile[e | ol] = cmul<A>(g.m[5], tile[e | ol]);
-                tile[e | oh] = cmul<A>(g.m[10], tile[e | oh]);
-                tile[e | oh | ol] = cmul<A>(g.m[15], tile[e | oh | ol]);
-            }
+// insert a zero bit at each of NINS fixed positions (masks ascending), then set the control bits
+template <int NINS> struct Expand {
+    u32 nm[NINS > 0 ? NINS : 1];
+    u32 ior;
+    __device__ __forceinline__ explicit Expand(const DevGate &g) {
+#pragma unroll
+        for (int q = 0; q < NINS; ++q) nm[q] = g.nmask[q];
+        ior = g.in_or;
+    }
+    __device__ __forceinline__ u32 operator()(u32 w) const {
+#pragma unroll
+        for (int q = 0; q < NINS; ++q) w += (w & nm[q]);
+        return w | ior;
+    }
+};
+// any number of fixed positions (rare shapes: more than four in-tile controls)
+struct ExpandAny {
+    const DevGate &g;
+    __device__ __forceinline__ explicit ExpandAny(const DevGate &g_) : g(g_) {}
+    __device__ __forceinline__ u32 operator()(u32 w) const {
+        for (int q = 0; q < g.nins; ++q) w += (w & g.nmask[q]);
+        return w | g.in_or;
+    }
+};
+
+// phase tables of a stage at this tile: value(e) = SL(e & lom) * T_hi[e >> lo]
+struct StageRef {
+    const double2 *__restrict__ T;     // T_lo at T[0 .. nlo), T_hi at T[nlo ..)
+    double2 S;                         // product of the outside-cell tables at this tile's base
+    int lo;
+    u32 nlo;
+    u32 sor;                           // in-tile controls of the stage
+};
+__device__ __forceinline__ StageRef stage_ref(const DevGate &st, const double2 *__restrict__ tables, u64 base, int tb) {
+    const StageInfo &si = *reinterpret_cast<const StageInfo *>(st.m);
+    StageRef r;
+    r.T = tables + si.tab_off;
+    r.lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
+    r.nlo = 1u << r.lo;
+    r.S = stage_scalar(si, r.T, base, r.nlo, 1u << (tb - r.lo));
+    r.sor = st.in_or;
+    return r;
+}
+
+// ---- dense 2-qubit gate: groups of four amplitudes ----
+template <typename A, bool UNI, typename EX>
+__device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+    const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
+    Cf<A> m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = cf<A>(g.m[i]);
+#pragma unroll 1
+    QIPB_SWEEP(w, ngroups) {
+        A *p = tile + ex(w);
+        const A a0 = p[0], a1 = p[ol], a2 = p[oh], a3 = p[oh + ol];
+        A r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = cmulc<A>(m[4 * i], a0);
+            cfmac<A>(r[i], m[4 * i + 1], a1);
+            cfmac<A>(r[i], m[4 * i + 2], a2);
+            cfmac<A>(r[i], m[4 * i + 3], a3);
         }
-    } else if (g.k == 1) {
-        const u32 o1 = 1u << g.tl[0];
-        const DevGate &st = *(&g + 1);                         // only read when g.post
-        bool post = g.post != 0 && (base & st.out_ctrl) == st.out_ctrl;
-        if (!post) {
-            for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                const u32 e = expand_local(w, g);
-                const A a0 = tile[e], a1 = tile[e | o1];
-                A r0 = cmul<A>(g.m[0], a0);
-                cfma<A>(r0, g.m[1], a1);
-                A r1 = cmul<A>(g.m[2], a0);
-                cfma<A>(r1, g.m[3], a1);
-                tile[e] = r0;
-                tile[e | o1] = r1;
-            }
-        } else {
-            // dense 1-qubit gate followed by a stage (H_k and its controlled phases in a QFT): the
-            // phases are applied to the pair while it is still in registers -- one sweep, not two
-            const StageInfo &si = *reinterpret_cast<const StageInfo *>(st.m);
-            const double2 *T = tables + si.tab_off;
-            const int lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
-            const u32 nlo = 1u << lo, nhi = 1u << (tb - lo);
-            const double2 S = stage_scalar(si, T, base, nlo, nhi);
-            const u32 sor = st.in_or;
-            if (sor == o1 && g.nins == 1) {
-                // the stage is controlled by exactly the gate's target bit (H_k + its controlled phases):
-                // branch-free, two pairs per iteration so that table and tile loads overlap the FP64 work
-                const u32 nm = g.nmask[0];
-                const double2 m0 = g.m[0], m1 = g.m[1], m2 = g.m[2], m3 = g.m[3];
-                const u32 lom = nlo - 1u;
-                for (u32 w = tid; w < ngroups; w += 2 * FUSED_THREADS) {
-                    const u32 w2 = w + FUSED_THREADS;
-                    const bool two = w2 < ngroups;
-                    const u32 ea = w + (w & nm), eb = two ? w2 + (w2 & nm) : ea;
-                    const u32 ea1 = ea | o1, eb1 = eb | o1;
-                    const A a0 = tile[ea], a1 = tile[ea1], b0 = tile[eb], b1 = tile[eb1];
-                    const double2 tha = T[nlo + (ea1 >> lo)], tla = T[ea1 & lom];
-                    const double2 thb = T[nlo + (eb1 >> lo)], tlb = T[eb1 & lom];
-                    A r0 = cmul<A>(m0, a0), r1 = cmul<A>(m2, a0), s0 = cmul<A>(m0, b0), s1 = cmul<A>(m2, b0);
-                    cfma<A>(r0, m1, a1);
-                    cfma<A>(r1, m3, a1);
-                    cfma<A>(s0, m1, b1);
-                    cfma<A>(s1, m3, b1);
-                    double2 pa = cmul<double2>(S, tha), pb = cmul<double2>(S, thb);
-                    pa = cmul<double2>(pa, tla);
-                    pb = cmul<double2>(pb, tlb);
-                    r1 = cmul<A>(pa, r1);
-                    s1 = cmul<A>(pb, s1);
-                    tile[ea] = r0;
-                    tile[ea1] = r1;
-                    if (two) {
-                        tile[eb] = s0;
-                        tile[eb1] = s1;
-                    }
-                }
-            } else {
-                for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-                    const u32 e = expand_local(w, g), e1 = e | o1;
-                    const A a0 = tile[e], a1 = tile[e1];
-                    A r0 = cmul<A>(g.m[0], a0);
-                    cfma<A>(r0, g.m[1], a1);
-                    A r1 = cmul<A>(g.m[2], a0);
-                    cfma<A>(r1, g.m[3], a1);
-                    if ((e & sor) == sor) {
-                        double2 ph = cmul<double2>(S, T[nlo + (e >> lo)]);
-                        ph = cmul<double2>(ph, T[e & (nlo - 1u)]);
-                        r0 = cmul<A>(ph, r0);
-                    }
-                    if ((e1 & sor) == sor) {
-                        double2 ph = cmul<double2>(S, T[nlo + (e1 >> lo)]);
-                        ph = cmul<double2>(ph, T[e1 & (nlo - 1u)]);
-                        r1 = cmul<A>(ph, r1);
-                    }
-                    tile[e] = r0;
-                    tile[e1] = r1;
-                }
-            }
+        p[0] = r[0];
+        p[ol] = r[1];
+        p[oh] = r[2];
+        p[oh + ol] = r[3];
+    }
+}
+
+// ---- dense 1-qubit gate: pairs ----
+template <typename A, bool UNI, typename EX>
+__device__ __forceinline__ void sweep_dense1(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+    const u32 o1 = 1u << g.tl[0];
+    const Cf<A> m0 = cf<A>(g.m[0]), m1 = cf<A>(g.m[1]), m2 = cf<A>(g.m[2]), m3 = cf<A>(g.m[3]);
+#pragma unroll 2
+    QIPB_SWEEP(w, ngroups) {
+        A *p = tile + ex(w);
+        const A a0 = p[0], a1 = p[o1];
+        A r0 = cmulc<A>(m0, a0), r1 = cmulc<A>(m2, a0);
+        cfmac<A>(r0, m1, a1);
+        cfmac<A>(r1, m3, a1);
+        p[0] = r0;
+        p[o1] = r1;
+    }
+}
+
+// ---- dense 1-qubit gate (no controls) with the following stage applied to the pair while it is in
+// registers: H_k and its controlled phases in a QFT are one sweep.  Every thread visits tile indices
+// whose low `lo` bits never change (the stride of the sweep is a multiple of 2^lo), so the T_lo factor
+// and the stage scalar are folded once per thread; per pair only T_hi is looked up. ----
+template <typename A, bool UNI>
+__device__ __forceinline__ void sweep_dense1_stage(A *tile, const DevGate &g, const StageRef sr, u32 ngroups, int tid) {
+    const u32 o1 = 1u << g.tl[0];
+    const u32 nm = g.nmask[0];
+    const u32 sor = sr.sor, lom = sr.nlo - 1u;
+    const Cf<A> m0 = cf<A>(g.m[0]), m1 = cf<A>(g.m[1]), m2 = cf<A>(g.m[2]), m3 = cf<A>(g.m[3]);
+    const double2 *__restrict__ Th = sr.T + sr.nlo;
+    const u32 e_first = (u32)tid + ((u32)tid & nm);
+    const double2 SL0 = cmul<double2>(sr.S, sr.T[e_first & lom]);
+    const double2 SL1 = cmul<double2>(sr.S, sr.T[(e_first | o1) & lom]);
+    const int lo = sr.lo;
+    if (sor == o1) {                        // the stage is controlled by exactly the gate's target
+#pragma unroll 2
+        QIPB_SWEEP(w, ngroups) {
+            const u32 e = w + (w & nm);
+            A *p = tile + e;
+            const A a0 = p[0], a1 = p[o1];
+            const double2 ph = cmul<double2>(SL1, Th[(e | o1) >> lo]);
+            A r0 = cmulc<A>(m0, a0), r1 = cmulc<A>(m2, a0);
+            cfmac<A>(r0, m1, a1);
+            cfmac<A>(r1, m3, a1);
+            p[0] = r0;
+            p[o1] = cmul<A>(ph, r1);
         }
-    } else {   // dense k == 2
+    } else {
+#pragma unroll 1
+        QIPB_SWEEP(w, ngroups) {
+            const u32 e = w + (w & nm), e1 = e | o1;
+            A *p = tile + e;
+            const A a0 = p[0], a1 = p[o1];
+            A r0 = cmulc<A>(m0, a0), r1 = cmulc<A>(m2, a0);
+            cfmac<A>(r0, m1, a1);
+            cfmac<A>(r1, m3, a1);
+            if ((e & sor) == sor) r0 = cmul<A>(cmul<double2>(SL0, Th[e >> lo]), r0);
+            if ((e1 & sor) == sor) r1 = cmul<A>(cmul<double2>(SL1, Th[e1 >> lo]), r1);
+            p[0] = r0;
+            p[o1] = r1;
+        }
+    }
+}
+
+// ---- a stage on its own: one phase per element ----
+template <typename A, bool UNI, typename EX>
+__device__ __forceinline__ void sweep_stage(A *tile, const StageRef sr, const EX ex, u32 n, int tid) {
+    const double2 *__restrict__ Th = sr.T + sr.nlo;
+    const double2 SL = cmul<double2>(sr.S, sr.T[ex((u32)tid) & (sr.nlo - 1u)]);   // low bits are sweep-invariant
+    const int lo = sr.lo;
+#pragma unroll 4
+    QIPB_SWEEP(x, n) {
+        const u32 e = ex(x);
+        tile[e] = cmul<A>(cmul<double2>(SL, Th[e >> lo]), tile[e]);
+    }
+}
+
+// ---- a lone diagonal gate (k <= 2 targets, any of them possibly outside the tile) ----
+template <typename A, bool UNI, typename EX>
+__device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX ex, u32 ngroups, u64 base, int tid) {
+    u32 sel_out = 0;           // matrix-index bits of the targets that lie outside the tile (fixed per tile)
+    for (int j = 0; j < g.k; ++j)
+        if (g.tl[j] == 0xFF) sel_out |= (u32)((base >> g.tg[j]) & 1ull) << (g.k - 1 - j);
+    const int D = 1 << g.k;
+    if (g.kin == 0) {
+        const double2 d = g.m[sel_out * D + sel_out];
+        if (d.x == 1.0 && d.y == 0.0) return;
+        const Cf<A> c = cf<A>(d);
+#pragma unroll 4
+        QIPB_SWEEP(w, ngroups) {
+            const u32 e = ex(w);
+            tile[e] = cmulc<A>(c, tile[e]);
+        }
+    } else if (g.kin == 1) {
+        const int j = (g.tl[0] != 0xFF) ? 0 : 1;
+        const u32 o1 = 1u << g.tl[j];
+        const u32 s1 = 1u << (g.k - 1 - j);
+        const Cf<A> d0 = cf<A>(g.m[sel_out * D + sel_out]), d1 = cf<A>(g.m[(sel_out | s1) * D + (sel_out | s1)]);
+#pragma unroll 2
+        QIPB_SWEEP(w, ngroups) {
+            A *p = tile + ex(w);
+            p[0] = cmulc<A>(d0, p[0]);
+            p[o1] = cmulc<A>(d1, p[o1]);
+        }
+    } else {
         const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
-        for (u32 w = tid; w < ngroups; w += FUSED_THREADS) {
-            const u32 e = expand_local(w, g);
-            const u32 idx[4] = {e, e | ol, e | oh, e | oh | ol};
-            A a[4], r[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] = tile[idx[j]];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                r[i] = cmul<A>(g.m[i * 4], a[0]);
-#pragma unroll
-                for (int j = 1; j < 4; ++j) cfma<A>(r[i], g.m[i * 4 + j], a[j]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tile[idx[i]] = r[i];
+        const Cf<A> d0 = cf<A>(g.m[0]), d1 = cf<A>(g.m[5]), d2 = cf<A>(g.m[10]), d3 = cf<A>(g.m[15]);
+#pragma unroll 1
+        QIPB_SWEEP(w, ngroups) {
+            A *p = tile + ex(w);
+            p[0] = cmulc<A>(d0, p[0]);
+            p[ol] = cmulc<A>(d1, p[ol]);
+            p[oh] = cmulc<A>(d2, p[oh]);
+            p[oh + ol] = cmulc<A>(d3, p[oh + ol]);
         }
     }
 }
 
-// A "stage": a run of diagonal gates that share the control bits in_or/out_ctrl and whose remaining
-// bits each fall into ONE cell of the index (tile-lo, tile-hi, or a group of <= 7 bits outside the
-// tile).  Their product is the phase  S * T_hi[e >> 6] * T_lo[e & 63]  per element, S being the product
-// of the outside-cell tables at this tile's base index: one shared-memory sweep and three complex
-// multiplies replace the whole run.
-template <typename A>
-__device__ __forceinline__ void run_stage(A *tile, const DevGate &g, const double2 *__restrict__ tables, u64 base, int tb,
-                                          u32 tsize, int tid) {
+// One op on the tile.  All branches here are uniform over the CTA (they depend on the descriptor and
+// on the tile's base index only).  UNI: every sweep of this launch has a multiple of the CTA size as
+// its item count (tile bits - fixed positions >= 8) and at most four fixed positions -- true for every
+// production-size pass; tiny states and gates with many in-tile controls take the generic kernel.
+template <typename A, bool UNI>
+__device__ __forceinline__ void run_op(A *tile, const DevGate &g, const DevGate &next, const double2 *__restrict__ tables,
+                                       u64 base, int tb, u32 tsize, int tid) {
     if ((base & g.out_ctrl) != g.out_ctrl) return;
-    const StageInfo &si = *reinterpret_cast<const StageInfo *>(g.m);
-    const double2 *T = tables + si.tab_off;
-    const int lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
-    const u32 nlo = 1u << lo, nhi = 1u << (tb - lo);
-    const double2 S = stage_scalar(si, T, base, nlo, nhi);
-    const u32 n = tsize >> g.nins;
-    u32 x = tid;
-    for (; x + 3 * FUSED_THREADS < n; x += 4 * FUSED_THREADS) {   // four independent elements per iteration
-        u32 e[4];
-        A v[4];
-        double2 th[4], tl[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            e[q] = expand_local(x + FUSED_THREADS * q, g);
-            v[q] = tile[e[q]];
-            th[q] = T[nlo + (e[q] >> lo)];
-            tl[q] = T[e[q] & (nlo - 1u)];
+    const u32 ngroups = tsize >> g.nins;
+    const int nins = UNI ? g.nins : -1;
+    if (g.diag == 2) {
+        const StageRef sr = stage_ref(g, tables, base, tb);
+        switch (nins) {
+        case 0: sweep_stage<A, UNI>(tile, sr, Expand<0>(g), ngroups, tid); break;
+        case 1: sweep_stage<A, UNI>(tile, sr, Expand<1>(g), ngroups, tid); break;
+        case 2: sweep_stage<A, UNI>(tile, sr, Expand<2>(g), ngroups, tid); break;
+        case 3: sweep_stage<A, UNI>(tile, sr, Expand<3>(g), ngroups, tid); break;
+        case 4: sweep_stage<A, UNI>(tile, sr, Expand<4>(g), ngroups, tid); break;
+        default: sweep_stage<A, false>(tile, sr, ExpandAny(g), ngroups, tid); break;
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double2 ph = cmul<double2>(S, th[q]);
-            ph = cmul<double2>(ph, tl[q]);
-            tile[e[q]] = cmul<A>(ph, v[q]);
+    } else if (g.diag == 1) {
+        switch (nins) {
+        case 0: sweep_diag<A, UNI>(tile, g, Expand<0>(g), ngroups, base, tid); break;
+        case 1: sweep_diag<A, UNI>(tile, g, Expand<1>(g), ngroups, base, tid); break;
+        case 2: sweep_diag<A, UNI>(tile, g, Expand<2>(g), ngroups, base, tid); break;
+        case 3: sweep_diag<A, UNI>(tile, g, Expand<3>(g), ngroups, base, tid); break;
+        case 4: sweep_diag<A, UNI>(tile, g, Expand<4>(g), ngroups, base, tid); break;
+        default: sweep_diag<A, false>(tile, g, ExpandAny(g), ngroups, base, tid); break;
         }
-    }
-    for (; x < n; x += FUSED_THREADS) {
-        const u32 e = expand_local(x, g);
-        double2 ph = cmul<double2>(S, T[nlo + (e >> lo)]);
-        ph = cmul<double2>(ph, T[e & (nlo - 1u)]);
-        tile[e] = cmul<A>(ph, tile[e]);
+    } else if (g.k == 2) {
+        switch (nins) {
+        case 2: sweep_dense2<A, UNI>(tile, g, Expand<2>(g), ngroups, tid); break;
+        case 3: sweep_dense2<A, UNI>(tile, g, Expand<3>(g), ngroups, tid); break;
+        case 4: sweep_dense2<A, UNI>(tile, g, Expand<4>(g), ngroups, tid); break;
+        default: sweep_dense2<A, false>(tile, g, ExpandAny(g), ngroups, tid); break;
+        }
+    } else {
+        if (g.post != 0 && (base & next.out_ctrl) == next.out_ctrl) {     // host guarantees nins == 1, no controls
+            sweep_dense1_stage<A, UNI>(tile, g, stage_ref(next, tables, base, tb), ngroups, tid);
+            return;
+        }
+        switch (nins) {
+        case 1: sweep_dense1<A, UNI>(tile, g, Expand<1>(g), ngroups, tid); break;
+        case 2: sweep_dense1<A, UNI>(tile, g, Expand<2>(g), ngroups, tid); break;
+        case 3: sweep_dense1<A, UNI>(tile, g, Expand<3>(g), ngroups, tid); break;
+        case 4: sweep_dense1<A, UNI>(tile, g, Expand<4>(g), ngroups, tid); break;
+        default: sweep_dense1<A, false>(tile, g, ExpandAny(g), ngroups, tid); break;
+        }
     }
 }
 
 // BULK: tile staging with cp.async.bulk (TMA 1-D bulk copies, one per contiguous run, completion on
 // an mbarrier) instead of LDG/STS through registers.  Requires runs of >= 16 bytes.
-template <typename A, bool BULK>
-__global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+template <typename A, bool BULK, bool UNI>
+__global__ void __launch_bounds__(FUSED_THREADS, sizeof(A) == 16 ? 3 : 4) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     A *tile = reinterpret_cast<A *>(smem_raw);
@@ -265,8 +357,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(A *__restrict__ st
         // ---- stage the tile: runs of 2^lowrun consecutive amplitudes ----
         if (BULK) {
             if (tid < 32) {
+                // no __syncwarp here: complete_tx may precede expect_tx (the phase cannot complete before
+                // lane 0 arrives), and a warp-level sync makes ptxas give up warp-uniform descriptor loads
                 if (tid == 0) mbar_expect_tx(&bar, tsize * (u32)sizeof(A));
-                __syncwarp();
                 for (u32 r = tid; r < nruns; r += 32) {
                     u64 off = 0;
                     for (int j = f.lowrun; j < f.tb; ++j) off |= (u64)((r >> (j - f.lowrun)) & 1u) << f.tbit[j];
@@ -287,8 +380,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(A *__restrict__ st
         // ---- run the gate list on the tile ----
         for (int gi = 0; gi < f.ngates; ++gi) {
             if (f.g[gi].diag == 3) continue;                    // stage already applied by the dense gate before it
-            if (f.g[gi].diag == 2) run_stage<A>(tile, f.g[gi], f.tables, base, f.tb, tsize, tid);
-            else run_gate<A>(tile, f.g[gi], f.tables, base, f.tb, tsize, tid);
+            run_op<A, UNI>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, base, f.tb, tsize, tid);
             __syncthreads();
         }
 
@@ -325,13 +417,17 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
     if (per_sm > 8) per_sm = 8;
     u64 grid = (u64)ctx->sm_count * per_sm;
     if (grid > f.ntiles) grid = f.ntiles;
-    if (bulk) {
-        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_kernel<A, true><<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(state, f);
-    } else {
-        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_kernel<A, false><<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(state, f);
-    }
+    // UNI: all specialised sweeps (<= 4 fixed positions) have a multiple of the CTA size as item count
+    const bool uni = bulk && f.tb >= 12;
+#define QIPB_LAUNCH_FUSED(B, U)                                                                                             \
+    do {                                                                                                                    \
+        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        fused_kernel<A, B, U><<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(state, f);                              \
+    } while (0)
+    if (uni) QIPB_LAUNCH_FUSED(true, true);
+    else if (bulk) QIPB_LAUNCH_FUSED(true, false);
+    else QIPB_LAUNCH_FUSED(false, false);
+#undef QIPB_LAUNCH_FUSED
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
     return QIPB_OK;
