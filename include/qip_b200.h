@@ -50,6 +50,7 @@ int qipb_destroy(qipb_ctx *ctx);
 int qipb_set_stream(qipb_ctx *ctx, void *cuda_stream);       /* cudaStream_t; NULL = default  */
 int qipb_sync(qipb_ctx *ctx);                                /* cudaStreamSynchronize          */
 unsigned long long qipb_launch_count(qipb_ctx *ctx);         /* kernels launched via this ctx  */
+unsigned long long qipb_ring_launch_count(qipb_ctx *ctx);    /* of which: persistent ring kernel of qipb_apply_fused (diagnostic) */
 
 /* ---- memory helpers for hosts without torch -------------------------------------------- */
 int qipb_dev_alloc(qipb_ctx *ctx, size_t bytes, void **out);

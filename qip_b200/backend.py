@@ -76,7 +76,7 @@ class B200Backend(object):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.fuse = fuse
         import os
-        self.tile_bits = tile_bits
+        self.tile_bits = int(os.environ.get("QIPB_TILE_BITS", tile_bits))               # tuning knob for profiling runs
         self.min_low_bits = int(os.environ.get("QIPB_MIN_LOW_BITS", min_low_bits))     # tuning knob for profiling runs
         self.strategy = strategy
         # logical qubit -> index bit.  Canonical is n-1-q; an un-controlled Swap only permutes this map

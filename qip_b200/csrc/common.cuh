@@ -133,6 +133,7 @@ struct qipb_ctx {
     double *scratch;        // device scratch for reduction partials
     size_t scratch_bytes;
     unsigned long long launches;   // kernels launched through this context
+    unsigned long long ring_launches;  // of which: persistent ring kernel of the fused pass (fused.cu)
     // diagonal-stage tables of the fused pass (fused.cu): device buffer + pinned staging ring
     double2 *tab_dev;
     size_t tab_cap;                // capacity in double2 elements (device buffer and every ring slot)

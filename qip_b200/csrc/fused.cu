@@ -46,6 +46,7 @@ static_assert(sizeof(StageInfo) <= sizeof(double2) * 16, "StageInfo must fit ove
 
 struct FusedArgs {
     int nbits, tb, ngates, lowrun;      // lowrun = number of contiguous low tile bits (0..L-1)
+    int prefetch, nstages;              // prefetch: pull the CTA's next tile into L2 ahead of time; nstages: ops with tables
     u64 ntiles;
     const double2 *tables;              // stage tables (global memory)
     unsigned char tbit[16];             // tile-local bit -> state bit, ascending
@@ -62,12 +63,12 @@ static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel para
 // LDS + DFMA + STS and nothing else (the first version re-loaded 24 coefficients per group with
 // indexed LDC and was issue bound at ~0.37 of the FP64 / shared-memory limit).
 
-// Sweep loops: `count` work items over the CTA's threads.  UNI (count is a multiple of the CTA size)
+// Sweep loops: `count` work items over the CTA's threads.  UNI (count is a multiple of NT, the number of threads sweeping the tile)
 // gives the loop a warp-uniform trip count; with a possibly divergent exit condition ptxas stops
 // treating the descriptor index as uniform and falls back to indexed LDC loads inside the loops.
 #define QIPB_SWEEP(var, count) \
-    for (u32 it_ = 0, nit_ = UNI ? (count) / FUSED_THREADS : ((count) + FUSED_THREADS - 1) / FUSED_THREADS, var = tid; \
-         it_ < nit_ && (UNI || var < (count)); ++it_, var += FUSED_THREADS)
+    for (u32 it_ = 0, nit_ = UNI ? (count) / NT : ((count) + NT - 1) / NT, var = tid; \
+         it_ < nit_ && (UNI || var < (count)); ++it_, var += NT)
 
 // matrix coefficient in the amplitude's precision
 template <typename A> struct Cf { typename amp_traits<A>::real x, y; };
@@ -124,36 +125,75 @@ struct StageRef {
     u32 nlo;
     u32 sor;                           // in-tile controls of the stage
 };
-__device__ __forceinline__ StageRef stage_ref(const DevGate &st, const double2 *__restrict__ tables, u64 base, int tb) {
+__device__ __forceinline__ StageRef stage_ref(const DevGate &st, const double2 *__restrict__ tables, const double2 S, int tb) {
     const StageInfo &si = *reinterpret_cast<const StageInfo *>(st.m);
     StageRef r;
     r.T = tables + si.tab_off;
     r.lo = tb < FUSED_LO_BITS ? tb : FUSED_LO_BITS;
     r.nlo = 1u << r.lo;
-    r.S = stage_scalar(si, r.T, base, r.nlo, 1u << (tb - r.lo));
+    r.S = S;
     r.sor = st.in_or;
     return r;
 }
 
+// The stage scalars of one tile (product of the outside-cell tables at the tile's base index), one op
+// per thread, computed while the tile's load is in flight; the sweeps read them from shared memory.
+template <int NT>
+__device__ __forceinline__ void stage_scalars(const FusedArgs &f, u64 base, double2 *stage_S, int tid) {
+    const int lo = f.tb < FUSED_LO_BITS ? f.tb : FUSED_LO_BITS;
+    for (int op = tid; op < f.ngates; op += NT)
+        if (f.g[op].diag >= 2) {
+            const StageInfo &si = *reinterpret_cast<const StageInfo *>(f.g[op].m);
+            stage_S[op] = stage_scalar(si, f.tables + si.tab_off, base, 1u << lo, 1u << (f.tb - lo));
+        }
+}
+
 // ---- dense 2-qubit gate: groups of four amplitudes ----
-template <typename A, bool UNI, typename EX>
+template <typename A>
+__device__ __forceinline__ void dense2_group(const Cf<A> (&m)[16], const A a0, const A a1, const A a2, const A a3, A (&r)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r[i] = cmulc<A>(m[4 * i], a0);
+        cfmac<A>(r[i], m[4 * i + 1], a1);
+        cfmac<A>(r[i], m[4 * i + 2], a2);
+        cfmac<A>(r[i], m[4 * i + 3], a3);
+    }
+}
+
+template <typename A, bool UNI, int NT, typename EX>
 __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
     Cf<A> m[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) m[i] = cf<A>(g.m[i]);
+    if (UNI && (ngroups % (2 * NT)) == 0) {
+        // two groups per iteration, all eight loads first: every coefficient fetched from the parameter
+        // bank serves both groups, and the second group's loads overlap the first group's arithmetic
+#pragma unroll 1
+        for (u32 it = 0, nit = ngroups / (2 * NT), w = tid; it < nit; ++it, w += 2 * NT) {
+            A *p = tile + ex(w), *q = tile + ex(w + NT);
+            const A a0 = p[0], a1 = p[ol], a2 = p[oh], a3 = p[oh + ol];
+            const A b0 = q[0], b1 = q[ol], b2 = q[oh], b3 = q[oh + ol];
+            A r[4], s[4];
+            dense2_group<A>(m, a0, a1, a2, a3, r);
+            dense2_group<A>(m, b0, b1, b2, b3, s);
+            p[0] = r[0];
+            p[ol] = r[1];
+            p[oh] = r[2];
+            p[oh + ol] = r[3];
+            q[0] = s[0];
+            q[ol] = s[1];
+            q[oh] = s[2];
+            q[oh + ol] = s[3];
+        }
+        return;
+    }
 #pragma unroll 1
     QIPB_SWEEP(w, ngroups) {
         A *p = tile + ex(w);
         const A a0 = p[0], a1 = p[ol], a2 = p[oh], a3 = p[oh + ol];
         A r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            r[i] = cmulc<A>(m[4 * i], a0);
-            cfmac<A>(r[i], m[4 * i + 1], a1);
-            cfmac<A>(r[i], m[4 * i + 2], a2);
-            cfmac<A>(r[i], m[4 * i + 3], a3);
-        }
+        dense2_group<A>(m, a0, a1, a2, a3, r);
         p[0] = r[0];
         p[ol] = r[1];
         p[oh] = r[2];
@@ -162,7 +202,7 @@ __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX
 }
 
 // ---- dense 1-qubit gate: pairs ----
-template <typename A, bool UNI, typename EX>
+template <typename A, bool UNI, int NT, typename EX>
 __device__ __forceinline__ void sweep_dense1(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     const u32 o1 = 1u << g.tl[0];
     const Cf<A> m0 = cf<A>(g.m[0]), m1 = cf<A>(g.m[1]), m2 = cf<A>(g.m[2]), m3 = cf<A>(g.m[3]);
@@ -182,7 +222,7 @@ __device__ __forceinline__ void sweep_dense1(A *tile, const DevGate &g, const EX
 // registers: H_k and its controlled phases in a QFT are one sweep.  Every thread visits tile indices
 // whose low `lo` bits never change (the stride of the sweep is a multiple of 2^lo), so the T_lo factor
 // and the stage scalar are folded once per thread; per pair only T_hi is looked up. ----
-template <typename A, bool UNI>
+template <typename A, bool UNI, int NT>
 __device__ __forceinline__ void sweep_dense1_stage(A *tile, const DevGate &g, const StageRef sr, u32 ngroups, int tid) {
     const u32 o1 = 1u << g.tl[0];
     const u32 nm = g.nmask[0];
@@ -193,7 +233,34 @@ __device__ __forceinline__ void sweep_dense1_stage(A *tile, const DevGate &g, co
     const double2 SL0 = cmul<double2>(sr.S, sr.T[e_first & lom]);
     const double2 SL1 = cmul<double2>(sr.S, sr.T[(e_first | o1) & lom]);
     const int lo = sr.lo;
-    if (sor == o1) {                        // the stage is controlled by exactly the gate's target
+    if (sor == o1 && UNI && (ngroups % (4 * NT)) == 0) {
+        // the QFT step proper (stage controlled by exactly the gate's target), four pairs per iteration with
+        // every load issued before the arithmetic: enough independent chains to cover the FP64 latency
+#pragma unroll 1
+        for (u32 it = 0, nit = ngroups / (4 * NT), w = tid; it < nit; ++it, w += 4 * NT) {
+            A *p[4];
+            A a0[4], a1[4];
+            double2 th[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const u32 wq = w + q * NT;
+                const u32 e = wq + (wq & nm);
+                p[q] = tile + e;
+                a0[q] = p[q][0];
+                a1[q] = p[q][o1];
+                th[q] = Th[(e | o1) >> lo];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 ph = cmul<double2>(SL1, th[q]);
+                A r0 = cmulc<A>(m0, a0[q]), r1 = cmulc<A>(m2, a0[q]);
+                cfmac<A>(r0, m1, a1[q]);
+                cfmac<A>(r1, m3, a1[q]);
+                p[q][0] = r0;
+                p[q][o1] = cmul<A>(ph, r1);
+            }
+        }
+    } else if (sor == o1) {                 // the same step on tiles whose sweep is not a multiple of 4 * NT pairs
 #pragma unroll 2
         QIPB_SWEEP(w, ngroups) {
             const u32 e = w + (w & nm);
@@ -224,12 +291,29 @@ __device__ __forceinline__ void sweep_dense1_stage(A *tile, const DevGate &g, co
 }
 
 // ---- a stage on its own: one phase per element ----
-template <typename A, bool UNI, typename EX>
+template <typename A, bool UNI, int NT, typename EX>
 __device__ __forceinline__ void sweep_stage(A *tile, const StageRef sr, const EX ex, u32 n, int tid) {
     const double2 *__restrict__ Th = sr.T + sr.nlo;
     const double2 SL = cmul<double2>(sr.S, sr.T[ex((u32)tid) & (sr.nlo - 1u)]);   // low bits are sweep-invariant
     const int lo = sr.lo;
-#pragma unroll 4
+    if (UNI && (n % (4 * NT)) == 0) {
+#pragma unroll 1
+        for (u32 it = 0, nit = n / (4 * NT), x = tid; it < nit; ++it, x += 4 * NT) {
+            u32 e[4];
+            A v[4];
+            double2 th[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                e[q] = ex(x + q * NT);
+                v[q] = tile[e[q]];
+                th[q] = Th[e[q] >> lo];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tile[e[q]] = cmul<A>(cmul<double2>(SL, th[q]), v[q]);
+        }
+        return;
+    }
+#pragma unroll 1
     QIPB_SWEEP(x, n) {
         const u32 e = ex(x);
         tile[e] = cmul<A>(cmul<double2>(SL, Th[e >> lo]), tile[e]);
@@ -237,7 +321,7 @@ __device__ __forceinline__ void sweep_stage(A *tile, const StageRef sr, const EX
 }
 
 // ---- a lone diagonal gate (k <= 2 targets, any of them possibly outside the tile) ----
-template <typename A, bool UNI, typename EX>
+template <typename A, bool UNI, int NT, typename EX>
 __device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX ex, u32 ngroups, u64 base, int tid) {
     u32 sel_out = 0;           // matrix-index bits of the targets that lie outside the tile (fixed per tile)
     for (int j = 0; j < g.k; ++j)
@@ -281,59 +365,61 @@ __device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX e
 // on the tile's base index only).  UNI: every sweep of this launch has a multiple of the CTA size as
 // its item count (tile bits - fixed positions >= 8) and at most four fixed positions -- true for every
 // production-size pass; tiny states and gates with many in-tile controls take the generic kernel.
-template <typename A, bool UNI>
+template <typename A, bool UNI, int NT>
 __device__ __forceinline__ void run_op(A *tile, const DevGate &g, const DevGate &next, const double2 *__restrict__ tables,
-                                       u64 base, int tb, u32 tsize, int tid) {
+                                       const double2 *stage_S, int gi, u64 base, int tb, u32 tsize, int tid) {
     if ((base & g.out_ctrl) != g.out_ctrl) return;
     const u32 ngroups = tsize >> g.nins;
-    const int nins = UNI ? g.nins : -1;
+    const int nins = (UNI && (ngroups % NT) == 0) ? g.nins : -1;
     if (g.diag == 2) {
-        const StageRef sr = stage_ref(g, tables, base, tb);
+        const StageRef sr = stage_ref(g, tables, stage_S[gi], tb);
         switch (nins) {
-        case 0: sweep_stage<A, UNI>(tile, sr, Expand<0>(g), ngroups, tid); break;
-        case 1: sweep_stage<A, UNI>(tile, sr, Expand<1>(g), ngroups, tid); break;
-        case 2: sweep_stage<A, UNI>(tile, sr, Expand<2>(g), ngroups, tid); break;
-        case 3: sweep_stage<A, UNI>(tile, sr, Expand<3>(g), ngroups, tid); break;
-        case 4: sweep_stage<A, UNI>(tile, sr, Expand<4>(g), ngroups, tid); break;
-        default: sweep_stage<A, false>(tile, sr, ExpandAny(g), ngroups, tid); break;
+        case 0: sweep_stage<A, UNI, NT>(tile, sr, Expand<0>(g), ngroups, tid); break;
+        case 1: sweep_stage<A, UNI, NT>(tile, sr, Expand<1>(g), ngroups, tid); break;
+        case 2: sweep_stage<A, UNI, NT>(tile, sr, Expand<2>(g), ngroups, tid); break;
+        case 3: sweep_stage<A, UNI, NT>(tile, sr, Expand<3>(g), ngroups, tid); break;
+        case 4: sweep_stage<A, UNI, NT>(tile, sr, Expand<4>(g), ngroups, tid); break;
+        default: sweep_stage<A, false, NT>(tile, sr, ExpandAny(g), ngroups, tid); break;
         }
     } else if (g.diag == 1) {
         switch (nins) {
-        case 0: sweep_diag<A, UNI>(tile, g, Expand<0>(g), ngroups, base, tid); break;
-        case 1: sweep_diag<A, UNI>(tile, g, Expand<1>(g), ngroups, base, tid); break;
-        case 2: sweep_diag<A, UNI>(tile, g, Expand<2>(g), ngroups, base, tid); break;
-        case 3: sweep_diag<A, UNI>(tile, g, Expand<3>(g), ngroups, base, tid); break;
-        case 4: sweep_diag<A, UNI>(tile, g, Expand<4>(g), ngroups, base, tid); break;
-        default: sweep_diag<A, false>(tile, g, ExpandAny(g), ngroups, base, tid); break;
+        case 0: sweep_diag<A, UNI, NT>(tile, g, Expand<0>(g), ngroups, base, tid); break;
+        case 1: sweep_diag<A, UNI, NT>(tile, g, Expand<1>(g), ngroups, base, tid); break;
+        case 2: sweep_diag<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, base, tid); break;
+        case 3: sweep_diag<A, UNI, NT>(tile, g, Expand<3>(g), ngroups, base, tid); break;
+        case 4: sweep_diag<A, UNI, NT>(tile, g, Expand<4>(g), ngroups, base, tid); break;
+        default: sweep_diag<A, false, NT>(tile, g, ExpandAny(g), ngroups, base, tid); break;
         }
     } else if (g.k == 2) {
         switch (nins) {
-        case 2: sweep_dense2<A, UNI>(tile, g, Expand<2>(g), ngroups, tid); break;
-        case 3: sweep_dense2<A, UNI>(tile, g, Expand<3>(g), ngroups, tid); break;
-        case 4: sweep_dense2<A, UNI>(tile, g, Expand<4>(g), ngroups, tid); break;
-        default: sweep_dense2<A, false>(tile, g, ExpandAny(g), ngroups, tid); break;
+        case 2: sweep_dense2<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid); break;
+        case 3: sweep_dense2<A, UNI, NT>(tile, g, Expand<3>(g), ngroups, tid); break;
+        case 4: sweep_dense2<A, UNI, NT>(tile, g, Expand<4>(g), ngroups, tid); break;
+        default: sweep_dense2<A, false, NT>(tile, g, ExpandAny(g), ngroups, tid); break;
         }
     } else {
         if (g.post != 0 && (base & next.out_ctrl) == next.out_ctrl) {     // host guarantees nins == 1, no controls
-            sweep_dense1_stage<A, UNI>(tile, g, stage_ref(next, tables, base, tb), ngroups, tid);
+            sweep_dense1_stage<A, UNI, NT>(tile, g, stage_ref(next, tables, stage_S[gi + 1], tb), ngroups, tid);
             return;
         }
         switch (nins) {
-        case 1: sweep_dense1<A, UNI>(tile, g, Expand<1>(g), ngroups, tid); break;
-        case 2: sweep_dense1<A, UNI>(tile, g, Expand<2>(g), ngroups, tid); break;
-        case 3: sweep_dense1<A, UNI>(tile, g, Expand<3>(g), ngroups, tid); break;
-        case 4: sweep_dense1<A, UNI>(tile, g, Expand<4>(g), ngroups, tid); break;
-        default: sweep_dense1<A, false>(tile, g, ExpandAny(g), ngroups, tid); break;
+        case 1: sweep_dense1<A, UNI, NT>(tile, g, Expand<1>(g), ngroups, tid); break;
+        case 2: sweep_dense1<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid); break;
+        case 3: sweep_dense1<A, UNI, NT>(tile, g, Expand<3>(g), ngroups, tid); break;
+        case 4: sweep_dense1<A, UNI, NT>(tile, g, Expand<4>(g), ngroups, tid); break;
+        default: sweep_dense1<A, false, NT>(tile, g, ExpandAny(g), ngroups, tid); break;
         }
     }
 }
 
 // BULK: tile staging with cp.async.bulk (TMA 1-D bulk copies, one per contiguous run, completion on
 // an mbarrier) instead of LDG/STS through registers.  Requires runs of >= 16 bytes.
-template <typename A, bool BULK, bool UNI>
-__global__ void __launch_bounds__(FUSED_THREADS, sizeof(A) == 16 ? 3 : 4) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+// NT threads per CTA: 256 for 2^12-amplitude tiles, 128 for 2^11 (twice as many CTAs per SM on the same shared memory)
+template <typename A, bool BULK, bool UNI, int NT>
+__global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(16) double2 stage_S[FUSED_MAX_OPS + 1];
     A *tile = reinterpret_cast<A *>(smem_raw);
     const int tid = threadIdx.x;
     const u32 tsize = 1u << f.tb;
@@ -360,16 +446,30 @@ __global__ void __launch_bounds__(FUSED_THREADS, sizeof(A) == 16 ? 3 : 4) fused_
                 // no __syncwarp here: complete_tx may precede expect_tx (the phase cannot complete before
                 // lane 0 arrives), and a warp-level sync makes ptxas give up warp-uniform descriptor loads
                 if (tid == 0) mbar_expect_tx(&bar, tsize * (u32)sizeof(A));
+                // optional (QIPB_FUSED_PREFETCH=1, off by default): pull this CTA's NEXT tile into L2 while this one
+                // is computed and written back.  Measured on B200: no gain for compute-heavy passes and a worse
+                // floor (profiles/r01_probe_fused_prefetch.txt), so it stays a profiling knob.
+                u64 nbase = t + gridDim.x;
+                const bool pf = f.prefetch && nbase < f.ntiles;
+                if (pf)
+                    for (int j = 0; j < f.tb; ++j) nbase = insert_zero(nbase, f.tbit[j]);
                 for (u32 r = tid; r < nruns; r += 32) {
                     u64 off = 0;
                     for (int j = f.lowrun; j < f.tb; ++j) off |= (u64)((r >> (j - f.lowrun)) & 1u) << f.tbit[j];
                     bulk_g2s(tile + (size_t)r * run_amps, state + base + off, run_bytes, &bar);
+                    if (pf) bulk_prefetch_l2(state + nbase + off, run_bytes);
                 }
+                // stage scalars of this tile, computed by the issuing warp while the copies are in flight
+                // (kept inside this warp's branch: a thread-dependent loop in the common path makes ptxas
+                // drop the warp-uniform descriptor loads of the sweeps)
+                if (f.nstages) stage_scalars<32>(f, base, stage_S, tid);
             }
             mbar_wait(&bar, parity);
             parity ^= 1u;
+            if (f.nstages) __syncthreads();
         } else {
-            for (u32 e = tid; e < tsize; e += FUSED_THREADS) {
+            if (f.nstages) stage_scalars<NT>(f, base, stage_S, tid);
+            for (u32 e = tid; e < tsize; e += NT) {
                 u64 off = e & lowmask;
                 for (int j = f.lowrun; j < f.tb; ++j) off |= (u64)((e >> j) & 1u) << f.tbit[j];
                 tile[e] = state[base + off];
@@ -380,7 +480,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, sizeof(A) == 16 ? 3 : 4) fused_
         // ---- run the gate list on the tile ----
         for (int gi = 0; gi < f.ngates; ++gi) {
             if (f.g[gi].diag == 3) continue;                    // stage already applied by the dense gate before it
-            run_op<A, UNI>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, base, f.tb, tsize, tid);
+            run_op<A, UNI, NT>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, stage_S, gi, base, f.tb, tsize, tid);
             __syncthreads();
         }
 
@@ -398,7 +498,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, sizeof(A) == 16 ? 3 : 4) fused_
             }
             __syncthreads();
         } else {
-            for (u32 e = tid; e < tsize; e += FUSED_THREADS) {
+            for (u32 e = tid; e < tsize; e += NT) {
                 u64 off = e & lowmask;
                 for (int j = f.lowrun; j < f.tb; ++j) off |= (u64)((e >> j) & 1u) << f.tbit[j];
                 state[base + off] = tile[e];
@@ -408,25 +508,149 @@ __global__ void __launch_bounds__(FUSED_THREADS, sizeof(A) == 16 ? 3 : 4) fused_
     }
 }
 
+// ---- persistent ring kernel: one CTA per SM, warp-specialised -------------------------------------
+// 16 compute warps sweep ONE tile at a time; one I/O warp keeps a ring of NBUF tile buffers moving with
+// TMA bulk copies: while tile k is being computed, tile k+1 (and k+2) are landing and tile k-1 is being
+// written back.  full[b]: the load of buffer b has landed (expect_tx / complete_tx); done[b]: the compute
+// warps are finished with buffer b.  Lane j of the I/O warp always moves the same runs of a buffer (r = j
+// mod 32), so "my stores from this buffer have been read out" (wait_group.read) is all it needs before it
+// refills the very same shared-memory bytes.
+#define RING_COMPUTE 512
+#define RING_THREADS (RING_COMPUTE + 32)
+
+template <typename A, int NBUF>
+__global__ void __launch_bounds__(RING_THREADS, 1) fused_ring_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[NBUF], done[NBUF];
+    __shared__ __align__(16) double2 stage_S[NBUF][FUSED_MAX_OPS + 1];   // per buffer: the I/O warp fills them at load time
+    const int tid = threadIdx.x;
+    const u32 tsize = 1u << f.tb;
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(&full[b], 32);           // every lane of the I/O warp arrives (lane 0 with the byte count)
+            mbar_init(&done[b], 1);
+        }
+        fence_proxy_async();
+    }
+    __syncthreads();
+    const u64 ntiles = f.ntiles, step = gridDim.x;
+    // warp-uniform role id (the shuffle lets ptxas keep the role branch, and with it the descriptor
+    // loads of the compute path, on the uniform datapath)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    if (warp >= RING_COMPUTE / 32) {
+        // ---------------- I/O warp ----------------
+        const u32 lane = (u32)tid - RING_COMPUTE;
+        const u32 run_amps = 1u << f.lowrun, nruns = tsize >> f.lowrun, run_bytes = run_amps * (u32)sizeof(A);
+        u64 off[4];                        // global offsets of this lane's runs inside a tile (nruns <= 128)
+        for (u32 i = 0; i < 4; ++i) {
+            const u32 r = lane + 32u * i;
+            u64 o = 0;
+            for (int j = f.lowrun; j < f.tb; ++j) o |= (u64)((r >> (j - f.lowrun)) & 1u) << f.tbit[j];
+            off[i] = o;
+        }
+        auto tile_base = [&](u64 t) {
+            u64 base = t;
+            for (int j = 0; j < f.tb; ++j) base = insert_zero(base, f.tbit[j]);
+            return base;
+        };
+        auto load_tile = [&](int b, u64 t) {
+            A *tile = reinterpret_cast<A *>(smem_raw) + (size_t)b * tsize;
+            const u64 base = tile_base(t);
+            // stage scalars first: the mbarrier's completion then also publishes them (lane 0's arrive is a
+            // release after its own writes; the other lanes' writes are ordered by the __syncwarp-free rule
+            // below: every lane arrives on the barrier itself)
+            if (f.nstages) stage_scalars<32>(f, base, stage_S[b], (int)lane);
+            if (lane == 0) mbar_expect_tx(&full[b], tsize * (u32)sizeof(A));
+            else mbar_arrive(&full[b]);
+#pragma unroll
+            for (u32 i = 0; i < 4; ++i) {
+                const u32 r = lane + 32u * i;
+                if (r < nruns) bulk_g2s(tile + (size_t)r * run_amps, state + base + off[i], run_bytes, &full[b]);
+            }
+        };
+        {
+            u64 t = blockIdx.x;
+            for (int b = 0; b < NBUF && t < ntiles; ++b, t += step) load_tile(b, t);
+        }
+        u32 k = 0;
+        for (u64 t = blockIdx.x; t < ntiles; t += step, ++k) {
+            const int b = (int)(k % NBUF);
+            mbar_wait(&done[b], (k / NBUF) & 1u);
+            A *tile = reinterpret_cast<A *>(smem_raw) + (size_t)b * tsize;
+            const u64 base = tile_base(t);
+#pragma unroll
+            for (u32 i = 0; i < 4; ++i) {
+                const u32 r = lane + 32u * i;
+                if (r < nruns) bulk_s2g(state + base + off[i], tile + (size_t)r * run_amps, run_bytes);
+            }
+            bulk_commit();
+            const u64 tn = t + (u64)NBUF * step;
+            if (tn < ntiles) {
+                bulk_wait_read_all();      // this lane's stores have left the buffer: refill the same bytes
+                load_tile(b, tn);
+            }
+        }
+        bulk_wait_all();
+    } else {
+        // ---------------- compute warps ----------------
+        u32 k = 0;
+        for (u64 t = blockIdx.x; t < ntiles; t += step, ++k) {
+            const int b = (int)(k % NBUF);
+            A *tile = reinterpret_cast<A *>(smem_raw) + (size_t)b * tsize;
+            u64 base = t;
+            for (int j = 0; j < f.tb; ++j) base = insert_zero(base, f.tbit[j]);
+            mbar_wait(&full[b], (k / NBUF) & 1u);
+            bool first = true;
+            for (int gi = 0; gi < f.ngates; ++gi) {
+                if (f.g[gi].diag == 3) continue;                // stage already applied by the dense gate before it
+                if (!first) named_bar_sync(1, RING_COMPUTE);
+                first = false;
+                run_op<A, true, RING_COMPUTE>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, stage_S[b], gi, base, f.tb, tsize, tid);
+            }
+            fence_proxy_async();           // generic-proxy writes -> visible to the bulk store
+            named_bar_sync(1, RING_COMPUTE);
+            if (tid == 0) mbar_arrive(&done[b]);
+        }
+    }
+}
+
+static bool ring_enabled() {
+    // opt-in (measured on B200, profiles/r01_probe_fused_ring.txt: one tile at a time on 16 warps sweeps
+    // slower than three independent CTAs per SM do); read per call so that tests can toggle it
+    const char *e = getenv("QIPB_FUSED_RING");
+    return e && atoi(e) != 0;
+}
+
+static inline u32 tsize_runs(const FusedArgs &f) { return 1u << (f.tb - f.lowrun); }
+
 template <typename A>
 static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
     const size_t smem = sizeof(A) << f.tb;
     const bool bulk = (sizeof(A) << f.lowrun) >= 512 && f.ntiles >= 2;
-    int per_sm = (int)((220u * 1024u) / (smem + 1024));
+    int per_sm = (int)((224u * 1024u) / (smem + 3072));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     u64 grid = (u64)ctx->sm_count * per_sm;
     if (grid > f.ntiles) grid = f.ntiles;
     // UNI: all specialised sweeps (<= 4 fixed positions) have a multiple of the CTA size as item count
-    const bool uni = bulk && f.tb >= 12;
-#define QIPB_LAUNCH_FUSED(B, U)                                                                                             \
+    const bool half = bulk && f.tb == 11;                      // 2^11 tiles: 128-thread CTAs
+    const bool uni = bulk && (f.tb >= 12 || half);
+#define QIPB_LAUNCH_FUSED(B, U, T)                                                                                          \
     do {                                                                                                                    \
-        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        fused_kernel<A, B, U><<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(state, f);                              \
+        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        fused_kernel<A, B, U, T><<<(unsigned)grid, T, smem, ctx->stream>>>(state, f);                                       \
     } while (0)
-    if (uni) QIPB_LAUNCH_FUSED(true, true);
-    else if (bulk) QIPB_LAUNCH_FUSED(true, false);
-    else QIPB_LAUNCH_FUSED(false, false);
+    if (uni && !half && ring_enabled() && f.ntiles >= 4ull * (u64)ctx->sm_count && (tsize_runs(f) <= 128)) {
+        constexpr int NBUF = sizeof(A) == 16 ? 3 : 6;
+        const size_t rsmem = (size_t)NBUF * smem;
+        QIPB_CUDA(cudaFuncSetAttribute(fused_ring_kernel<A, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        fused_ring_kernel<A, NBUF><<<(unsigned)ctx->sm_count, RING_THREADS, rsmem, ctx->stream>>>(state, f);
+        ctx->ring_launches++;
+    } else if (half) QIPB_LAUNCH_FUSED(true, true, 128);
+    else if (uni) QIPB_LAUNCH_FUSED(true, true, 256);
+    else if (bulk) QIPB_LAUNCH_FUSED(true, false, 256);
+    else QIPB_LAUNCH_FUSED(false, false, 256);
 #undef QIPB_LAUNCH_FUSED
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
@@ -613,6 +837,10 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     f.nbits = nbits;
     f.tb = ntile_bits;
     f.ntiles = 1ull << (nbits - ntile_bits);
+    {
+        const char *e = getenv("QIPB_FUSED_PREFETCH");        // tuning knob for profiling runs
+        f.prefetch = e ? atoi(e) : 0;   // measured: no gain, the floor gets worse (profiles/r01_probe_fused_prefetch.txt)
+    }
     int local_of[64];
     for (int b = 0; b < 64; ++b) local_of[b] = -1;
     u64 tmask = 0;
@@ -732,6 +960,8 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
                     nx.diag = 3;
                 }
             }
+        f.nstages = 0;
+        for (size_t oi = 0; oi < cnt; ++oi) f.nstages += f.g[oi].diag >= 2;
         if (getenv("QIPB_DEBUG")) {
             int nst = 0, npost = 0, ndense = 0, ndiag = 0;
             for (size_t oi = 0; oi < cnt; ++oi) {

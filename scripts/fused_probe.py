@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--c64", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cases", default="")
+    ap.add_argument("--low", type=int, default=7, help="contiguous low tile bits of the scattered tile (7 -> 2^12 tile, 6 -> 2^11)")
     args = ap.parse_args()
     import torch
     from qip_b200 import B200Backend
@@ -41,8 +42,8 @@ def main():
         return haar_unitary(rng, 2)
 
     hi = [n - 10, n - 8, n - 5, n - 3, n - 1]
-    tile_a = tuple(range(7)) + tuple(hi)                 # the planner's usual shape: 7 low + 5 scattered high
-    tile_c = tuple(range(12))                            # contiguous tile
+    tile_a = tuple(range(args.low)) + tuple(hi)          # the planner's usual shape: 7 low + 5 scattered high
+    tile_c = tuple(range(args.low + 5))                  # contiguous tile
     ph = np.diag([np.exp(0.3j)])
 
     def dense2(bits):

@@ -197,6 +197,53 @@ def test_fused_pass_with_tile_bits_in_the_middle_and_top():
     assert float(np.max(np.abs(got - np.asarray(gu.get_state())))) <= 1e-12
 
 
+@pytest.mark.parametrize("statetype,tol", [(np.complex128, TOL128), (np.complex64, TOL64)])
+def test_ring_kernel_layered_and_controls_match_unfused(statetype, tol, monkeypatch):
+    # 24 qubits = 4096 tiles: the persistent ring kernel (TMA ring, warp-specialised) runs the fused passes.
+    # Checked against the product's own un-fused register kernels (which the oracle pins at small n) on the
+    # same circuit, and against the norm; the circuit mixes the layered generator with controlled /
+    # diagonal / low-bit gates so that every sweep specialisation is hit.
+    n = 24
+    rng = np.random.default_rng(124)
+    psi = _rand_state(rng, n)
+    B = _backend()
+    monkeypatch.setenv("QIPB_FUSED_RING", "1")
+    gf = B.make_state(n, [list(range(n))], [psi], statetype=statetype, strategy="tile")
+    gu = B.make_state(n, [list(range(n))], [psi], statetype=statetype, fuse=False)
+    extra = [{(n - 1, n - 2): haar_unitary(rng, 4)}, {(n - 3, n - 1): haar_unitary(rng, 4)}, {n - 2: haar_unitary(rng, 2)},
+             {(0, n - 1): CMat(haar_unitary(rng, 2))}, {(n - 4, 3, n - 1): CMat(CMat(haar_unitary(rng, 2)))},
+             {(n - 1, n - 2, n - 3, 5): CMat(CMat(CMat(haar_unitary(rng, 2))))},
+             {(n - 2, 4, 7): CMat(haar_unitary(rng, 4))}, {(n - 5, n - 1): np.diag(np.exp(1j * rng.normal(size=4)))},
+             {(2, 9): np.diag(np.exp(1j * rng.normal(size=4)))}, {n - 1: rm_mat(3)}, {(1, n - 6): CMat(rm_mat(4))},
+             {(n - 1, 0): SwapMat(1)}, {(5, n - 2, n - 7): CMat(SwapMat(1))}]
+    ops_ = list(layered_stream(n, 2, 7)) + extra + list(layered_stream(n, 1, 8))
+    for mats in ops_:
+        gf.kronselect_dot(mats)
+        gu.kronselect_dot(mats)
+    a, b = np.asarray(gf.get_state()), np.asarray(gu.get_state())
+    assert gf.stats["fused_passes"] >= 3
+    assert int(gf.L.qipb_ring_launch_count(gf.ctx)) >= 3
+    assert float(np.max(np.abs(a - b))) / float(np.max(np.abs(b))) <= tol
+    assert abs(float(np.vdot(a.astype(np.complex128), a.astype(np.complex128)).real) - 1.0) <= (1e-12 if statetype == np.complex128 else 1e-4)
+
+
+@pytest.mark.parametrize("ring", [0, 1])
+def test_qfft_24_closed_form_both_fused_kernels(ring, monkeypatch):
+    # BASELINE configs[1]: QFFT on 24 qubits complex128; closed form sqrt(N) * ifft.
+    # ring = 0: three-CTAs-per-SM tile kernel (default); ring = 1: persistent ring kernel.
+    n = 24
+    rng = np.random.default_rng(24)
+    psi = _rand_state(rng, n)
+    monkeypatch.setenv("QIPB_FUSED_RING", str(ring))
+    g = _backend().make_state(n, [list(range(n))], [psi])
+    for mats in qfft_stream(n):
+        g.kronselect_dot(mats)
+    out = np.asarray(g.get_state())
+    assert (int(g.L.qipb_ring_launch_count(g.ctx)) >= 1) == bool(ring)
+    want = np.fft.ifft(psi) * np.sqrt(2 ** n)
+    assert float(np.max(np.abs(out - want))) / float(np.max(np.abs(want))) <= 1e-12
+
+
 # ------------------------------------------------------------------ init / func_apply / measurement
 def test_kron_init_shuffled_groups_and_one_hot():
     n = 10
