@@ -79,6 +79,22 @@ template <typename A> __device__ __forceinline__ Cf<A> cf(const double2 m) {
     c.y = (R)m.y;
     return c;
 }
+// coefficient i of a gate descriptor, stored by the host in the amplitude's precision (complex64 launches
+// hold float2 over the same bytes: a per-use F2F of a warp-uniform double costs more than the FFMA it feeds)
+template <typename A> __device__ __forceinline__ Cf<A> coef(const DevGate &g, int i);
+template <> __device__ __forceinline__ Cf<double2> coef<double2>(const DevGate &g, int i) {
+    Cf<double2> c;
+    c.x = g.m[i].x;
+    c.y = g.m[i].y;
+    return c;
+}
+template <> __device__ __forceinline__ Cf<float2> coef<float2>(const DevGate &g, int i) {
+    const float2 v = reinterpret_cast<const float2 *>(g.m)[i];
+    Cf<float2> c;
+    c.x = v.x;
+    c.y = v.y;
+    return c;
+}
 template <typename A> __device__ __forceinline__ A cmulc(const Cf<A> m, const A a) {
     A r;
     r.x = m.x * a.x - m.y * a.y;
@@ -165,7 +181,7 @@ __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX
     const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
     Cf<A> m[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = cf<A>(g.m[i]);
+    for (int i = 0; i < 16; ++i) m[i] = coef<A>(g, i);
     if (UNI && (ngroups % (2 * NT)) == 0) {
         // two groups per iteration, all eight loads first: every coefficient fetched from the parameter
         // bank serves both groups, and the second group's loads overlap the first group's arithmetic
@@ -201,11 +217,83 @@ __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX
     }
 }
 
+// ---- the same gates when a target sits on one of the lowest tile bits ----
+// Shared memory serves one 128-byte line per cycle, i.e. 2^LOWB amplitudes (8 complex128 / 16 complex64).
+// The lanes of one request phase hold consecutive group numbers, so with c targets below bit LOWB only
+// 2^(LOWB-c) different bank groups are hit per request: a 2^c-way bank conflict on every load and store.
+// Fix without touching the data layout: lane l visits the members of ITS group in the order j ^ R(l)
+// (R = the c bits of the lane number that would otherwise collide, placed on the matrix-index bits of the
+// low targets), so one request covers all bank groups.  The 2-qubit sweep swaps the loaded amplitudes back
+// into member order with predicated register selects (coefficients stay warp-uniform); the 1-qubit sweep
+// applies the correspondingly permuted matrix M'[i][j] = M[i ^ R][j ^ R] instead (8 registers per lane).
+template <typename A> struct LowBits { static constexpr int value = sizeof(A) == 16 ? 3 : 4; };
+
+template <typename A> __device__ __forceinline__ void cswap(const bool c, A &u, A &v) {
+    const A t = c ? v : u;
+    v = c ? u : v;
+    u = t;
+}
+
+template <typename A, bool UNI, int NT, typename EX>
+__device__ __forceinline__ void sweep_dense2_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+    constexpr int LOWB = LowBits<A>::value;
+    const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
+    const int c = (g.tl[0] < LOWB) + (g.tl[1] < LOWB);
+    const u32 B = (g.tl[0] < LOWB ? 2u : 0u) | (g.tl[1] < LOWB ? 1u : 0u);
+    const u32 rb = ((u32)tid >> (LOWB - c)) & ((1u << c) - 1u);
+    const u32 R = c == 2 ? rb : (rb ? B : 0u);
+    const bool R0 = (R & 1u) != 0u, R1 = (R & 2u) != 0u;
+    Cf<A> m[16];                       // uniform: the 16 coefficients would not fit per lane (64 registers)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = coef<A>(g, i);
+    u32 off[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) off[k] = (((k ^ R) & 2u) ? oh : 0u) + (((k ^ R) & 1u) ? ol : 0u);
+#pragma unroll 1
+    QIPB_SWEEP(w, ngroups) {
+        A *p = tile + ex(w);
+        A x[4], r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = p[off[k]];          // x[k] = member k ^ R
+        cswap<A>(R0, x[0], x[1]);                               // back to member order in registers
+        cswap<A>(R0, x[2], x[3]);
+        cswap<A>(R1, x[0], x[2]);
+        cswap<A>(R1, x[1], x[3]);
+        dense2_group<A>(m, x[0], x[1], x[2], x[3], r);
+        cswap<A>(R0, r[0], r[1]);
+        cswap<A>(R0, r[2], r[3]);
+        cswap<A>(R1, r[0], r[2]);
+        cswap<A>(R1, r[1], r[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[off[k]] = r[k];
+    }
+}
+
+template <typename A, bool UNI, int NT, typename EX>
+__device__ __forceinline__ void sweep_dense1_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+    constexpr int LOWB = LowBits<A>::value;
+    const u32 o1 = 1u << g.tl[0];
+    const bool R = (((u32)tid >> (LOWB - 1)) & 1u) != 0u;
+    const Cf<A> c0 = coef<A>(g, 0), c1 = coef<A>(g, 1), c2 = coef<A>(g, 2), c3 = coef<A>(g, 3);
+    const Cf<A> m0 = R ? c3 : c0, m1 = R ? c2 : c1, m2 = R ? c1 : c2, m3 = R ? c0 : c3;
+    const u32 f0 = R ? o1 : 0u, f1 = R ? 0u : o1;
+#pragma unroll 2
+    QIPB_SWEEP(w, ngroups) {
+        A *p = tile + ex(w);
+        const A a0 = p[f0], a1 = p[f1];
+        A r0 = cmulc<A>(m0, a0), r1 = cmulc<A>(m2, a0);
+        cfmac<A>(r0, m1, a1);
+        cfmac<A>(r1, m3, a1);
+        p[f0] = r0;
+        p[f1] = r1;
+    }
+}
+
 // ---- dense 1-qubit gate: pairs ----
 template <typename A, bool UNI, int NT, typename EX>
 __device__ __forceinline__ void sweep_dense1(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     const u32 o1 = 1u << g.tl[0];
-    const Cf<A> m0 = cf<A>(g.m[0]), m1 = cf<A>(g.m[1]), m2 = cf<A>(g.m[2]), m3 = cf<A>(g.m[3]);
+    const Cf<A> m0 = coef<A>(g, 0), m1 = coef<A>(g, 1), m2 = coef<A>(g, 2), m3 = coef<A>(g, 3);
 #pragma unroll 2
     QIPB_SWEEP(w, ngroups) {
         A *p = tile + ex(w);
@@ -227,7 +315,7 @@ __device__ __forceinline__ void sweep_dense1_stage(A *tile, const DevGate &g, co
     const u32 o1 = 1u << g.tl[0];
     const u32 nm = g.nmask[0];
     const u32 sor = sr.sor, lom = sr.nlo - 1u;
-    const Cf<A> m0 = cf<A>(g.m[0]), m1 = cf<A>(g.m[1]), m2 = cf<A>(g.m[2]), m3 = cf<A>(g.m[3]);
+    const Cf<A> m0 = coef<A>(g, 0), m1 = coef<A>(g, 1), m2 = coef<A>(g, 2), m3 = coef<A>(g, 3);
     const double2 *__restrict__ Th = sr.T + sr.nlo;
     const u32 e_first = (u32)tid + ((u32)tid & nm);
     const double2 SL0 = cmul<double2>(sr.S, sr.T[e_first & lom]);
@@ -328,9 +416,8 @@ __device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX e
         if (g.tl[j] == 0xFF) sel_out |= (u32)((base >> g.tg[j]) & 1ull) << (g.k - 1 - j);
     const int D = 1 << g.k;
     if (g.kin == 0) {
-        const double2 d = g.m[sel_out * D + sel_out];
-        if (d.x == 1.0 && d.y == 0.0) return;
-        const Cf<A> c = cf<A>(d);
+        const Cf<A> c = coef<A>(g, sel_out * D + sel_out);
+        if (c.x == 1 && c.y == 0) return;
 #pragma unroll 4
         QIPB_SWEEP(w, ngroups) {
             const u32 e = ex(w);
@@ -340,7 +427,7 @@ __device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX e
         const int j = (g.tl[0] != 0xFF) ? 0 : 1;
         const u32 o1 = 1u << g.tl[j];
         const u32 s1 = 1u << (g.k - 1 - j);
-        const Cf<A> d0 = cf<A>(g.m[sel_out * D + sel_out]), d1 = cf<A>(g.m[(sel_out | s1) * D + (sel_out | s1)]);
+        const Cf<A> d0 = coef<A>(g, sel_out * D + sel_out), d1 = coef<A>(g, (sel_out | s1) * D + (sel_out | s1));
 #pragma unroll 2
         QIPB_SWEEP(w, ngroups) {
             A *p = tile + ex(w);
@@ -349,7 +436,7 @@ __device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX e
         }
     } else {
         const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
-        const Cf<A> d0 = cf<A>(g.m[0]), d1 = cf<A>(g.m[5]), d2 = cf<A>(g.m[10]), d3 = cf<A>(g.m[15]);
+        const Cf<A> d0 = coef<A>(g, 0), d1 = coef<A>(g, 5), d2 = coef<A>(g, 10), d3 = coef<A>(g, 15);
 #pragma unroll 1
         QIPB_SWEEP(w, ngroups) {
             A *p = tile + ex(w);
@@ -391,6 +478,10 @@ __device__ __forceinline__ void run_op(A *tile, const DevGate &g, const DevGate 
         default: sweep_diag<A, false, NT>(tile, g, ExpandAny(g), ngroups, base, tid); break;
         }
     } else if (g.k == 2) {
+        if (nins == 2 && (g.tl[0] < LowBits<A>::value || g.tl[1] < LowBits<A>::value)) {
+            sweep_dense2_low<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid);
+            return;
+        }
         switch (nins) {
         case 2: sweep_dense2<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid); break;
         case 3: sweep_dense2<A, UNI, NT>(tile, g, Expand<3>(g), ngroups, tid); break;
@@ -400,6 +491,10 @@ __device__ __forceinline__ void run_op(A *tile, const DevGate &g, const DevGate 
     } else {
         if (g.post != 0 && (base & next.out_ctrl) == next.out_ctrl) {     // host guarantees nins == 1, no controls
             sweep_dense1_stage<A, UNI, NT>(tile, g, stage_ref(next, tables, stage_S[gi + 1], tb), ngroups, tid);
+            return;
+        }
+        if (nins == 1 && g.tl[0] < LowBits<A>::value) {
+            sweep_dense1_low<A, UNI, NT>(tile, g, Expand<1>(g), ngroups, tid);
             return;
         }
         switch (nins) {
@@ -939,7 +1034,12 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
                     }
                 }
                 const int D = 1 << s.k;
-                for (int e = 0; e < D * D; ++e) d.m[e] = make_double2(s.mat[2 * e], s.mat[2 * e + 1]);
+                if (dtype == QIPB_C64) {            // the kernel reads float2 over the same bytes (coef<float2>)
+                    float2 *mf = reinterpret_cast<float2 *>(d.m);
+                    for (int e = 0; e < D * D; ++e) mf[e] = make_float2((float)s.mat[2 * e], (float)s.mat[2 * e + 1]);
+                } else {
+                    for (int e = 0; e < D * D; ++e) d.m[e] = make_double2(s.mat[2 * e], s.mat[2 * e + 1]);
+                }
             }
             d.out_ctrl = ctrl_mask & ~tmask;
             d.in_or = 0;

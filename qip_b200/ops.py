@@ -431,18 +431,20 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
 
 
 # --------------------------------------------------------------------------------- strategy choice
-# Cost of one gate inside a fused tile pass, as a fraction of one full HBM sweep (read + write of
-# the whole state), calibrated on B200 (profiles/): the tile kernel becomes shared-memory / issue
-# bound once the gate list is long.  plan() uses it to choose between
+# Cost of one dense 2-qubit gate inside a fused tile pass, as a fraction of one full HBM sweep (read +
+# write of the whole state), calibrated on B200 (profiles/r01_probe_fused_final.txt: 11.3 ms floor at 31
+# qubits, 15.4 ms with 4 dense gates, 27 ms with 8): the sweeps are FP64-issue bound and only the first
+# two hide behind the tile traffic.  plan() uses it to choose between
 #   A. blocks of <= 2 qubits -> fused tile passes (diagonal gates and controls anywhere), and
 #   B. blocks of <= 4 qubits -> one register-blocked stand-alone launch per block (HBM roofline).
-TILE_GATE_COST = 0.45
+TILE_GATE_COST = 0.23
 
 
 def pass_cost(p: Pass, nbits: int, amp_bytes: int) -> float:
-    """Estimated cost of a pass in HBM-byte equivalents, calibrated at 33 qubits complex128 on B200
-    (profiles/): a fused pass costs one full sweep of HBM traffic overlapped with ~0.45 sweep-times of
-    shared-memory work per dense gate; the register-blocked K=3/K=4 kernels are FP64-limited."""
+    """Estimated cost of a pass in HBM-byte equivalents, calibrated at 31/33 qubits complex128 on B200
+    (profiles/): a fused pass costs one full sweep of HBM traffic overlapped with ~0.23 sweep-times of
+    shared-memory / FP64 work per dense 2-qubit gate (0.15 per dense 1-qubit gate); the register-blocked
+    K=3/K=4 kernels are FP64-limited."""
     full = 2.0 * amp_bytes * 2.0 ** nbits
     if not p.fused:
         g = p.gates[0]
@@ -456,7 +458,7 @@ def pass_cost(p: Pass, nbits: int, amp_bytes: int) -> float:
         elif g.diagonal or g.k == 0:
             work += 0.1 * frac
         else:
-            work += frac
+            work += frac * (1.0 if g.k >= 2 else 0.65)
     return full * max(1.0, 0.5 + TILE_GATE_COST * work)
 
 
