@@ -64,7 +64,10 @@ int qipb_memcpy_d2h(qipb_ctx *ctx, void *dst_host, const void *src_dev, size_t b
  * qipb_init_basis: all zeros, and amplitude `index` = 1 if 0 <= index < 2^nbits (pass -1 on
  *   shards that do not own |0...0>) -- the empty-feed case, qip/backend.py:90-91.
  * qipb_init_kron: state[i] = prod_g feeds_g[sub_g(G)] where G = (shard_index << nbits) | i is
- *   the global index, for every G with (G & zero_mask) == 0, else 0.  Group g lists
+ *   the global index, for every G with (G & fixed_mask) == fixed_value, else 0 (un-fed qubits are
+ *   fixed to 0; a group fed with a one-hot basis index -- qip/distributed/backend.py:42-45, and the
+ *   int `Qubit.default` of qip/pipeline.py:101-109 -- is fixed to that index instead of being
+ *   multiplied in, so no 2^k vector is ever built).  ngroups may be 0.  Group g lists
  *   group_len[g] GLOBAL bit positions in group_bits (concatenated, most significant sub-index
  *   bit first, i.e. the order of the reference's index group).  feeds_dev = the groups'
  *   vectors concatenated, complex128, on the device.  The product is taken left to right
@@ -72,7 +75,7 @@ int qipb_memcpy_d2h(qipb_ctx *ctx, void *dst_host, const void *src_dev, size_t b
 int qipb_init_basis(qipb_ctx *ctx, void *state, int nbits, int dtype, long long index);
 int qipb_init_kron(qipb_ctx *ctx, void *state, int nbits, int dtype, int ngroups,
                    const int *group_len, const int *group_bits, const void *feeds_dev,
-                   uint64_t zero_mask, uint64_t shard_index);
+                   uint64_t fixed_mask, uint64_t fixed_value, uint64_t shard_index);
 
 /* ---- gate application ----------------------------------------------------------------------
  * Replaces cdot_loop (qip/ext/kronprod.pyx:43-200) for ONE entry of a `mats` dict after the host

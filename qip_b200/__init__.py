@@ -8,7 +8,8 @@ the graph front-end stays the reference's.  See DESIGN.md and INTEGRATION.md.
 """
 from .mats import CMat, SwapMat
 from .backend import B200Backend, DeviceState
+from .graph import CompiledCircuit, compile_circuit, run
 
 make_state = B200Backend.make_state
 
-__all__ = ["B200Backend", "DeviceState", "CMat", "SwapMat", "make_state"]
+__all__ = ["B200Backend", "DeviceState", "CMat", "SwapMat", "make_state", "CompiledCircuit", "compile_circuit", "run"]

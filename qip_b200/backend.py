@@ -36,6 +36,25 @@ def _torch():
     return torch
 
 
+# Library contexts own small device / pinned scratch buffers (reduction partials, stage tables, the kron
+# table); creating and destroying them costs cudaMalloc / cudaFree / cudaMallocHost calls that synchronise
+# the device.  One run() = one backend object, so contexts are pooled per device and re-used.
+_CTX_POOL = {}
+
+
+def _acquire_ctx(L, dev_index):
+    pool = _CTX_POOL.setdefault(dev_index, [])
+    if pool:
+        return pool.pop()
+    ctx = ctypes.c_void_p()
+    _lib.check(L.qipb_create(dev_index, ctypes.byref(ctx)))
+    return ctx
+
+
+def _release_ctx(dev_index, ctx):
+    _CTX_POOL.setdefault(dev_index, []).append(ctx)
+
+
 class DeviceState(object):
     """Array-like handle on a device-resident state (returned by get_state() for large n, accepted
     back as a feed).  Supports len(), .shape, numpy.asarray(), slicing (D2H of the slice only)."""
@@ -60,7 +79,7 @@ class B200Backend(object):
     """StateType implementation on one B200 (see module docstring)."""
 
     def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
-                 strategy: str = "auto", relabel_swaps: bool = True):
+                 strategy: str = "auto", relabel_swaps: bool = True, host_state_max_qubits: int = _HOST_STATE_MAX_QUBITS):
         torch = _torch()
         self.L = _lib.load()
         if not torch.cuda.is_available():
@@ -75,6 +94,8 @@ class B200Backend(object):
         self.np_dtype = np.dtype(dtype)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.fuse = fuse
+        self.host_state_max_qubits = host_state_max_qubits   # get_state(): host ndarray up to here, DeviceState beyond
+        self.plan_cache = None       # (dict, key) set by qip_b200.graph.CompiledCircuit: planned passes per gate segment
         import os
         self.tile_bits = int(os.environ.get("QIPB_TILE_BITS", tile_bits))               # tuning knob for profiling runs
         self.min_low_bits = int(os.environ.get("QIPB_MIN_LOW_BITS", min_low_bits))     # tuning knob for profiling runs
@@ -83,9 +104,9 @@ class B200Backend(object):
         # (free) and the state is brought back to canonical order when it is read out in index order.
         self.relabel_swaps = relabel_swaps and fuse
         self.pos = [self.n - 1 - q for q in range(self.n)]
-        ctx = ctypes.c_void_p()
-        _lib.check(self.L.qipb_create(self.device.index or 0, ctypes.byref(ctx)))
-        self.ctx = ctx
+        self.ctx = _acquire_ctx(self.L, self.device.index or 0)
+        self._launch_base = int(self.L.qipb_launch_count(self.ctx))
+        self._ring_base = int(self.L.qipb_ring_launch_count(self.ctx))
         self.state = None            # torch tensor, 2^n amplitudes
         self.queue: List[Gate] = []        # logical gates, merged / lowered / planned at flush time
         self.stats = {"gates": 0, "passes": 0, "fused_passes": 0, "flushes": 0}
@@ -133,29 +154,15 @@ class B200Backend(object):
             if len(groups) == 0:                               # qip/backend.py:90-91
                 _lib.check(self.L.qipb_init_basis(self.ctx, self._ptr(), n, self.code, 0))
                 return
-            feeds = []
-            for g, f in zip(groups, feed_list):
-                if isinstance(f, (int, np.integer)):           # one-hot index, qip/distributed/backend.py:42-45
-                    v = np.zeros(2 ** len(g), dtype=np.complex128)
-                    v[int(f)] = 1.0
-                elif isinstance(f, DeviceState):
-                    v = np.asarray(f, dtype=np.complex128)
-                else:
-                    v = np.asarray(f, dtype=np.complex128).reshape(-1)
-                if v.shape[0] != 2 ** len(g):
-                    raise ValueError("feed length {} does not match 2**{} for group {}".format(v.shape[0], len(g), g))
-                feeds.append(v)
-            cat = np.ascontiguousarray(np.concatenate(feeds))
-            dev_feeds = torch.from_numpy(cat).to(self.device)
-            zero_mask = 0
-            fed = set(flat)
-            for q in range(n):
-                if q not in fed:
-                    zero_mask |= 1 << (n - 1 - q)
-            glen = _lib.int_array([len(g) for g in groups])
-            gbits = _lib.int_array([n - 1 - q for q in flat])
-            _lib.check(self.L.qipb_init_kron(self.ctx, self._ptr(), n, self.code, len(groups), glen, gbits,
-                                             ctypes.c_void_p(dev_feeds.data_ptr()), zero_mask, 0))
+            vgroups, vfeeds, fixed_mask, fixed_value = split_feeds(groups, feed_list, n, lambda q: n - 1 - q)
+            if not vgroups:                                    # only one-hot feeds: a basis state
+                _lib.check(self.L.qipb_init_basis(self.ctx, self._ptr(), n, self.code, fixed_value))
+                return
+            dev_feeds = feeds_to_device(vfeeds, self.device)
+            glen = _lib.int_array([len(g) for g in vgroups])
+            gbits = _lib.int_array([n - 1 - q for g in vgroups for q in g])
+            _lib.check(self.L.qipb_init_kron(self.ctx, self._ptr(), n, self.code, len(vgroups), glen, gbits,
+                                             ctypes.c_void_p(dev_feeds.data_ptr()), fixed_mask, fixed_value, 0))
             self._keepalive = dev_feeds
 
     # ------------------------------------------------------------------ gate path
@@ -169,6 +176,16 @@ class B200Backend(object):
                 self.queue.append(s)
                 self.stats["gates"] += 1
 
+    def apply_gates(self, gates, cache=None, key=None) -> None:
+        """Queue gates that are already decoded and simplified (ops.Gate) and run them as one segment.
+        With `cache`/`key` (qip_b200.graph.CompiledCircuit) the planned passes of the segment are
+        remembered, so a replay skips merging and planning altogether."""
+        self.queue.extend(gates)
+        self.stats["gates"] += len(gates)
+        if cache is not None:
+            self.plan_cache = (cache, key)
+        self.flush()
+
     def _launch_single(self, g: BitGate):
         if g.kind == "swap":
             _lib.check(self.L.qipb_apply_swap(self.ctx, self._ptr(), self.n, self.code, g.bits[0], g.bits[1], g.ctrl_mask))
@@ -179,30 +196,47 @@ class B200Backend(object):
     _SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
 
     def _launch_fused(self, p: Pass):
-        arr = (_lib.Gate * len(p.gates))()
-        for i, g in enumerate(p.gates):
-            mat, diag = (self._SWAP4, False) if g.kind == "swap" else (g.mat, g.diagonal)
-            arr[i].k = g.k
-            arr[i].diagonal = 1 if diag else 0
-            for j, b in enumerate(g.bits):
-                arr[i].bits[j] = b
-            arr[i].ctrl_mask = g.ctrl_mask
-            flat = np.ascontiguousarray(mat, dtype=np.complex128).reshape(-1)
-            ctypes.memmove(arr[i].mat, flat.ctypes.data, 16 * flat.size)
+        packed = getattr(p, "_packed", None)       # the C structs of a pass are built once (compiled circuits replay passes)
+        if packed is None:
+            arr = (_lib.Gate * len(p.gates))()
+            for i, g in enumerate(p.gates):
+                mat, diag = (self._SWAP4, False) if g.kind == "swap" else (g.mat, g.diagonal)
+                arr[i].k = g.k
+                arr[i].diagonal = 1 if diag else 0
+                for j, b in enumerate(g.bits):
+                    arr[i].bits[j] = b
+                arr[i].ctrl_mask = g.ctrl_mask
+                flat = np.ascontiguousarray(mat, dtype=np.complex128).reshape(-1)
+                ctypes.memmove(arr[i].mat, flat.ctypes.data, 16 * flat.size)
+            packed = (arr, _lib.int_array(p.tile_bits))
+            p._packed = packed
         _lib.check(self.L.qipb_apply_fused(self.ctx, self._ptr(), self.n, self.code, len(p.tile_bits),
-                                           _lib.int_array(p.tile_bits), len(p.gates), arr))
+                                           packed[1], len(p.gates), packed[0]))
 
     def flush(self) -> None:
         """Execute every queued gate.  Called before anything reads or measures the state."""
         if not self.queue:
             return
-        torch = _torch()
-        gates = self._relabel(self.queue)
-        self.queue = []
-        if not gates:
-            return
-        passes, chosen = plan(gates, self.n, self.amp_bytes, fuse=self.fuse, tile_bits=self.tile_bits,
-                              min_low_bits=self.min_low_bits, strategy=self.strategy)
+        cache, key = self.plan_cache if self.plan_cache is not None else (None, None)
+        self.plan_cache = None
+        if cache is not None and key in cache and cache[key][0] == tuple(self.pos):
+            # a compiled circuit replays this segment: same gates, same starting bit map -> same passes
+            _, passes, chosen, pos_after, nrelabels = cache[key]
+            self.queue = []
+            self.pos = list(pos_after)
+            if nrelabels:
+                self.stats["relabels"] = self.stats.get("relabels", 0) + nrelabels
+        else:
+            pos_before = tuple(self.pos)
+            r0 = self.stats.get("relabels", 0)
+            gates = self._relabel(self.queue)
+            self.queue = []
+            if not gates:
+                return
+            passes, chosen = plan(gates, self.n, self.amp_bytes, fuse=self.fuse, tile_bits=self.tile_bits,
+                                  min_low_bits=self.min_low_bits, strategy=self.strategy)
+            if cache is not None:
+                cache[key] = (pos_before, passes, chosen, tuple(self.pos), self.stats.get("relabels", 0) - r0)
         self.stats["strategy_" + chosen] = self.stats.get("strategy_" + chosen, 0) + 1
         self._run_passes(passes)
         self.stats["flushes"] += 1
@@ -402,7 +436,7 @@ class B200Backend(object):
         self._canonicalise()
         with torch.cuda.device(self.device):
             torch.cuda.current_stream(self.device).synchronize()
-            if self.n <= _HOST_STATE_MAX_QUBITS:
+            if self.n <= self.host_state_max_qubits:
                 return self.state.cpu().numpy()
             return DeviceState(self.state)
 
@@ -433,7 +467,11 @@ class B200Backend(object):
             torch.cuda.current_stream(self.device).synchronize()
 
     def launch_count(self) -> int:
-        return int(self.L.qipb_launch_count(self.ctx))
+        """Kernels launched for this state (library contexts are pooled, their counters are cumulative)."""
+        return int(self.L.qipb_launch_count(self.ctx)) - self._launch_base
+
+    def ring_launch_count(self) -> int:
+        return int(self.L.qipb_ring_launch_count(self.ctx)) - self._ring_base
 
     def synchronize(self):
         self.flush()
@@ -441,7 +479,7 @@ class B200Backend(object):
 
     def close(self):
         if getattr(self, "ctx", None):
-            self.L.qipb_destroy(self.ctx)
+            _release_ctx(self.device.index or 0, self.ctx)
             self.ctx = None
         self.state = None
 
@@ -453,6 +491,65 @@ class B200Backend(object):
 
 
 # ---------------------------------------------------------------------- host helpers (CPU-testable)
+def split_feeds(groups, feed_list, n, bit_of):
+    """Separate the fed groups into vector feeds (multiplied into the kron product on the device) and
+    one-hot basis indices (python ints: qip/distributed/backend.py:42-45, and what an int `Qubit.default`
+    means, qip/pipeline.py:101-109), which only FIX index bits -- no 2^k vector is materialised for them.
+    Returns (vector groups, their feeds, fixed_mask, fixed_value) with masks over GLOBAL index bits
+    (`bit_of(q)`); un-fed qubits are fixed to 0.  A group's sub-index is big-endian over its qubit list
+    (qip/util.py:118-123)."""
+    vgroups, vfeeds = [], []
+    fixed_mask = fixed_value = 0
+    fed = set()
+    for g, f in zip(groups, feed_list):
+        fed.update(g)
+        if isinstance(f, (int, np.integer)) and not isinstance(f, bool):
+            v = int(f)
+            if not (0 <= v < 2 ** len(g)):
+                raise ValueError("one-hot feed index {} out of range for {} qubits".format(v, len(g)))
+            for t, q in enumerate(g):
+                fixed_mask |= 1 << bit_of(q)
+                if (v >> (len(g) - 1 - t)) & 1:
+                    fixed_value |= 1 << bit_of(q)
+            continue
+        length = f.shape[0] if hasattr(f, "shape") and len(getattr(f, "shape")) == 1 else None
+        if length is None:
+            f = np.asarray(f, dtype=np.complex128).reshape(-1)
+            length = f.shape[0]
+        if length != 2 ** len(g):
+            raise ValueError("feed length {} does not match 2**{} for group {}".format(length, len(g), g))
+        vgroups.append(list(g))
+        vfeeds.append(f)
+    for q in range(n):
+        if q not in fed:
+            fixed_mask |= 1 << bit_of(q)
+    return vgroups, vfeeds, fixed_mask, fixed_value
+
+
+def feeds_to_device(vfeeds, device):
+    """Concatenate the vector feeds as complex128 on `device`.  Feeds that already live on a GPU
+    (DeviceState handles, torch tensors) never touch the host."""
+    torch = _torch()
+    parts = []
+    host_run = []
+
+    def flush_host():
+        if host_run:
+            cat = np.ascontiguousarray(np.concatenate(host_run))
+            parts.append(torch.from_numpy(cat).to(device))
+            host_run.clear()
+
+    for f in vfeeds:
+        t = f.tensor if isinstance(f, DeviceState) else f
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            flush_host()
+            parts.append(t.to(device=device, dtype=torch.complex128).reshape(-1))
+        else:
+            host_run.append(np.asarray(t, dtype=np.complex128).reshape(-1))
+    flush_host()
+    return parts[0] if len(parts) == 1 else torch.cat(parts)
+
+
 def kernel_label(p: Pass, nbits: int, amp_bytes: int):
     """(kernel name, algorithmic HBM bytes of the launch) for bench.py's roofline accounting."""
     from .ops import gate_bytes
@@ -502,6 +599,9 @@ def tabulate(func, nbits_in: int) -> np.ndarray:
     """f(x) for x < 2^nbits_in as int64 (qip/ext/func_apply.pyx:66-69).  Tries one vectorised call
     on a numpy array first (and cross-checks it on a sample), falls back to the reference's loop."""
     size = 2 ** nbits_in
+    table = getattr(func, "table", None)                       # a function that carries its own table (qip_b200.functions)
+    if isinstance(table, np.ndarray) and table.shape == (size,) and table.dtype.kind in "iu":
+        return np.ascontiguousarray(table, dtype=np.int64)
     xs = np.arange(size, dtype=np.int64)
     try:
         ys = func(xs)

@@ -25,12 +25,15 @@ extern "C" int qipb_create(int device, qipb_ctx **out) {
     QIPB_CUDA(cudaGetDeviceCount(&ndev));
     QIPB_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d visible)", device, ndev);
     QIPB_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    QIPB_CUDA(cudaGetDeviceProperties(&prop, device));
-    QIPB_REQUIRE(prop.major >= 10, "libqipb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    // single attributes, not cudaGetDeviceProperties (tens of milliseconds: a context is made per run())
+    int major = 0, minor = 0, sms = 0;
+    QIPB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    QIPB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    QIPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    QIPB_REQUIRE(major >= 10, "libqipb200 is built for sm_100a only; device %d is sm_%d%d", device, major, minor);
     qipb_ctx *c = new qipb_ctx();
     c->device = device;
-    c->sm_count = prop.multiProcessorCount;
+    c->sm_count = sms;
     c->stream = 0;
     c->scratch = nullptr;
     c->scratch_bytes = 0;
@@ -39,6 +42,7 @@ extern "C" int qipb_create(int device, qipb_ctx **out) {
     c->tab_dev = nullptr;
     c->tab_cap = 0;
     c->tab_slot = 0;
+    c->kron_table = nullptr;
     for (int i = 0; i < 4; ++i) { c->tab_host[i] = nullptr; c->tab_ev[i] = nullptr; }
     *out = c;
     return QIPB_OK;
@@ -49,6 +53,7 @@ extern "C" int qipb_destroy(qipb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->tab_dev) cudaFree(ctx->tab_dev);
+    if (ctx->kron_table) cudaFree(ctx->kron_table);
     for (int i = 0; i < 4; ++i) {
         if (ctx->tab_host[i]) cudaFreeHost(ctx->tab_host[i]);
         if (ctx->tab_ev[i]) cudaEventDestroy(ctx->tab_ev[i]);

@@ -140,4 +140,5 @@ struct qipb_ctx {
     double2 *tab_host[4];
     cudaEvent_t tab_ev[4];
     int tab_slot;
+    double2 *kron_table;           // init.cu: product of the low-bit feed groups, 2^12 entries
 };

@@ -1,0 +1,48 @@
+"""Vectorised oracle functions for `F(func, reg1, reg2)`.
+
+The reference tabulates `func` with 2^|reg1| python calls on every `func_apply`
+(qip/ext/func_apply.pyx:66-69).  The functions here accept python ints AND numpy int64 arrays, so
+B200Backend.func_apply tabulates them with one vectorised call; `tabulated(f, nbits)` attaches the table
+itself (built once, reused by every application and by compiled circuits)."""
+import numpy as np
+
+
+def equals(x0: int):
+    """x -> 1 if x == x0 else 0: the Grover oracle of examples/grovers_iterative.py:20-21."""
+    def f(x):
+        return (x == x0) * 1
+    return f
+
+
+def modexp(base: int, modulus: int):
+    """i -> base**i mod modulus: the Shor oracle of examples/shors.py:113 (`pow(x, i, N)`), by
+    square-and-multiply on int64 arrays (exact while modulus < 2**31)."""
+    base, modulus = int(base), int(modulus)
+    if not (0 < modulus < 2 ** 31):
+        raise ValueError("modexp needs 0 < modulus < 2**31")
+
+    def f(i):
+        if isinstance(i, (int, np.integer)):
+            return pow(base, int(i), modulus)
+        e = np.asarray(i, dtype=np.int64).copy()
+        result = np.ones_like(e)
+        b = np.int64(base % modulus)
+        while np.any(e > 0):
+            odd = (e & 1) == 1
+            result[odd] = (result[odd] * b) % modulus
+            b = (b * b) % modulus
+            e >>= 1
+        return result
+    return f
+
+
+class tabulated(object):
+    """`func` with its table over nbits input bits attached (`.table`, int64)."""
+
+    def __init__(self, func, nbits: int):
+        from .backend import tabulate
+        self.func = func
+        self.table = tabulate(func, nbits)
+
+    def __call__(self, x):
+        return self.table[x]

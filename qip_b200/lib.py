@@ -74,7 +74,7 @@ def load():
     L.qipb_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
     L.qipb_memcpy_d2h.argtypes = [vp, vp, vp, ctypes.c_size_t]
     L.qipb_init_basis.argtypes = [vp, vp, ci, ci, ctypes.c_longlong]
-    L.qipb_init_kron.argtypes = [vp, vp, ci, ci, ci, i32p, i32p, vp, u64, u64]
+    L.qipb_init_kron.argtypes = [vp, vp, ci, ci, ci, i32p, i32p, vp, u64, u64, u64]
     L.qipb_apply_matrix.argtypes = [vp, vp, ci, ci, ci, i32p, dblp, u64, ci]
     L.qipb_apply_swap.argtypes = [vp, vp, ci, ci, ci, ci, u64]
     L.qipb_apply_fused.argtypes = [vp, vp, ci, ci, ci, i32p, ci, ctypes.POINTER(Gate)]

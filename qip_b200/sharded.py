@@ -137,7 +137,10 @@ class ShardedB200Backend(object):
         if len(groups) != len(feed_list) or len(set(flat)) != len(flat) or any(not (0 <= q < n) for q in flat):
             raise ValueError("bad feed groups")
         for g, f in zip(groups, feed_list):
-            if not isinstance(f, (int, np.integer)) and np.asarray(f).reshape(-1).shape[0] != 2 ** len(g):
+            if isinstance(f, (int, np.integer)):
+                if not (0 <= int(f) < 2 ** len(g)):
+                    raise ValueError("one-hot feed index out of range")
+            elif (f.shape[0] if hasattr(f, "shape") and len(f.shape) == 1 else np.asarray(f).reshape(-1).shape[0]) != 2 ** len(g):
                 raise ValueError("feed length does not match 2**len(group)")
         self._pending_init = (groups, list(feed_list))
         if not self.lazy_layout:
@@ -160,28 +163,27 @@ class ShardedB200Backend(object):
         if not groups:
             _lib.check(self.L.qipb_init_basis(self.ctx, self.ptr, nl, self.code, 0 if self.rank == 0 else -1))
             return
-        feeds = []
-        for g, f in zip(groups, feed_list):
-            if isinstance(f, (int, np.integer)):
-                v = np.zeros(2 ** len(g), dtype=np.complex128)
-                v[int(f)] = 1.0
-            else:
-                v = np.asarray(f, dtype=np.complex128).reshape(-1)
-            if v.shape[0] != 2 ** len(g):
-                raise ValueError("feed length does not match 2**len(group)")
-            feeds.append(v)
-        dev_feeds = torch.from_numpy(np.ascontiguousarray(np.concatenate(feeds))).to(self.device)
-        zero_mask = 0
-        for q in range(n):
-            if q not in flat:
-                zero_mask |= 1 << pos[q]
-        _lib.check(self.L.qipb_init_kron(self.ctx, self.ptr, nl, self.code, len(groups),
-                                         _lib.int_array([len(g) for g in groups]),
-                                         _lib.int_array([pos[q] for q in flat]),
-                                         ctypes.c_void_p(dev_feeds.data_ptr()), zero_mask, self.rank))
+        from .backend import feeds_to_device, split_feeds
+        vgroups, vfeeds, fixed_mask, fixed_value = split_feeds(groups, feed_list, n, lambda q: pos[q])
+        if not vgroups:                                        # only one-hot feeds: a basis state
+            mine = (fixed_value >> nl) == self.rank
+            _lib.check(self.L.qipb_init_basis(self.ctx, self.ptr, nl, self.code,
+                                              (fixed_value & ((1 << nl) - 1)) if mine else -1))
+            return
+        dev_feeds = feeds_to_device(vfeeds, self.device)
+        _lib.check(self.L.qipb_init_kron(self.ctx, self.ptr, nl, self.code, len(vgroups),
+                                         _lib.int_array([len(g) for g in vgroups]),
+                                         _lib.int_array([pos[q] for g in vgroups for q in g]),
+                                         ctypes.c_void_p(dev_feeds.data_ptr()), fixed_mask, fixed_value, self.rank))
         self._keep = dev_feeds
 
     # ------------------------------------------------------------------ gates
+    def apply_gates(self, gates, cache=None, key=None) -> None:
+        """Pre-decoded gates of a compiled circuit (qip_b200.graph); scheduling is redone per run because
+        the exchange plan depends on the whole queue."""
+        self.queue.extend(gates)
+        self.stats["gates"] += len(gates)
+
     def kronselect_dot(self, mats, input_offset: int = 0, output_offset: int = 0) -> None:
         if input_offset != 0 or output_offset != 0:
             raise ValueError("offset windows are not supported; the state is sharded by its top qubits")

@@ -93,6 +93,36 @@ def main():
     want[0] = 1
     assert np.array_equal(g.get_state(), want)
     g.close()
+    # one-hot int feeds (qip/distributed/backend.py:42-45) mixed with a vector group: only index bits are fixed
+    groups3, hot = [[3, 0, 9], [1, 2], [11, 10, 4, 5]], np.zeros(8)
+    hot[6] = 1.0
+    v3 = rng.normal(size=4) + 1j * rng.normal(size=4)
+    hot16 = np.zeros(16)
+    hot16[9] = 1.0
+    g = ShardedB200Backend.make_state(n, groups3, [6, v3, 9])
+    c = orc.OracleBackend.make_state(n, groups3, [hot, v3, hot16])
+    check("one-hot feeds", g.get_state(), c.get_state(), 1e-15)
+    g.close()
+    g = ShardedB200Backend.make_state(n, [list(range(n))], [2741])            # a basis state, no vector at all
+    assert int(np.argmax(np.abs(g.get_state()))) == 2741 and abs(g.total_prob() - 1.0) < 1e-15
+    g.close()
+    # production-size shards (2^24 amplitudes each: the specialised fused kernels, the multi-bit remap): QFFT of
+    # a basis state |j> against its closed form e^{+2 pi i j k / N} / sqrt(N)
+    G = int(np.log2(world))
+    nb = 24 + G
+    j = 0x5A5A5A5 & ((1 << nb) - 1)
+    g = ShardedB200Backend.make_state(nb, [list(range(nb))], [j])
+    for mats in qfft_stream(nb):
+        g.kronselect_dot(mats)
+    assert abs(g.total_prob() - 1.0) < 1e-12
+    for start in (0, 12345, (1 << nb) - 4096, (1 << (nb - 1)) - 7):
+        k = np.arange(start, start + 2048, dtype=np.int64)
+        want = np.exp(2j * np.pi * ((j * k) & ((1 << nb) - 1)).astype(np.float64) / float(1 << nb)) / np.sqrt(float(1 << nb))
+        got = g.get_relative_range(start, start + 2048)
+        assert float(np.max(np.abs(got - want))) * np.sqrt(float(1 << nb)) <= 1e-9, ("big qfft", start)
+    if rank == 0:
+        print("OK big qfft n=%d exchanges=%d" % (nb, g.stats["exchanges"]))
+    g.close()
     dist.barrier()
     if rank == 0:
         print("SHARDED PARITY OK world=%d" % world)

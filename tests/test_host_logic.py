@@ -30,13 +30,6 @@ class PlannedHostBackend(orc.OracleBackend):
         return b
 
 
-class TileHostBackend(PlannedHostBackend):
-    strategy = "tile"
-
-
-class Dense4HostBackend(PlannedHostBackend):
-    strategy = "dense4"
-
     def kronselect_dot(self, mats, input_offset=0, output_offset=0):
         for g in ops.decode_mats(mats, self.n):
             s = ops.simplify(g)
@@ -78,6 +71,20 @@ class Dense4HostBackend(PlannedHostBackend):
     def total_prob(self):
         self._flush()
         return super().total_prob()
+
+    def apply_gates(self, gates, cache=None, key=None):       # compiled circuits (qip_b200.graph)
+        self.queue.extend(gates)
+
+    def close(self):
+        pass
+
+
+class TileHostBackend(PlannedHostBackend):
+    strategy = "tile"
+
+
+class Dense4HostBackend(PlannedHostBackend):
+    strategy = "dense4"
 
 
 SMALL = [i for i, s in enumerate(STREAMS) if s["n"] <= 12]
