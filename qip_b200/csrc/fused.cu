@@ -255,15 +255,23 @@ __device__ __forceinline__ void sweep_dense2_low(A *tile, const DevGate &g, cons
         A x[4], r[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) x[k] = p[off[k]];          // x[k] = member k ^ R
-        cswap<A>(R0, x[0], x[1]);                               // back to member order in registers
-        cswap<A>(R0, x[2], x[3]);
-        cswap<A>(R1, x[0], x[2]);
-        cswap<A>(R1, x[1], x[3]);
+        if (B & 1u) {                                           // back to member order in registers
+            cswap<A>(R0, x[0], x[1]);                           // (uniform branches: only the levels whose
+            cswap<A>(R0, x[2], x[3]);                           //  target really is a low bit cost selects)
+        }
+        if (B & 2u) {
+            cswap<A>(R1, x[0], x[2]);
+            cswap<A>(R1, x[1], x[3]);
+        }
         dense2_group<A>(m, x[0], x[1], x[2], x[3], r);
-        cswap<A>(R0, r[0], r[1]);
-        cswap<A>(R0, r[2], r[3]);
-        cswap<A>(R1, r[0], r[2]);
-        cswap<A>(R1, r[1], r[3]);
+        if (B & 1u) {
+            cswap<A>(R0, r[0], r[1]);
+            cswap<A>(R0, r[2], r[3]);
+        }
+        if (B & 2u) {
+            cswap<A>(R1, r[0], r[2]);
+            cswap<A>(R1, r[1], r[3]);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) p[off[k]] = r[k];
     }
@@ -948,15 +956,6 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     }
     f.lowrun = 0;
     while (f.lowrun < ntile_bits && tile_bits[f.lowrun] == f.lowrun) f.lowrun++;
-    if (fused3_enabled()) {                 // register-resident kernel (fused3.cu); -1 = not eligible
-        for (int gi = 0; gi < ngates; ++gi) {
-            const qipb_gate &s = gates[gi];
-            QIPB_REQUIRE(s.k >= 0 && s.k <= 2, "fused gate %d: k=%d unsupported", gi, s.k);
-            for (int j = 0; j < s.k; ++j) QIPB_REQUIRE(s.bits[j] >= 0 && s.bits[j] < nbits, "fused gate %d: bad target bit", gi);
-        }
-        const int rc3 = fused3_apply(ctx, state, nbits, dtype, ntile_bits, tile_bits, local_of, tmask, ngates, gates);
-        if (rc3 >= 0) return rc3;
-    }
     // ---- pass 1: validate, and fold runs of diagonal gates into stages ----
     std::vector<Op> ops;
     std::vector<cplx> tables;

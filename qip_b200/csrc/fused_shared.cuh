@@ -1,4 +1,4 @@
-// qip_b200/csrc/fused_shared.cuh -- pieces shared by the two fused-pass kernels (fused.cu, fused3.cu).
+// qip_b200/csrc/fused_shared.cuh -- mbarrier / bulk-copy primitives and host-side stage types of the fused pass (fused.cu).
 #pragma once
 #include <complex>
 #include <vector>
@@ -91,8 +91,5 @@ bool stages_enabled();
 void build_stages(const qipb_gate *gates, const std::vector<int> &run, int nbits, int tb, const int *local_of,
                   u64 tmask, std::vector<Op> &ops, std::vector<cplx> &tables, int min_run);
 int upload_tables(qipb_ctx *ctx, const std::vector<cplx> &tables, const double2 **out);
-bool fused3_enabled();
-int fused3_apply(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
-                 const int *local_of, u64 tmask, int ngates, const qipb_gate *gates);
 
 }  // namespace qipb

@@ -10,8 +10,6 @@ import sys
 
 
 def short(name):
-    if "fused3_kernel" in name:
-        return "fused3_kernel"
     if "fused_kernel" in name:
         return "fused_kernel"
     return name.split("(")[0].replace("void ", "").replace("qipb::", "")
