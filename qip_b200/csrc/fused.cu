@@ -13,8 +13,10 @@
 //   * runs of >= 3 consecutive diagonal gates are folded on the host into a "stage": per-cell phase
 //     tables (tile-lo, tile-hi, groups of <= 7 outside bits) applied in one sweep (a QFT stage is
 //     ~n controlled phases).
-// Roofline: HBM-bound until the gate list is long enough for shared-memory bandwidth / FP64 to
-// take over (about 5 dense gates per pass at 3 CTAs/SM); 2 * sizeof(amp) * 2^nbits bytes per pass.
+// Roofline: 2 * sizeof(amp) * 2^nbits bytes per pass against HBM; the tile pipeline alone runs at the copy
+// roofline (6.1 TB/s measured), a sweep costs >= 2^TB * 32 B of shared-memory traffic (1024 cycles per tile at
+// 128 B/clk) or, for general complex 4x4 blocks, 128 FP64 issue cycles per group; the first two dense sweeps of
+// a pass hide behind the tile traffic, each further one adds ~0.25 of a sweep of HBM time.
 #include <stdlib.h>
 #include <complex>
 #include <vector>
@@ -37,7 +39,10 @@ struct DevGate {
     unsigned char tg[2];    // target j: position in the state index
     u32 nmask[FUSED_MAX_INS];   // ~((1 << p) - 1) for the fixed positions p, ascending
     u32 in_or;              // tile-local mask of in-tile control bits
-    u32 post;               // dense 1-qubit gate without controls: the NEXT op is a stage applied in the same sweep
+    unsigned char post;     // dense 1-qubit gate without controls: the NEXT op is a stage applied in the same sweep
+    unsigned char mk;       // dense 2-qubit block: MK_GENERAL / MK_REAL / MK_REALPHASE / MK_MONOMIAL (coefficient layout below)
+    unsigned char phmask;   // MK_REALPHASE: columns with a non-trivial phase; MK_MONOMIAL: columns whose coefficient is not 1
+    unsigned char perm;     // MK_MONOMIAL: bits 2j..2j+1 = the row that column j maps to
     u64 out_ctrl;           // state-index mask of controls outside the tile
     double2 m[16];
 };
@@ -72,13 +77,6 @@ static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel para
 
 // matrix coefficient in the amplitude's precision
 template <typename A> struct Cf { typename amp_traits<A>::real x, y; };
-template <typename A> __device__ __forceinline__ Cf<A> cf(const double2 m) {
-    typedef typename amp_traits<A>::real R;
-    Cf<A> c;
-    c.x = (R)m.x;
-    c.y = (R)m.y;
-    return c;
-}
 // coefficient i of a gate descriptor, stored by the host in the amplitude's precision (complex64 launches
 // hold float2 over the same bytes: a per-use F2F of a warp-uniform double costs more than the FFMA it feeds)
 template <typename A> __device__ __forceinline__ Cf<A> coef(const DevGate &g, int i);
@@ -165,23 +163,76 @@ __device__ __forceinline__ void stage_scalars(const FusedArgs &f, u64 base, doub
 }
 
 // ---- dense 2-qubit gate: groups of four amplitudes ----
-template <typename A>
-__device__ __forceinline__ void dense2_group(const Cf<A> (&m)[16], const A a0, const A a1, const A a2, const A a3, A (&r)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        r[i] = cmulc<A>(m[4 * i], a0);
-        cfmac<A>(r[i], m[4 * i + 1], a1);
-        cfmac<A>(r[i], m[4 * i + 2], a2);
-        cfmac<A>(r[i], m[4 * i + 3], a3);
-    }
+// ---- dense 2-qubit blocks by matrix structure ----
+// The sweeps are bound by FP64 issue (a DFMA holds the dispatch port for two cycles), so the number of FP64
+// instructions per group is what counts.  Merged blocks of real-world circuits are rarely general: in the
+// layered benchmark 26 % are real (H (x) H with CX / Swap), 36 % are a real matrix times column phases
+// (an Rm folded in), 10 % are permutations with phases (Swap, CX with Rm's), 38 % general.  The host
+// (classify_block) picks the cheapest exact form:
+//   MK_GENERAL    16 complex coefficients                         64 FP64 instructions per group
+//   MK_REAL       16 real coefficients (first 16 scalars of m)    32
+//   MK_REALPHASE  M = R . diag(ph): phases at complex slots 8..11 32 + 4 per phased column
+//   MK_MONOMIAL   one non-zero per row/column: coefficients at complex slots 0..3, `perm`    4 per non-unit entry
+enum { MK_GENERAL = 0, MK_REAL = 1, MK_REALPHASE = 2, MK_MONOMIAL = 3 };
+
+template <typename A> __device__ __forceinline__ typename amp_traits<A>::real rcoef(const DevGate &g, int i) {
+    return reinterpret_cast<const typename amp_traits<A>::real *>(g.m)[i];
 }
 
-template <typename A, bool UNI, int NT, typename EX>
+template <typename A, int MK> struct Block2 {
+    typedef typename amp_traits<A>::real R;
+    Cf<A> m[MK == MK_GENERAL ? 16 : 4];
+    R r[MK == MK_GENERAL ? 1 : 16];
+    u32 phmask;
+    __device__ __forceinline__ explicit Block2(const DevGate &g) {
+        phmask = g.phmask;
+        if (MK == MK_GENERAL) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m[i] = coef<A>(g, i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = rcoef<A>(g, i);
+            if (MK == MK_REALPHASE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = coef<A>(g, 8 + j);
+            }
+        }
+    }
+    __device__ __forceinline__ void apply(A a0, A a1, A a2, A a3, A (&o)[4]) const {
+        if (MK == MK_GENERAL) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                o[i] = cmulc<A>(m[4 * i], a0);
+                cfmac<A>(o[i], m[4 * i + 1], a1);
+                cfmac<A>(o[i], m[4 * i + 2], a2);
+                cfmac<A>(o[i], m[4 * i + 3], a3);
+            }
+        } else {
+            if (MK == MK_REALPHASE) {                          // uniform branches: the mask comes from the descriptor
+                if (phmask & 1u) a0 = cmulc<A>(m[0], a0);
+                if (phmask & 2u) a1 = cmulc<A>(m[1], a1);
+                if (phmask & 4u) a2 = cmulc<A>(m[2], a2);
+                if (phmask & 8u) a3 = cmulc<A>(m[3], a3);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                o[i].x = r[4 * i] * a0.x;
+                o[i].y = r[4 * i] * a0.y;
+                o[i].x = fma(r[4 * i + 1], a1.x, o[i].x);
+                o[i].y = fma(r[4 * i + 1], a1.y, o[i].y);
+                o[i].x = fma(r[4 * i + 2], a2.x, o[i].x);
+                o[i].y = fma(r[4 * i + 2], a2.y, o[i].y);
+                o[i].x = fma(r[4 * i + 3], a3.x, o[i].x);
+                o[i].y = fma(r[4 * i + 3], a3.y, o[i].y);
+            }
+        }
+    }
+};
+
+template <typename A, bool UNI, int NT, int MK, typename EX>
 __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
-    Cf<A> m[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = coef<A>(g, i);
+    const Block2<A, MK> blk(g);
     if (UNI && (ngroups % (2 * NT)) == 0) {
         // two groups per iteration, all eight loads first: every coefficient fetched from the parameter
         // bank serves both groups, and the second group's loads overlap the first group's arithmetic
@@ -191,8 +242,8 @@ __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX
             const A a0 = p[0], a1 = p[ol], a2 = p[oh], a3 = p[oh + ol];
             const A b0 = q[0], b1 = q[ol], b2 = q[oh], b3 = q[oh + ol];
             A r[4], s[4];
-            dense2_group<A>(m, a0, a1, a2, a3, r);
-            dense2_group<A>(m, b0, b1, b2, b3, s);
+            blk.apply(a0, a1, a2, a3, r);
+            blk.apply(b0, b1, b2, b3, s);
             p[0] = r[0];
             p[ol] = r[1];
             p[oh] = r[2];
@@ -209,11 +260,39 @@ __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX
         A *p = tile + ex(w);
         const A a0 = p[0], a1 = p[ol], a2 = p[oh], a3 = p[oh + ol];
         A r[4];
-        dense2_group<A>(m, a0, a1, a2, a3, r);
+        blk.apply(a0, a1, a2, a3, r);
         p[0] = r[0];
         p[ol] = r[1];
         p[oh] = r[2];
         p[oh + ol] = r[3];
+    }
+}
+
+// permutation with phases (Swap, CX / CZ-like blocks with phase gates folded in): pure data movement plus at
+// most one complex multiply per amplitude; column j goes to row perm[j]
+template <typename A, bool UNI, int NT, typename EX>
+__device__ __forceinline__ void sweep_mono2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+    const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
+    const u32 perm = g.perm, phmask = g.phmask;
+    const Cf<A> c0 = coef<A>(g, 0), c1 = coef<A>(g, 1), c2 = coef<A>(g, 2), c3 = coef<A>(g, 3);
+    u32 dst[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const u32 row = (perm >> (2 * j)) & 3u;
+        dst[j] = ((row & 2u) ? oh : 0u) + ((row & 1u) ? ol : 0u);
+    }
+#pragma unroll 2
+    QIPB_SWEEP(w, ngroups) {
+        A *p = tile + ex(w);
+        A a0 = p[0], a1 = p[ol], a2 = p[oh], a3 = p[oh + ol];
+        if (phmask & 1u) a0 = cmulc<A>(c0, a0);
+        if (phmask & 2u) a1 = cmulc<A>(c1, a1);
+        if (phmask & 4u) a2 = cmulc<A>(c2, a2);
+        if (phmask & 8u) a3 = cmulc<A>(c3, a3);
+        p[dst[0]] = a0;
+        p[dst[1]] = a1;
+        p[dst[2]] = a2;
+        p[dst[3]] = a3;
     }
 }
 
@@ -234,7 +313,7 @@ template <typename A> __device__ __forceinline__ void cswap(const bool c, A &u, 
     u = t;
 }
 
-template <typename A, bool UNI, int NT, typename EX>
+template <typename A, bool UNI, int NT, int MK, typename EX>
 __device__ __forceinline__ void sweep_dense2_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     constexpr int LOWB = LowBits<A>::value;
     const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
@@ -243,9 +322,7 @@ __device__ __forceinline__ void sweep_dense2_low(A *tile, const DevGate &g, cons
     const u32 rb = ((u32)tid >> (LOWB - c)) & ((1u << c) - 1u);
     const u32 R = c == 2 ? rb : (rb ? B : 0u);
     const bool R0 = (R & 1u) != 0u, R1 = (R & 2u) != 0u;
-    Cf<A> m[16];                       // uniform: the 16 coefficients would not fit per lane (64 registers)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = coef<A>(g, i);
+    const Block2<A, MK> blk(g);       // uniform: the 16 coefficients would not fit per lane (64 registers)
     u32 off[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) off[k] = (((k ^ R) & 2u) ? oh : 0u) + (((k ^ R) & 1u) ? ol : 0u);
@@ -263,7 +340,7 @@ __device__ __forceinline__ void sweep_dense2_low(A *tile, const DevGate &g, cons
             cswap<A>(R1, x[0], x[2]);
             cswap<A>(R1, x[1], x[3]);
         }
-        dense2_group<A>(m, x[0], x[1], x[2], x[3], r);
+        blk.apply(x[0], x[1], x[2], x[3], r);
         if (B & 1u) {
             cswap<A>(R0, r[0], r[1]);
             cswap<A>(R0, r[2], r[3]);
@@ -486,15 +563,24 @@ __device__ __forceinline__ void run_op(A *tile, const DevGate &g, const DevGate 
         default: sweep_diag<A, false, NT>(tile, g, ExpandAny(g), ngroups, base, tid); break;
         }
     } else if (g.k == 2) {
-        if (nins == 2 && (g.tl[0] < LowBits<A>::value || g.tl[1] < LowBits<A>::value)) {
-            sweep_dense2_low<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid);
+        if (nins == 2) {                                        // no in-tile controls: the structured forms
+            if (g.mk == MK_MONOMIAL) {
+                sweep_mono2<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid);
+            } else if (g.tl[0] < LowBits<A>::value || g.tl[1] < LowBits<A>::value) {
+                if (g.mk == MK_REAL) sweep_dense2_low<A, UNI, NT, MK_REAL>(tile, g, Expand<2>(g), ngroups, tid);
+                else if (g.mk == MK_REALPHASE) sweep_dense2_low<A, UNI, NT, MK_REALPHASE>(tile, g, Expand<2>(g), ngroups, tid);
+                else sweep_dense2_low<A, UNI, NT, MK_GENERAL>(tile, g, Expand<2>(g), ngroups, tid);
+            } else {
+                if (g.mk == MK_REAL) sweep_dense2<A, UNI, NT, MK_REAL>(tile, g, Expand<2>(g), ngroups, tid);
+                else if (g.mk == MK_REALPHASE) sweep_dense2<A, UNI, NT, MK_REALPHASE>(tile, g, Expand<2>(g), ngroups, tid);
+                else sweep_dense2<A, UNI, NT, MK_GENERAL>(tile, g, Expand<2>(g), ngroups, tid);
+            }
             return;
         }
-        switch (nins) {
-        case 2: sweep_dense2<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid); break;
-        case 3: sweep_dense2<A, UNI, NT>(tile, g, Expand<3>(g), ngroups, tid); break;
-        case 4: sweep_dense2<A, UNI, NT>(tile, g, Expand<4>(g), ngroups, tid); break;
-        default: sweep_dense2<A, false, NT>(tile, g, ExpandAny(g), ngroups, tid); break;
+        switch (nins) {                                         // the host keeps MK_GENERAL for these
+        case 3: sweep_dense2<A, UNI, NT, MK_GENERAL>(tile, g, Expand<3>(g), ngroups, tid); break;
+        case 4: sweep_dense2<A, UNI, NT, MK_GENERAL>(tile, g, Expand<4>(g), ngroups, tid); break;
+        default: sweep_dense2<A, false, NT, MK_GENERAL>(tile, g, ExpandAny(g), ngroups, tid); break;
         }
     } else {
         if (g.post != 0 && (base & next.out_ctrl) == next.out_ctrl) {     // host guarantees nins == 1, no controls
@@ -727,10 +813,78 @@ static bool ring_enabled() {
 
 static inline u32 tsize_runs(const FusedArgs &f) { return 1u << (f.tb - f.lowrun); }
 
+// BULK: TMA staging (runs of >= 512 bytes, more than one tile).  UNI: the specialised sweeps (tile of 2^12, or
+// 2^11 with 128-thread CTAs).  Also decides whether descriptors may carry the structured matrix forms.
+static inline bool launch_is_bulk(const FusedArgs &f, size_t amp_bytes) { return (amp_bytes << f.lowrun) >= 512 && f.ntiles >= 2; }
+static inline bool launch_is_uni(const FusedArgs &f, size_t amp_bytes) { return launch_is_bulk(f, amp_bytes) && f.tb >= 11; }
+
+// Exact structure of a dense 4x4 block (see Block2): fills the descriptor's coefficient area in the layout of
+// the chosen form.  `put_c(slot, re, im)` / `put_r(slot, v)` write in the amplitude's precision.
+template <typename PutC, typename PutR>
+static void classify_block(const double *mat, DevGate &d, PutC put_c, PutR put_r) {
+    cplx M[4][4];
+    double big = 0.0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            M[i][j] = cplx(mat[2 * (4 * i + j)], mat[2 * (4 * i + j) + 1]);
+            big = std::max(big, std::abs(M[i][j]));
+        }
+    // monomial: exactly one non-zero per row and per column
+    int row_of[4], rows_hit = 0;
+    bool mono = true;
+    for (int j = 0; j < 4 && mono; ++j) {
+        int cnt = 0;
+        for (int i = 0; i < 4; ++i)
+            if (M[i][j] != cplx(0.0, 0.0)) { row_of[j] = i; ++cnt; }
+        mono = cnt == 1;
+        if (mono) rows_hit |= 1 << row_of[j];
+    }
+    if (mono && rows_hit == 15) {
+        d.mk = MK_MONOMIAL;
+        d.perm = d.phmask = 0;
+        for (int j = 0; j < 4; ++j) {
+            d.perm |= (unsigned char)(row_of[j] << (2 * j));
+            const cplx c = M[row_of[j]][j];
+            if (c != cplx(1.0, 0.0)) d.phmask |= (unsigned char)(1 << j);
+            put_c(j, c.real(), c.imag());
+        }
+        return;
+    }
+    // real matrix times column phases: M[:, j] = ph_j * (real column); imaginary residue at rounding level only
+    const double eps = 4e-16 * big;
+    cplx ph[4];
+    double R[4][4];
+    bool rc = true;
+    for (int j = 0; j < 4 && rc; ++j) {
+        int k = 0;
+        for (int i = 1; i < 4; ++i)
+            if (std::abs(M[i][j]) > std::abs(M[k][j])) k = i;
+        const double a = std::abs(M[k][j]);
+        ph[j] = a > 0.0 ? M[k][j] / a : cplx(1.0, 0.0);
+        if (ph[j].imag() == 0.0) ph[j] = cplx(1.0, 0.0);       // a real column keeps its signs in R
+        for (int i = 0; i < 4; ++i) {
+            const cplx z = M[i][j] * std::conj(ph[j]);
+            if (std::fabs(z.imag()) > eps) { rc = false; break; }
+            R[i][j] = z.real();
+        }
+    }
+    if (rc) {
+        d.phmask = 0;
+        for (int j = 0; j < 4; ++j)
+            if (ph[j] != cplx(1.0, 0.0)) d.phmask |= (unsigned char)(1 << j);
+        d.mk = d.phmask ? MK_REALPHASE : MK_REAL;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) put_r(4 * i + j, R[i][j]);
+        for (int j = 0; j < 4; ++j) put_c(8 + j, ph[j].real(), ph[j].imag());
+        return;
+    }
+    d.mk = MK_GENERAL;
+}
+
 template <typename A>
 static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
     const size_t smem = sizeof(A) << f.tb;
-    const bool bulk = (sizeof(A) << f.lowrun) >= 512 && f.ntiles >= 2;
+    const bool bulk = launch_is_bulk(f, sizeof(A));
     int per_sm = (int)((224u * 1024u) / (smem + 3072));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
@@ -738,7 +892,7 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
     if (grid > f.ntiles) grid = f.ntiles;
     // UNI: all specialised sweeps (<= 4 fixed positions) have a multiple of the CTA size as item count
     const bool half = bulk && f.tb == 11;                      // 2^11 tiles: 128-thread CTAs
-    const bool uni = bulk && (f.tb >= 12 || half);
+    const bool uni = launch_is_uni(f, sizeof(A));
 #define QIPB_LAUNCH_FUSED(B, U, T)                                                                                          \
     do {                                                                                                                    \
         QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
@@ -996,6 +1150,10 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
     }
 
     // ---- pass 2: device descriptors, FUSED_MAX_OPS per launch ----
+    static const bool structured = []() {
+        const char *e = getenv("QIPB_FUSED_STRUCTURED");      // tuning knob for profiling runs
+        return e ? atoi(e) != 0 : true;
+    }();
     for (size_t first = 0; first < ops.size(); first += FUSED_MAX_OPS) {
         const size_t cnt = ops.size() - first < FUSED_MAX_OPS ? ops.size() - first : FUSED_MAX_OPS;
         f.ngates = (int)cnt;
@@ -1050,6 +1208,26 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
             d.nins = 0;
             for (int j = 0; j < ntile_bits; ++j)
                 if ((fixed_local >> j) & 1ull) d.nmask[d.nins++] = ~((1u << j) - 1u);
+            // structured forms of a dense 2-qubit block (only the specialised sweeps without in-tile controls read them)
+            if (!o.stage && !d.diag && d.k == 2 && d.nins == 2 && structured && launch_is_uni(f, dtype == QIPB_C128 ? 16 : 8)) {
+                const double *mat = gates[o.gate].mat;
+                if (dtype == QIPB_C64) {
+                    float2 *mc = reinterpret_cast<float2 *>(d.m);
+                    float *mr = reinterpret_cast<float *>(d.m);
+                    float2 keep[16];
+                    memcpy(keep, mc, sizeof(keep));
+                    classify_block(mat, d, [&](int slot, double re, double im) { mc[slot] = make_float2((float)re, (float)im); },
+                                   [&](int slot, double v) { mr[slot] = (float)v; });
+                    if (d.mk == MK_GENERAL) memcpy(mc, keep, sizeof(keep));
+                } else {
+                    double2 keep[16];
+                    memcpy(keep, d.m, sizeof(keep));
+                    double *mr = reinterpret_cast<double *>(d.m);
+                    classify_block(mat, d, [&](int slot, double re, double im) { d.m[slot] = make_double2(re, im); },
+                                   [&](int slot, double v) { mr[slot] = v; });
+                    if (d.mk == MK_GENERAL) memcpy(d.m, keep, sizeof(keep));
+                }
+            }
         }
         if (post_enabled())
             for (size_t oi = 0; oi + 1 < cnt; ++oi) {

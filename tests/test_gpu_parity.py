@@ -227,6 +227,29 @@ def test_ring_kernel_layered_and_controls_match_unfused(statetype, tol, monkeypa
     assert abs(float(np.vdot(a.astype(np.complex128), a.astype(np.complex128)).real) - 1.0) <= (1e-12 if statetype == np.complex128 else 1e-4)
 
 
+@pytest.mark.parametrize("statetype,tol", [(np.complex128, TOL128), (np.complex64, TOL64)])
+def test_structured_dense_blocks_match_oracle(statetype, tol):
+    # merged 2-qubit blocks in each exact form the fused kernel specialises on (fused.cu, Block2 / classify_block):
+    # real (H (x) H . CX), real x column phases (Rm folded in), monomial (Swap / CX with phases), general (Haar);
+    # on high tile bits and on the lowest bits (bank-conflict-free variant); 16 tiles, checked against the oracle
+    n = 16
+    rng = np.random.default_rng(31)
+    psi = _rand_state(rng, n)
+    g, c = _pair(n, psi, statetype=statetype, strategy="tile")
+    ops_ = []
+    for (a, b) in ((0, 3), (14, 15), (2, 15), (13, 1), (12, 14)):
+        ops_ += [{a: H2}, {b: H2}, {(a, b): CMat(X2)}]                                   # real
+        ops_ += [{a: H2}, {b: rm_mat(3)}, {(b, a): SwapMat(1)}, {a: rm_mat(5)}, {b: H2}]   # real x column phases
+        ops_ += [{a: rm_mat(2)}, {b: rm_mat(7)}, {(a, b): CMat(X2)}]                     # monomial with phases
+        ops_ += [{(a, b): SwapMat(1)}, {(b, a): haar_unitary(rng, 4)}]                   # permutation, general
+        ops_ += [{(a, b): np.kron(H2, np.array([[0, 1], [1, 0]]))}, {a: rm_mat(4)}]
+    for mats in ops_:
+        g.kronselect_dot(mats)
+        c.kronselect_dot(mats)
+    _agree(g, c, tol)
+    assert g.stats["fused_passes"] >= 1
+
+
 @pytest.mark.parametrize("ring", [0, 1])
 def test_qfft_24_closed_form_both_fused_kernels(ring, monkeypatch):
     # BASELINE configs[1]: QFFT on 24 qubits complex128; closed form sqrt(N) * ifft.
