@@ -158,6 +158,40 @@ def choose_initial_layout(gates: Sequence[Gate], lay: Layout) -> None:
             lay.swap_qubits(q, victim)
 
 
+def defer_global(gates: Sequence[Gate], lay: Layout) -> List[Gate]:
+    """Order-preserving reorder that postpones everything which needs a qubit sitting on a rank bit.
+
+    Gates on disjoint qubits commute, so a gate with a non-diagonal target on a rank bit -- and every later
+    gate that shares a qubit with a postponed one -- can move behind all the gates that are purely local.
+    A layer that touches every qubit (the layered benchmark: 1-qubit gates on all n qubits, then a perfect
+    matching of 2-qubit gates) then needs ONE multi-bit exchange instead of one per first use: all local
+    work first, one remap that brings every rank-bit qubit in (the victims are finished for this flush),
+    then the postponed tail.  Relabelling swaps are tracked on a copy of the layout; `lay` is not changed."""
+    if lay.G == 0 or len(gates) < 2:
+        return list(gates)
+    sim = lay.copy()
+    now: List[Gate] = []
+    later: List[Gate] = []
+    held = set()                                 # qubits touched by a postponed gate
+    for g in gates:
+        qs = set(g.targets) | set(g.controls)
+        relabel = g.kind == "swap" and not g.controls
+        if relabel:
+            nondiag = []
+        elif g.kind == "swap":
+            nondiag = list(g.targets)
+        else:
+            nondiag = [] if (g.diagonal or g.k == 0) else list(g.targets)
+        if (qs & held) or any(sim.is_global(q) for q in nondiag):
+            later.append(g)
+            held |= qs
+            continue
+        if relabel:
+            sim.swap_qubits(g.targets[0], g.targets[1])
+        now.append(g)
+    return now + later
+
+
 def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates: bool = False) -> List[object]:
     """Turn logical gates into rank-independent actions; `lay` is updated in place.
     peer_gates: run a dense 1-qubit gate on a rank bit as one fused compute+exchange kernel when its
@@ -165,6 +199,7 @@ def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates
     direction, an Exchange followed by a local gate only half a shard (measured on B200)."""
     nl = lay.nl
     actions: List[object] = []
+    gates = defer_global(gates, lay)
 
     def nondiag_targets(g: Gate):
         if g.kind == "swap":
