@@ -185,3 +185,32 @@ def test_consecutive_exchanges_coalesce_into_one_remap():
     lay = sp.Layout(n, gbits)
     actions = sp.schedule(gates, lay)
     assert any(isinstance(a, sp.MultiExchange) and len(a.pairs) >= 2 for a in actions)
+
+
+@pytest.mark.parametrize("gbits", [1, 2, 3])
+def test_deferred_global_gates_need_one_exchange_per_layer(gbits):
+    # shardplan.defer_global: gates on disjoint qubits commute, so everything that needs a rank-bit qubit moves
+    # behind the local work and a layer that touches every qubit is local work -> ONE remap -> a short tail
+    n = 14
+    lay = sp.Layout(n, gbits)
+    for seed in range(6):
+        gates = logical_gates(layered_stream(n, 1, 40 + seed), n)
+        reordered = sp.defer_global(gates, lay)
+        assert sorted(map(id, reordered)) == sorted(map(id, gates))               # a permutation of the same gates
+        # dependent gates (sharing a qubit) keep their relative order
+        where = {id(g): i for i, g in enumerate(reordered)}
+        for i, a in enumerate(gates):
+            qa = set(a.targets) | set(a.controls)
+            for b in gates[i + 1:]:
+                if qa & (set(b.targets) | set(b.controls)):
+                    assert where[id(a)] < where[id(b)]
+        actions = sp.schedule(gates, lay)                                         # lay carries over: layer after layer
+        moves = [a for a in actions if isinstance(a, (sp.Exchange, sp.MultiExchange, sp.PeerGate1))]
+        assert len(moves) <= 1, (seed, moves)
+    # and the result is still the circuit: virtual shards against the in-order simulator
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=2 ** 9) + 1j * rng.normal(size=2 ** 9)
+    psi /= np.linalg.norm(psi)
+    gates = logical_gates(list(layered_stream(9, 2, 5)) + [{(0, 8): SwapMat(1)}, {0: H2}, {(1, 0): CMat(X2)}, {(8, 0): SwapMat(1)}, {8: H2}], 9)
+    vs, _ = run_sharded(psi, gates, 9, gbits)
+    assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, 9)))) <= 1e-13
