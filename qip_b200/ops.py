@@ -120,10 +120,21 @@ _SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtyp
 def _bit_split(mat, k, j):
     """Blocks of `mat` w.r.t. matrix-index bit for target j (0 = MSB): (M00, M01, M10, M11)."""
     d = 1 << k
-    pos = k - 1 - j
-    idx0 = [i for i in range(d) if not (i >> pos) & 1]
-    idx1 = [i for i in range(d) if (i >> pos) & 1]
-    return (mat[np.ix_(idx0, idx0)], mat[np.ix_(idx0, idx1)], mat[np.ix_(idx1, idx0)], mat[np.ix_(idx1, idx1)])
+    lo = 1 << (k - 1 - j)
+    hi = d // (2 * lo)
+    t = mat.reshape(hi, 2, lo, hi, 2, lo)          # (row hi, row bit, row lo, col hi, col bit, col lo)
+    h = d // 2
+    return (t[:, 0, :, :, 0, :].reshape(h, h), t[:, 0, :, :, 1, :].reshape(h, h),
+            t[:, 1, :, :, 0, :].reshape(h, h), t[:, 1, :, :, 1, :].reshape(h, h))
+
+
+_EYES = {d: np.eye(d) for d in (1, 2, 4, 8, 16)}
+
+
+def _is_identity(m) -> bool:
+    d = m.shape[0]
+    eye = _EYES.get(d)
+    return np.array_equal(m, eye if eye is not None else np.eye(d))
 
 
 def simplify(g: Gate) -> Optional[Gate]:
@@ -137,13 +148,13 @@ def simplify(g: Gate) -> Optional[Gate]:
         k = len(targets)
         for j in range(k):
             m00, m01, m10, m11 = _bit_split(mat, k, j)
-            if not m01.any() and not m10.any() and np.array_equal(m00, np.eye(m00.shape[0])):
+            if not m01.any() and not m10.any() and _is_identity(m00):
                 controls.append(targets.pop(j))
                 mat = np.ascontiguousarray(m11)
                 changed = True
                 break
     d = mat.shape[0]
-    if np.array_equal(mat, np.eye(d)):
+    if _is_identity(mat):
         return None
     if d == 4 and np.array_equal(mat, _SWAP4):
         return Gate("swap", tuple(targets), tuple(controls))
@@ -399,9 +410,10 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
     low = set(range(min(min_low_bits, tb)))
     cur: List[BitGate] = []
     need = set()
+    ncoefs = 0
 
     def flush():
-        nonlocal cur, need
+        nonlocal cur, need, ncoefs
         if not cur:
             return
         solo = sum(gate_bytes(g, nbits, amp_bytes) for g in cur)
@@ -410,7 +422,7 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
             passes.append(Pass(True, cur, choose_tile(need, nbits, tb)))
         else:
             passes.extend(Pass(False, [g]) for g in cur)
-        cur, need = [], set()
+        cur, need, ncoefs = [], set(), 0
 
     for g in gates:
         if not enable or not _fusable(g):
@@ -418,13 +430,14 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
             passes.append(Pass(False, [g]))
             continue
         nn = need | _needs(g)
-        if len(nn | low) > tb or len(cur) >= max_gates or sum(_ncoef(x) for x in cur) + _ncoef(g) > max_coefs:
+        if len(nn | low) > tb or len(cur) >= max_gates or ncoefs + _ncoef(g) > max_coefs:
             flush()
             nn = _needs(g)
             if len(nn | low) > tb:        # cannot happen for k <= 2 and tb >= min_low_bits + 2
                 passes.append(Pass(False, [g]))
                 continue
         cur.append(g)
+        ncoefs += _ncoef(g)
         need = nn
     flush()
     return passes
