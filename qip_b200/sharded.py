@@ -36,6 +36,13 @@ class _RawCuda(object):
                                          "version": 3, "strides": None}
 
 
+# Shard allocations are pooled per process: cudaMalloc of a 128 GiB shard, its IPC export and the P-1 peer
+# mappings cost ~0.3 s per run() at 8 GPUs.  Every rank runs the same program (SPMD), so the pools of all
+# ranks hold the same sizes at the same time and a re-used shard keeps its peer mappings valid.  A request of
+# a different size first releases what is pooled (collectively).
+_SHARD_POOL = {}        # (device index, bytes, world size) -> (ptr, peers)
+
+
 class ShardedB200Backend(object):
     def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
                  peer_gates: bool = False, lazy_layout: bool = True):
@@ -66,20 +73,46 @@ class ShardedB200Backend(object):
         self._pending_init = None       # (groups, feeds): the state is built at the first flush
         self.stats = {"gates": 0, "exchanges": 0, "peer_gates": 0, "nvlink_bytes_out": 0}
         # shard memory comes from cudaMalloc (qipb_dev_alloc) so that its IPC handle maps it exactly
-        ptr = ctypes.c_void_p()
-        _lib.check(self.L.qipb_dev_alloc(self.ctx, (1 << self.nl) * self.amp_bytes, ctypes.byref(ptr)))
         self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.peers = {}
-        self._adopt_shard(ptr)
+        key = self._pool_key()
+        pooled = _SHARD_POOL.pop(key, None)
+        if pooled is not None:
+            self._wrap_shard(pooled[0])
+            self.peers = pooled[1]
+            self._sync_all()
+        else:
+            self._drain_pool()
+            ptr = ctypes.c_void_p()
+            _lib.check(self.L.qipb_dev_alloc(self.ctx, (1 << self.nl) * self.amp_bytes, ctypes.byref(ptr)))
+            self._adopt_shard(ptr)
+
+    def _pool_key(self):
+        return (self.device.index or 0, (1 << self.nl) * self.amp_bytes, self.P)
+
+    def _drain_pool(self):
+        """Release every pooled shard (all ranks call this at the same point of the program)."""
+        torch = _torch()
+        if not _SHARD_POOL:
+            return
+        torch.cuda.synchronize()
+        for key in list(_SHARD_POOL.keys()):
+            ptr, peers = _SHARD_POOL.pop(key)
+            for pp in peers.values():
+                self.L.qipb_ipc_close(self.ctx, pp)
+            self.dist.barrier()
+            self.L.qipb_dev_free(self.ctx, ptr)
+
+    def _wrap_shard(self, ptr):
+        torch = _torch()
+        self.ptr = ptr
+        self.eng.state = torch.as_tensor(_RawCuda(ptr.value, 1 << self.nl, "<c16" if self.amp_bytes == 16 else "<c8"),
+                                         device=self.device)
+        assert self.eng.state.data_ptr() == ptr.value
 
     def _adopt_shard(self, ptr):
         """Wrap a cudaMalloc'ed shard for torch, export its IPC handle and map every peer's shard."""
-        torch = _torch()
-        count = 1 << self.nl
-        self.ptr = ptr
-        self.eng.state = torch.as_tensor(_RawCuda(ptr.value, count, "<c16" if self.amp_bytes == 16 else "<c8"),
-                                         device=self.device)
-        assert self.eng.state.data_ptr() == ptr.value
+        self._wrap_shard(ptr)
         handle = ctypes.create_string_buffer(64)
         _lib.check(self.L.qipb_ipc_export(self.ctx, ptr, handle))
         handles = [None] * self.P
@@ -574,7 +607,19 @@ class ShardedB200Backend(object):
         _torch().cuda.current_stream(self.device).synchronize()
 
     def close(self):
+        """Return the shard (with its peer mappings) to the pool; nothing may touch it afterwards."""
         if getattr(self, "ptr", None) is None:
             return
-        self._release_shard()
+        torch = _torch()
+        torch.cuda.synchronize()
+        self._sync_all()                        # no peer kernel is still reading or writing this shard
+        torch.cuda.synchronize()
+        key = self._pool_key()
+        if key in _SHARD_POOL:                  # two live states of one size: keep one pooled, free the other
+            self._release_shard()
+        else:
+            _SHARD_POOL[key] = (self.ptr, self.peers)
+            self.peers = {}
+            self.eng.state = None
+            self.ptr = None
         self.eng.close()
