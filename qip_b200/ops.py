@@ -311,6 +311,51 @@ def _absorb(block, qs, u):
     block[1] = _apply_to_block(bm, new_q, u, qs)
 
 
+def sink_lone_diagonals(gates: Sequence[Gate], min_run: int = 3) -> List[Gate]:
+    """Cluster isolated diagonal gates.  The fused kernel folds a run of >= 3 consecutive diagonal gates
+    into ONE table sweep (fused.cu, "stage"), but a lone diagonal gate costs a sweep of its own.  A diagonal
+    gate commutes with every other diagonal gate and with any gate whose non-diagonal targets avoid its qubits
+    (controls are diagonal too), so diagonal gates that sit in runs shorter than `min_run` are moved as late
+    as commutation allows; they meet at the end of the segment (or in front of the first gate that really
+    needs one of their qubits) and fold there.  Runs that already fold -- the controlled phases behind each H of a
+    QFT, which ride on that H's sweep -- stay where they are.  Exact: only the order of commuting gates changes."""
+    n = len(gates)
+    is_diag = [g.kind == "matrix" and (g.diagonal or g.k == 0) for g in gates]
+    floater = [False] * n
+    i = 0
+    while i < n:
+        if not is_diag[i]:
+            i += 1
+            continue
+        j = i
+        while j < n and is_diag[j]:
+            j += 1
+        if j - i < min_run:
+            for t in range(i, j):
+                floater[t] = True
+        i = j
+    if not any(floater):
+        return list(gates)
+    out: List[Gate] = []
+    pending: List[Gate] = []
+    for idx, g in enumerate(gates):
+        if floater[idx]:
+            pending.append(g)
+            continue
+        if not is_diag[idx] and pending:
+            hit = set(g.targets)                     # a swap's targets are non-diagonal as well
+            stay = []
+            for d in pending:
+                if hit & (set(d.targets) | set(d.controls)):
+                    out.append(d)
+                else:
+                    stay.append(d)
+            pending = stay
+        out.append(g)
+    out.extend(pending)
+    return out
+
+
 # --------------------------------------------------------------------------------- bit-level form
 @dataclass
 class BitGate:
@@ -484,7 +529,10 @@ def plan(gates: Sequence[Gate], n: int, amp_bytes: int = 16, fuse: bool = True, 
     if strategy in ("auto", "tile"):
         import os
         ca = os.environ.get("QIPB_COST_AWARE", "1") != "0"         # tuning knob for profiling runs
-        a = plan_passes([lower(g, n) for g in merge_blocks(gates, 2, cost_aware=ca)], n, amp_bytes,
+        merged = merge_blocks(gates, 2, cost_aware=ca)
+        if os.environ.get("QIPB_SINK_DIAGONALS", "1") != "0":      # tuning knob for profiling runs
+            merged = sink_lone_diagonals(merged)
+        a = plan_passes([lower(g, n) for g in merged], n, amp_bytes,
                         tile_bits=tile_bits, min_low_bits=min_low_bits)
         out["tile"] = (sum(pass_cost(p, n, amp_bytes) for p in a), a)
     if strategy in ("auto", "dense4"):

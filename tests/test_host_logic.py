@@ -263,3 +263,31 @@ def test_layered_generator_equals_reference_front_end_stream():
     mine = list(layered_stream(8, 4, 33))
     assert len(ref_ops) == len(mine)
     assert all(_same_mats(a, b) for a, b in zip(mine, ref_ops))
+
+
+def test_sink_lone_diagonals_only_reorders_commuting_gates():
+    # isolated diagonal gates move behind the gates they commute with and meet in one run (one table sweep in
+    # the fused kernel); runs that already fold (QFT) stay put; the circuit is unchanged
+    n = 7
+    rng = np.random.default_rng(12)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    from qip_b200.circuits import haar_unitary
+    mats_list = [{0: rm_mat(3)}, {(1, 2): haar_unitary(rng, 4)}, {3: rm_mat(2)}, {(0, 4): CMat(X2)}, {5: rm_mat(4)},
+                 {(3, 6): haar_unitary(rng, 4)}, {(2, 5): CMat(rm_mat(3))}, {5: H2}, {1: rm_mat(6)}, {(6, 1): CMat(X2)}]
+    gates = [s for mats in mats_list for s in (ops.simplify(g) for g in ops.decode_mats(mats, n)) if s is not None]
+    moved = ops.sink_lone_diagonals(gates)
+    assert sorted(map(id, moved)) == sorted(map(id, gates)) and [id(g) for g in moved] != [id(g) for g in gates]
+    a, b = psi.copy(), psi.copy()
+    for g in gates:
+        a = bitsim.apply_bitgate(a, ops.lower(g, n), n)
+    for g in moved:
+        b = bitsim.apply_bitgate(b, ops.lower(g, n), n)
+    assert float(np.max(np.abs(a - b))) <= 1e-13
+    # the phases on qubits 0 and 3 cannot pass the gates that target those qubits; the other lone phases (qubits 5: no,
+    # H(5) targets it; qubit 1: CX targets it) are emitted right in front of their blockers -- at least two end up adjacent
+    diag = [g.kind == "matrix" and (g.diagonal or g.k == 0) for g in moved]
+    assert any(diag[i] and diag[i + 1] for i in range(len(diag) - 1))
+    # a QFT keeps its structure: every H whose controlled phases fold into a stage (runs of >= 3) is still
+    # directly followed by them (H0 + 5, H1 + 4, H2 + 3 phases = the first 15 gates of a 6-qubit QFFT)
+    q = [s for mats in qfft_stream(6, rev=False) for s in (ops.simplify(g) for g in ops.decode_mats(mats, 6)) if s is not None]
+    assert [id(g) for g in ops.sink_lone_diagonals(q)[:15]] == [id(g) for g in q[:15]]
