@@ -389,7 +389,11 @@ def merge_bitgates(gates: Sequence["BitGate"], max_k: int = 2) -> List["BitGate"
         ctrl = tuple(b for b in range(64) if (g.ctrl_mask >> b) & 1)
         logical.append(Gate(g.kind, tuple(g.bits), ctrl, g.mat, g.diagonal))
     out = []
-    for g in merge_blocks(logical, max_k, cost_aware=True):
+    merged = merge_blocks(logical, max_k, cost_aware=True)
+    import os
+    if os.environ.get("QIPB_SINK_DIAGONALS", "1") != "0":
+        merged = sink_lone_diagonals(merged)
+    for g in merged:
         cm = 0
         for b in g.controls:
             cm |= 1 << b
