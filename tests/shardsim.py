@@ -86,5 +86,40 @@ class VirtualShards(object):
                 for r in range(self.P):
                     self.shards[r] = apply_local(self.shards[r], r, a, nl)
 
+    def run_planned(self, actions, tile_bits=5, min_low_bits=2):
+        """Like run(), but rank-local gates go through the product's rank-local pipeline exactly as
+        ShardedB200Backend._execute/_run_local does it: batches between exchanges are merged
+        (ops.merge_bitgates, incl. the clustering of lone diagonal gates), planned into passes
+        (ops.plan_passes) and executed pass by pass."""
+        from qip_b200.ops import merge_bitgates, plan_passes
+        nl = self.nl
+        batch = []
+
+        def flush():
+            if not batch:
+                return
+            for r in range(self.P):
+                local = []
+                for a in batch:
+                    if isinstance(a, sp.Apply):
+                        bg = sp.lower_for_rank(a.gate, nl, r)
+                        if bg is not None:
+                            local.append(bg)
+                    else:
+                        local.append(BitGate("swap", (a.a, a.b)))
+                if local:
+                    passes = plan_passes(merge_bitgates(local, 2), nl, 16, tile_bits=min(tile_bits, nl),
+                                         min_low_bits=min(min_low_bits, nl))
+                    self.shards[r] = bitsim.run_passes(self.shards[r], passes, nl)
+            batch.clear()
+
+        for a in actions:
+            if isinstance(a, (sp.Apply, sp.LocalSwap)):
+                batch.append(a)
+            else:
+                flush()
+                self.run([a])
+        flush()
+
     def gather(self):
         return np.concatenate(self.shards)

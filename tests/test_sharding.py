@@ -214,3 +214,29 @@ def test_deferred_global_gates_need_one_exchange_per_layer(gbits):
     gates = logical_gates(list(layered_stream(9, 2, 5)) + [{(0, 8): SwapMat(1)}, {0: H2}, {(1, 0): CMat(X2)}, {(8, 0): SwapMat(1)}, {8: H2}], 9)
     vs, _ = run_sharded(psi, gates, 9, gbits)
     assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, 9)))) <= 1e-13
+
+
+@pytest.mark.parametrize("gbits", [1, 2, 3])
+@pytest.mark.parametrize("kind", ["layered", "qft", "mixed"])
+def test_rank_local_merge_and_plan_on_virtual_shards(gbits, kind):
+    # the rank-local pipeline of ShardedB200Backend._run_local (merge_bitgates with lone-diagonal clustering ->
+    # plan_passes -> fused / stand-alone passes), executed per virtual shard by the numpy pass executor
+    n = 10
+    rng = np.random.default_rng(17 + gbits)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    if kind == "layered":
+        stream = list(layered_stream(n, 3, 21))
+    elif kind == "qft":
+        stream = list(qfft_stream(n))
+    else:
+        stream = [{0: rm_mat(3)}, {(1, 2): haar_unitary(rng, 4)}, {3: rm_mat(2)}, {(0, 4): CMat(X2)}, {9: rm_mat(4)},
+                  {(3, 6): haar_unitary(rng, 4)}, {(2, 5): CMat(rm_mat(3))}, {5: H2}, {1: rm_mat(6)}, {(6, 1): CMat(X2)},
+                  {0: H2}, {(9, 0): SwapMat(1)}, {(0, 7): haar_unitary(rng, 4)}, {8: rm_mat(2)}, {7: rm_mat(5)}]
+    gates = logical_gates(stream, n)
+    lay = sp.Layout(n, gbits)
+    vs = shardsim.VirtualShards(_permuted(psi, lay), gbits)
+    vs.run_planned(sp.schedule(gates, lay))
+    vs.run_planned(sp.canonicalise(lay))
+    assert lay.canonical()
+    assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-12
