@@ -67,6 +67,7 @@ class ShardedB200Backend(object):
         self.code, self.amp_bytes, self.np_dtype = self.eng.code, self.eng.amp_bytes, self.eng.np_dtype
         self.layout = sp.Layout(self.n, self.G)
         self.queue: List[Gate] = []
+        self._seg_cache, self._seg_keys = None, []      # compiled-circuit segments queued since the last flush
         self.fuse = fuse
         self.peer_gates = peer_gates
         self.lazy_layout = lazy_layout
@@ -212,10 +213,16 @@ class ShardedB200Backend(object):
 
     # ------------------------------------------------------------------ gates
     def apply_gates(self, gates, cache=None, key=None) -> None:
-        """Pre-decoded gates of a compiled circuit (qip_b200.graph); scheduling is redone per run because
-        the exchange plan depends on the whole queue."""
+        """Pre-decoded gates of a compiled circuit (qip_b200.graph).  The exchange plan depends on the whole
+        queue, so segments are only queued here; with `cache`/`key` the flush that runs them remembers its
+        rank-local program under (keys of all its segments, layout before) and a replay skips scheduling."""
         self.queue.extend(gates)
         self.stats["gates"] += len(gates)
+        if cache is not None and self._seg_keys is not None:
+            self._seg_cache = cache
+            self._seg_keys.append(key)
+        else:
+            self._seg_keys = None                  # mixed with un-keyed gates: this flush is not cacheable
 
     def kronselect_dot(self, mats, input_offset: int = 0, output_offset: int = 0) -> None:
         if input_offset != 0 or output_offset != 0:
@@ -225,15 +232,17 @@ class ShardedB200Backend(object):
             if s is not None:
                 self.queue.append(s)
                 self.stats["gates"] += 1
+                self._seg_keys = None              # un-keyed gates in the queue: the next flush is not cacheable
 
-    def _run_local(self, batch: List[BitGate]):
-        if not batch:
-            return
-        torch = _torch()
+    def _plan_local(self, batch: List[BitGate]):
+        """Rank-local: every rank merges and plans its own resolved gate list."""
         if self.fuse:
-            batch = merge_bitgates(batch, 2)       # rank-local: every rank merges its own resolved list
-        passes = plan_passes(batch, self.nl, self.amp_bytes, tile_bits=self.eng.tile_bits,
-                             min_low_bits=self.eng.min_low_bits, enable=self.fuse)
+            batch = merge_bitgates(batch, 2)
+        return plan_passes(batch, self.nl, self.amp_bytes, tile_bits=self.eng.tile_bits,
+                           min_low_bits=self.eng.min_low_bits, enable=self.fuse)
+
+    def _run_passes(self, passes):
+        torch = _torch()
         for p in passes:
             if self.eng.profile is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -315,36 +324,49 @@ class ShardedB200Backend(object):
         self.stats["peer_gates"] += 1
         self.stats["nvlink_bytes_out"] += self.amp_bytes * half
 
-    def _execute(self, actions):
+    def _run_program(self, program):
         torch = _torch()
-        batch: List[BitGate] = []
         with torch.cuda.device(self.device):
             self._stream()
-            for a in actions:
-                if isinstance(a, sp.Apply):
-                    bg = sp.lower_for_rank(a.gate, self.nl, self.rank)
-                    if bg is not None:
-                        batch.append(bg)
-                elif isinstance(a, sp.LocalSwap):
-                    batch.append(BitGate("swap", (a.a, a.b)))
+            for a in program:
+                if isinstance(a, tuple):
+                    self._run_passes(a[1])
+                elif isinstance(a, sp.Exchange):
+                    self._exchange(a)
+                elif isinstance(a, sp.MultiExchange):
+                    self._multi_exchange(a)
                 else:
-                    self._run_local(batch)
-                    batch = []
-                    if isinstance(a, sp.Exchange):
-                        self._exchange(a)
-                    elif isinstance(a, sp.MultiExchange):
-                        self._multi_exchange(a)
-                    else:
-                        self._peer_gate(a)
-            self._run_local(batch)
+                    self._peer_gate(a)
+
+    def _execute(self, actions):
+        self._run_program(sp.compile_program(actions, self.nl, self.rank, self._plan_local))
 
     def flush(self) -> None:
         self._materialise()
+        cache, keys = self._seg_cache, self._seg_keys
+        self._seg_cache, self._seg_keys = None, []
         if not self.queue:
             return
         gates = list(self.queue)
         self.queue = []
-        self._execute(sp.schedule(gates, self.layout, peer_gates=self.peer_gates))
+        ckey = None
+        if cache is not None and keys:
+            # what the schedule depends on: the gates (named by their segment keys), the layout they start
+            # from, and the knobs of the rank-local planner; the program itself is per rank
+            ckey = ("sharded-flush", tuple(keys), tuple(self.layout.pos), self.rank, self.P, self.fuse,
+                    self.peer_gates, self.eng.tile_bits, self.eng.min_low_bits, self.amp_bytes)
+            hit = cache.get(ckey)
+            if hit is not None:
+                program, pos_after = hit
+                self.layout.pos = list(pos_after)
+                self.stats["cached_flushes"] = self.stats.get("cached_flushes", 0) + 1
+                self._run_program(program)
+                return
+        program = sp.compile_program(sp.schedule(gates, self.layout, peer_gates=self.peer_gates),
+                                     self.nl, self.rank, self._plan_local)
+        if ckey is not None:
+            cache[ckey] = (program, tuple(self.layout.pos))
+        self._run_program(program)
 
     def func_apply(self, reg1_indices, reg2_indices, func, input_offset: int = 0, output_offset: int = 0) -> None:
         torch = _torch()

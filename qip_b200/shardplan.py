@@ -276,6 +276,37 @@ def coalesce_exchanges(actions: List[object], max_pairs: int = 3) -> List[object
     return out
 
 
+def compile_program(actions: Sequence[object], nl: int, rank: int, plan_local) -> List[object]:
+    """The rank-local program of a schedule: every maximal run of Apply / LocalSwap actions is resolved
+    for `rank` (lower_for_rank) and handed to `plan_local(list[BitGate]) -> list[ops.Pass]`; the result is
+    kept as ("local", passes).  Exchanges and peer gates stay as they are.  The program depends only on
+    (actions, rank), so a compiled circuit caches it per flush (ShardedB200Backend.flush) and a replay
+    skips scheduling, merging and planning.  Pure host logic: tests/shardsim.py runs the same programs
+    on virtual shards."""
+    program: List[object] = []
+    batch: List[BitGate] = []
+
+    def flush():
+        if batch:
+            passes = plan_local(list(batch))
+            if passes:
+                program.append(("local", passes))
+            batch.clear()
+
+    for a in actions:
+        if isinstance(a, Apply):
+            bg = lower_for_rank(a.gate, nl, rank)
+            if bg is not None:
+                batch.append(bg)
+        elif isinstance(a, LocalSwap):
+            batch.append(BitGate("swap", (a.a, a.b)))
+        else:
+            flush()
+            program.append(a)
+    flush()
+    return program
+
+
 def canonicalise(lay: Layout) -> List[object]:
     """Actions that bring the layout back to qubit q at bit n-1-q (needed before the state is
     read out in index order).  Rank-bit <-> rank-bit swaps go through a local position."""

@@ -88,38 +88,40 @@ class VirtualShards(object):
 
     def run_planned(self, actions, tile_bits=5, min_low_bits=2):
         """Like run(), but rank-local gates go through the product's rank-local pipeline exactly as
-        ShardedB200Backend._execute/_run_local does it: batches between exchanges are merged
-        (ops.merge_bitgates, incl. the clustering of lone diagonal gates), planned into passes
-        (ops.plan_passes) and executed pass by pass."""
+        ShardedB200Backend._execute does it: shardplan.compile_program resolves the batches between
+        exchanges per rank, merges them (ops.merge_bitgates, incl. the clustering of lone diagonal gates)
+        and plans them into passes (ops.plan_passes); the programs are then executed in lockstep."""
         from qip_b200.ops import merge_bitgates, plan_passes
         nl = self.nl
-        batch = []
 
-        def flush():
-            if not batch:
-                return
+        def plan_local(batch):
+            return plan_passes(merge_bitgates(batch, 2), nl, 16, tile_bits=min(tile_bits, nl),
+                               min_low_bits=min(min_low_bits, nl))
+
+        self.run_programs([sp.compile_program(actions, nl, r, plan_local) for r in range(self.P)])
+
+    def run_programs(self, programs):
+        """Execute one rank-local program per virtual shard (what ShardedB200Backend._run_program does on
+        each GPU).  Every program holds the same sequence of moves (exchanges / peer gates are
+        rank-independent); ("local", passes) steps in between may be missing on ranks with nothing to do."""
+        nl = self.nl
+        cursors = [0] * self.P
+        while True:
             for r in range(self.P):
-                local = []
-                for a in batch:
-                    if isinstance(a, sp.Apply):
-                        bg = sp.lower_for_rank(a.gate, nl, r)
-                        if bg is not None:
-                            local.append(bg)
-                    else:
-                        local.append(BitGate("swap", (a.a, a.b)))
-                if local:
-                    passes = plan_passes(merge_bitgates(local, 2), nl, 16, tile_bits=min(tile_bits, nl),
-                                         min_low_bits=min(min_low_bits, nl))
-                    self.shards[r] = bitsim.run_passes(self.shards[r], passes, nl)
-            batch.clear()
-
-        for a in actions:
-            if isinstance(a, (sp.Apply, sp.LocalSwap)):
-                batch.append(a)
-            else:
-                flush()
-                self.run([a])
-        flush()
+                prog = programs[r]
+                while cursors[r] < len(prog) and isinstance(prog[cursors[r]], tuple):
+                    self.shards[r] = bitsim.run_passes(self.shards[r], prog[cursors[r]][1], nl)
+                    cursors[r] += 1
+            done = [cursors[r] >= len(programs[r]) for r in range(self.P)]
+            if all(done):
+                return
+            assert not any(done), "programs disagree on the number of moves"
+            move = programs[0][cursors[0]]
+            for r in range(self.P):
+                other = programs[r][cursors[r]]
+                assert type(other) is type(move) and vars(other).keys() == vars(move).keys()
+                cursors[r] += 1
+            self.run([move])
 
     def gather(self):
         return np.concatenate(self.shards)

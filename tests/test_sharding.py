@@ -219,7 +219,7 @@ def test_deferred_global_gates_need_one_exchange_per_layer(gbits):
 @pytest.mark.parametrize("gbits", [1, 2, 3])
 @pytest.mark.parametrize("kind", ["layered", "qft", "mixed"])
 def test_rank_local_merge_and_plan_on_virtual_shards(gbits, kind):
-    # the rank-local pipeline of ShardedB200Backend._run_local (merge_bitgates with lone-diagonal clustering ->
+    # the rank-local pipeline of ShardedB200Backend._plan_local (merge_bitgates with lone-diagonal clustering ->
     # plan_passes -> fused / stand-alone passes), executed per virtual shard by the numpy pass executor
     n = 10
     rng = np.random.default_rng(17 + gbits)
@@ -240,3 +240,71 @@ def test_rank_local_merge_and_plan_on_virtual_shards(gbits, kind):
     vs.run_planned(sp.canonicalise(lay))
     assert lay.canonical()
     assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-12
+
+
+def _host_only_backend(n, gbits, rank, tile_bits=5, min_low_bits=2):
+    """A ShardedB200Backend with its device side cut off: the real apply_gates / kronselect_dot / flush
+    run (queueing, schedule, rank-local planning, the compiled-circuit program cache), `_run_program`
+    only records what it would launch."""
+    import types
+    from qip_b200.sharded import ShardedB200Backend
+    b = object.__new__(ShardedB200Backend)
+    b.n, b.G, b.nl, b.rank, b.P = n, gbits, n - gbits, rank, 1 << gbits
+    b.layout = sp.Layout(n, gbits)
+    b.queue, b._seg_cache, b._seg_keys = [], None, []
+    b.fuse, b.peer_gates, b.amp_bytes = True, False, 16
+    b.eng = types.SimpleNamespace(tile_bits=tile_bits, min_low_bits=min_low_bits)
+    b.stats = {"gates": 0}
+    b._pending_init = None
+    b.programs = []
+    b._run_program = b.programs.append
+    return b
+
+
+@pytest.mark.parametrize("gbits", [1, 2])
+def test_sharded_flush_caches_the_rank_local_program_of_compiled_segments(gbits):
+    # qip_b200.graph.CompiledCircuit.run hands every gate segment to apply_gates(gates, cache, key); the flush
+    # that executes them must replay the cached program only for the same segments from the same layout, and
+    # the replayed program must still be the circuit
+    n = 9
+    P = 1 << gbits
+    rng = np.random.default_rng(5)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    seg_a = logical_gates(layered_stream(n, 2, 7), n)
+    seg_b = logical_gates(list(qfft_stream(n)), n)
+    caches = [dict() for _ in range(P)]            # one process (and one CompiledCircuit cache) per rank
+    first_programs = None
+    for replay in range(3):
+        backends = [_host_only_backend(n, gbits, r) for r in range(P)]
+        for r, b in enumerate(backends):
+            b.apply_gates(seg_a, caches[r], ("seg", 0))
+            b.apply_gates(seg_b, caches[r], ("seg", 1))
+            b.flush()                               # both segments in one flush: one schedule, one cache entry
+            b.apply_gates(seg_a, caches[r], ("seg", 0))
+            b.flush()                               # same segment, different starting layout: its own entry
+            assert b.queue == [] and len(b.programs) == 2
+            assert b.stats.get("cached_flushes", 0) == (0 if replay == 0 else 2)
+            assert len(caches[r]) == 2
+        if replay == 0:
+            first_programs = [b.programs for b in backends]
+        else:
+            for b, first in zip(backends, first_programs):
+                assert all(x is y for x, y in zip(b.programs, first))       # replays reuse the planned passes
+        vs = shardsim.VirtualShards(psi, gbits)
+        for step in range(2):
+            vs.run_programs([b.programs[step] for b in backends])
+        lay = backends[0].layout
+        assert all(b.layout.pos == lay.pos for b in backends)
+        vs.run_planned(sp.canonicalise(lay))
+        assert float(np.max(np.abs(vs.gather() - reference_state(psi, seg_a + seg_b + seg_a, n)))) <= 1e-12
+
+    # un-keyed gates in the queue make the flush un-cacheable (and leave the cache alone)
+    b = _host_only_backend(n, gbits, 0)
+    b.apply_gates(seg_a, caches[0], ("seg", 0))
+    b.kronselect_dot({0: H2})
+    b.flush()
+    assert b.stats.get("cached_flushes", 0) == 0 and len(caches[0]) == 2
+    b.apply_gates(seg_a, caches[0], ("seg", 0))    # the next flush is cacheable again
+    b.flush()
+    assert len(caches[0]) == 3
