@@ -324,22 +324,32 @@ class ShardedB200Backend(object):
         self.stats["peer_gates"] += 1
         self.stats["nvlink_bytes_out"] += self.amp_bytes * half
 
+    def _run_step(self, a):
+        if isinstance(a, tuple):
+            self._run_passes(a[1])
+        elif isinstance(a, sp.Exchange):
+            self._exchange(a)
+        elif isinstance(a, sp.MultiExchange):
+            self._multi_exchange(a)
+        else:
+            self._peer_gate(a)
+
     def _run_program(self, program):
         torch = _torch()
         with torch.cuda.device(self.device):
             self._stream()
             for a in program:
-                if isinstance(a, tuple):
-                    self._run_passes(a[1])
-                elif isinstance(a, sp.Exchange):
-                    self._exchange(a)
-                elif isinstance(a, sp.MultiExchange):
-                    self._multi_exchange(a)
-                else:
-                    self._peer_gate(a)
+                self._run_step(a)
+
+    def _compile_and_run(self, actions):
+        """Every step is launched as soon as it is planned (the host plans batch k+1 while batch k runs)."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            self._stream()
+            return sp.compile_program(actions, self.nl, self.rank, self._plan_local, emit=self._run_step)
 
     def _execute(self, actions):
-        self._run_program(sp.compile_program(actions, self.nl, self.rank, self._plan_local))
+        self._compile_and_run(actions)
 
     def flush(self) -> None:
         self._materialise()
@@ -362,11 +372,9 @@ class ShardedB200Backend(object):
                 self.stats["cached_flushes"] = self.stats.get("cached_flushes", 0) + 1
                 self._run_program(program)
                 return
-        program = sp.compile_program(sp.schedule(gates, self.layout, peer_gates=self.peer_gates),
-                                     self.nl, self.rank, self._plan_local)
+        program = self._compile_and_run(sp.schedule(gates, self.layout, peer_gates=self.peer_gates))
         if ckey is not None:
             cache[ckey] = (program, tuple(self.layout.pos))
-        self._run_program(program)
 
     def func_apply(self, reg1_indices, reg2_indices, func, input_offset: int = 0, output_offset: int = 0) -> None:
         torch = _torch()

@@ -276,21 +276,27 @@ def coalesce_exchanges(actions: List[object], max_pairs: int = 3) -> List[object
     return out
 
 
-def compile_program(actions: Sequence[object], nl: int, rank: int, plan_local) -> List[object]:
+def compile_program(actions: Sequence[object], nl: int, rank: int, plan_local, emit=None) -> List[object]:
     """The rank-local program of a schedule: every maximal run of Apply / LocalSwap actions is resolved
     for `rank` (lower_for_rank) and handed to `plan_local(list[BitGate]) -> list[ops.Pass]`; the result is
     kept as ("local", passes).  Exchanges and peer gates stay as they are.  The program depends only on
     (actions, rank), so a compiled circuit caches it per flush (ShardedB200Backend.flush) and a replay
-    skips scheduling, merging and planning.  Pure host logic: tests/shardsim.py runs the same programs
-    on virtual shards."""
+    skips scheduling, merging and planning.  `emit(step)` is called as soon as a step is known, so that the
+    executor launches a batch while the host still plans the next one.  Pure host logic: tests/shardsim.py
+    runs the same programs on virtual shards."""
     program: List[object] = []
     batch: List[BitGate] = []
+
+    def push(step):
+        program.append(step)
+        if emit is not None:
+            emit(step)
 
     def flush():
         if batch:
             passes = plan_local(list(batch))
             if passes:
-                program.append(("local", passes))
+                push(("local", passes))
             batch.clear()
 
     for a in actions:
@@ -302,7 +308,7 @@ def compile_program(actions: Sequence[object], nl: int, rank: int, plan_local) -
             batch.append(BitGate("swap", (a.a, a.b)))
         else:
             flush()
-            program.append(a)
+            push(a)
     flush()
     return program
 

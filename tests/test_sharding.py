@@ -244,8 +244,8 @@ def test_rank_local_merge_and_plan_on_virtual_shards(gbits, kind):
 
 def _host_only_backend(n, gbits, rank, tile_bits=5, min_low_bits=2):
     """A ShardedB200Backend with its device side cut off: the real apply_gates / kronselect_dot / flush
-    run (queueing, schedule, rank-local planning, the compiled-circuit program cache), `_run_program`
-    only records what it would launch."""
+    run (queueing, schedule, rank-local planning, launching step by step, the compiled-circuit program
+    cache); only the four launch helpers are replaced by recorders."""
     import types
     from qip_b200.sharded import ShardedB200Backend
     b = object.__new__(ShardedB200Backend)
@@ -256,8 +256,22 @@ def _host_only_backend(n, gbits, rank, tile_bits=5, min_low_bits=2):
     b.eng = types.SimpleNamespace(tile_bits=tile_bits, min_low_bits=min_low_bits)
     b.stats = {"gates": 0}
     b._pending_init = None
-    b.programs = []
-    b._run_program = b.programs.append
+    b.device = -1                                   # torch.cuda.device(-1) is a no-op context
+    b._stream = lambda: None
+    b.programs = []                                 # one list of launched steps per flush
+
+    def launch(step):
+        b.programs[-1].append(step)
+    b._run_passes = lambda passes: launch(("local", passes))
+    b._exchange = b._multi_exchange = b._peer_gate = launch
+    real_flush = b.flush
+
+    def flush():
+        b.programs.append([])
+        real_flush()
+        if not b.programs[-1]:
+            b.programs.pop()
+    b.flush = flush
     return b
 
 
@@ -290,7 +304,9 @@ def test_sharded_flush_caches_the_rank_local_program_of_compiled_segments(gbits)
             first_programs = [b.programs for b in backends]
         else:
             for b, first in zip(backends, first_programs):
-                assert all(x is y for x, y in zip(b.programs, first))       # replays reuse the planned passes
+                for prog, first_prog in zip(b.programs, first):             # replays reuse the planned passes
+                    assert len(prog) == len(first_prog)
+                    assert all((x[1] is y[1]) if isinstance(x, tuple) else (x is y) for x, y in zip(prog, first_prog))
         vs = shardsim.VirtualShards(psi, gbits)
         for step in range(2):
             vs.run_programs([b.programs[step] for b in backends])
