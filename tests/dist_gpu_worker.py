@@ -106,6 +106,25 @@ def main():
     g = ShardedB200Backend.make_state(n, [list(range(n))], [2741])            # a basis state, no vector at all
     assert int(np.argmax(np.abs(g.get_state()))) == 2741 and abs(g.total_prob() - 1.0) < 1e-15
     g.close()
+    # compiled circuit replayed on the sharded engine: the flush of every gate segment caches its rank-local
+    # program (schedule + planned passes) and the replays must reproduce the first run
+    from qip_b200.graph import CompiledCircuit
+    seg = list(layered_stream(n, 2, 4)) + list(qfft_stream(n))
+    ops_c = [("k", m) for m in seg] + [("p", [0, n - 1, 5])] + [("k", m) for m in layered_stream(n, 1, 8)]
+    circ = CompiledCircuit.from_ops(n, groups, feeds, ops_c)
+    c = orc.OracleBackend.make_state(n, groups, feeds)
+    for m in seg:
+        c.kronselect_dot(m)
+    want_p = c.measure_probabilities([0, n - 1, 5])
+    for m in layered_stream(n, 1, 8):
+        c.kronselect_dot(m)
+    for replay in range(3):
+        state, classic = circ.run(backend_constructor=ShardedB200Backend.make_state)
+        check("compiled state %d" % replay, state, c.get_state())
+        check("compiled probs %d" % replay, classic[len(seg)], want_p, 1e-13)
+        assert circ.last_stats.get("cached_flushes", 0) == (0 if replay == 0 else 2), circ.last_stats
+    if rank == 0:
+        print("OK compiled circuit replays (cached sharded programs)")
     # production-size shards (2^24 amplitudes each: the specialised fused kernels, the multi-bit remap): QFFT of
     # a basis state |j> against its closed form e^{+2 pi i j k / N} / sqrt(N)
     G = int(np.log2(world))
