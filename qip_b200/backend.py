@@ -75,6 +75,29 @@ class DeviceState(object):
         return self.tensor[item].cpu().numpy()
 
 
+_SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+def pack_pass(p: Pass):
+    """The C arguments of qipb_apply_fused for a fused pass: (qipb_gate array, tile-bit array).  Built once per
+    Pass object (compiled circuits replay passes)."""
+    packed = getattr(p, "_packed", None)
+    if packed is None:
+        arr = (_lib.Gate * len(p.gates))()
+        for i, g in enumerate(p.gates):
+            mat, diag = (_SWAP4, False) if g.kind == "swap" else (g.mat, g.diagonal)
+            arr[i].k = g.k
+            arr[i].diagonal = 1 if diag else 0
+            for j, b in enumerate(g.bits):
+                arr[i].bits[j] = b
+            arr[i].ctrl_mask = g.ctrl_mask
+            flat = np.ascontiguousarray(mat, dtype=np.complex128).reshape(-1)
+            ctypes.memmove(arr[i].mat, flat.ctypes.data, 16 * flat.size)
+        packed = (arr, _lib.int_array(p.tile_bits))
+        p._packed = packed
+    return packed
+
+
 class B200Backend(object):
     """StateType implementation on one B200 (see module docstring)."""
 
@@ -193,23 +216,8 @@ class B200Backend(object):
             _lib.check(self.L.qipb_apply_matrix(self.ctx, self._ptr(), self.n, self.code, g.k, _lib.int_array(g.bits),
                                                 _lib.mat_array(g.mat), g.ctrl_mask, 1 if g.diagonal else 0))
 
-    _SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
-
     def _launch_fused(self, p: Pass):
-        packed = getattr(p, "_packed", None)       # the C structs of a pass are built once (compiled circuits replay passes)
-        if packed is None:
-            arr = (_lib.Gate * len(p.gates))()
-            for i, g in enumerate(p.gates):
-                mat, diag = (self._SWAP4, False) if g.kind == "swap" else (g.mat, g.diagonal)
-                arr[i].k = g.k
-                arr[i].diagonal = 1 if diag else 0
-                for j, b in enumerate(g.bits):
-                    arr[i].bits[j] = b
-                arr[i].ctrl_mask = g.ctrl_mask
-                flat = np.ascontiguousarray(mat, dtype=np.complex128).reshape(-1)
-                ctypes.memmove(arr[i].mat, flat.ctypes.data, 16 * flat.size)
-            packed = (arr, _lib.int_array(p.tile_bits))
-            p._packed = packed
+        packed = pack_pass(p)
         _lib.check(self.L.qipb_apply_fused(self.ctx, self._ptr(), self.n, self.code, len(p.tile_bits),
                                            packed[1], len(p.gates), packed[0]))
 

@@ -10,6 +10,10 @@ namespace qipb {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
+// Sweep arithmetic and index helpers are host+device so that tests/csrc/fused_emul.cu can run the very same
+// code on a CPU tile (the product never executes them on the host).
+#define QIPB_HD __host__ __device__ __forceinline__
+
 // ---- amplitude types -------------------------------------------------------------------
 // complex128 amplitude = double2 (one 128-bit transaction), complex64 = float2 (64-bit).
 template <typename A> struct amp_traits;
@@ -31,7 +35,7 @@ __device__ __forceinline__ void cfma(A &acc, const double2 m, const A a) {
     acc.y = fma(mi, a.x, acc.y);
 }
 template <typename A>
-__device__ __forceinline__ A cmul(const double2 m, const A a) {
+QIPB_HD A cmul(const double2 m, const A a) {
     typedef typename amp_traits<A>::real R;
     const R mr = (R)m.x, mi = (R)m.y;
     A r;
@@ -46,7 +50,7 @@ __device__ __forceinline__ double norm2(const A a) {
 
 // ---- bit helpers -----------------------------------------------------------------------
 // Insert a zero bit at position p (bits >= p move up by one).
-__device__ __forceinline__ u64 insert_zero(u64 v, int p) {
+QIPB_HD u64 insert_zero(u64 v, int p) {
     const u64 lo = v & ((1ull << p) - 1ull);
     return ((v >> p) << (p + 1)) | lo;
 }

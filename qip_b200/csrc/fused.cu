@@ -79,27 +79,27 @@ static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel para
 template <typename A> struct Cf { typename amp_traits<A>::real x, y; };
 // coefficient i of a gate descriptor, stored by the host in the amplitude's precision (complex64 launches
 // hold float2 over the same bytes: a per-use F2F of a warp-uniform double costs more than the FFMA it feeds)
-template <typename A> __device__ __forceinline__ Cf<A> coef(const DevGate &g, int i);
-template <> __device__ __forceinline__ Cf<double2> coef<double2>(const DevGate &g, int i) {
+template <typename A> QIPB_HD Cf<A> coef(const DevGate &g, int i);
+template <> QIPB_HD Cf<double2> coef<double2>(const DevGate &g, int i) {
     Cf<double2> c;
     c.x = g.m[i].x;
     c.y = g.m[i].y;
     return c;
 }
-template <> __device__ __forceinline__ Cf<float2> coef<float2>(const DevGate &g, int i) {
+template <> QIPB_HD Cf<float2> coef<float2>(const DevGate &g, int i) {
     const float2 v = reinterpret_cast<const float2 *>(g.m)[i];
     Cf<float2> c;
     c.x = v.x;
     c.y = v.y;
     return c;
 }
-template <typename A> __device__ __forceinline__ A cmulc(const Cf<A> m, const A a) {
+template <typename A> QIPB_HD A cmulc(const Cf<A> m, const A a) {
     A r;
     r.x = m.x * a.x - m.y * a.y;
     r.y = m.x * a.y + m.y * a.x;
     return r;
 }
-template <typename A> __device__ __forceinline__ void cfmac(A &acc, const Cf<A> m, const A a) {
+template <typename A> QIPB_HD void cfmac(A &acc, const Cf<A> m, const A a) {
     acc.x = fma(m.x, a.x, acc.x);
     acc.x = fma(-m.y, a.y, acc.x);
     acc.y = fma(m.x, a.y, acc.y);
@@ -110,12 +110,12 @@ template <typename A> __device__ __forceinline__ void cfmac(A &acc, const Cf<A> 
 template <int NINS> struct Expand {
     u32 nm[NINS > 0 ? NINS : 1];
     u32 ior;
-    __device__ __forceinline__ explicit Expand(const DevGate &g) {
+    QIPB_HD explicit Expand(const DevGate &g) {
 #pragma unroll
         for (int q = 0; q < NINS; ++q) nm[q] = g.nmask[q];
         ior = g.in_or;
     }
-    __device__ __forceinline__ u32 operator()(u32 w) const {
+    QIPB_HD u32 operator()(u32 w) const {
 #pragma unroll
         for (int q = 0; q < NINS; ++q) w += (w & nm[q]);
         return w | ior;
@@ -124,8 +124,8 @@ template <int NINS> struct Expand {
 // any number of fixed positions (rare shapes: more than four in-tile controls)
 struct ExpandAny {
     const DevGate &g;
-    __device__ __forceinline__ explicit ExpandAny(const DevGate &g_) : g(g_) {}
-    __device__ __forceinline__ u32 operator()(u32 w) const {
+    QIPB_HD explicit ExpandAny(const DevGate &g_) : g(g_) {}
+    QIPB_HD u32 operator()(u32 w) const {
         for (int q = 0; q < g.nins; ++q) w += (w & g.nmask[q]);
         return w | g.in_or;
     }
@@ -139,7 +139,7 @@ struct StageRef {
     u32 nlo;
     u32 sor;                           // in-tile controls of the stage
 };
-__device__ __forceinline__ StageRef stage_ref(const DevGate &st, const double2 *__restrict__ tables, const double2 S, int tb) {
+QIPB_HD StageRef stage_ref(const DevGate &st, const double2 *__restrict__ tables, const double2 S, int tb) {
     const StageInfo &si = *reinterpret_cast<const StageInfo *>(st.m);
     StageRef r;
     r.T = tables + si.tab_off;
@@ -153,7 +153,7 @@ __device__ __forceinline__ StageRef stage_ref(const DevGate &st, const double2 *
 // The stage scalars of one tile (product of the outside-cell tables at the tile's base index), one op
 // per thread, computed while the tile's load is in flight; the sweeps read them from shared memory.
 template <int NT>
-__device__ __forceinline__ void stage_scalars(const FusedArgs &f, u64 base, double2 *stage_S, int tid) {
+QIPB_HD void stage_scalars(const FusedArgs &f, u64 base, double2 *stage_S, int tid) {
     const int lo = f.tb < FUSED_LO_BITS ? f.tb : FUSED_LO_BITS;
     for (int op = tid; op < f.ngates; op += NT)
         if (f.g[op].diag >= 2) {
@@ -174,8 +174,10 @@ __device__ __forceinline__ void stage_scalars(const FusedArgs &f, u64 base, doub
 //   MK_REALPHASE  M = R . diag(ph): phases at complex slots 8..11 32 + 4 per phased column
 //   MK_MONOMIAL   one non-zero per row/column: coefficients at complex slots 0..3, `perm`    4 per non-unit entry
 enum { MK_GENERAL = 0, MK_REAL = 1, MK_REALPHASE = 2, MK_MONOMIAL = 3 };
+// exact forms of a dense 1-qubit gate (DevGate::mk of a k == 1 op)
+enum { MK1_GENERAL = 0, MK1_REAL = 1 };
 
-template <typename A> __device__ __forceinline__ typename amp_traits<A>::real rcoef(const DevGate &g, int i) {
+template <typename A> QIPB_HD typename amp_traits<A>::real rcoef(const DevGate &g, int i) {
     return reinterpret_cast<const typename amp_traits<A>::real *>(g.m)[i];
 }
 
@@ -184,7 +186,7 @@ template <typename A, int MK> struct Block2 {
     Cf<A> m[MK == MK_GENERAL ? 16 : 4];
     R r[MK == MK_GENERAL ? 1 : 16];
     u32 phmask;
-    __device__ __forceinline__ explicit Block2(const DevGate &g) {
+    QIPB_HD explicit Block2(const DevGate &g) {
         phmask = g.phmask;
         if (MK == MK_GENERAL) {
 #pragma unroll
@@ -198,7 +200,7 @@ template <typename A, int MK> struct Block2 {
             }
         }
     }
-    __device__ __forceinline__ void apply(A a0, A a1, A a2, A a3, A (&o)[4]) const {
+    QIPB_HD void apply(A a0, A a1, A a2, A a3, A (&o)[4]) const {
         if (MK == MK_GENERAL) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -230,7 +232,7 @@ template <typename A, int MK> struct Block2 {
 };
 
 template <typename A, bool UNI, int NT, int MK, typename EX>
-__device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+QIPB_HD void sweep_dense2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
     const Block2<A, MK> blk(g);
     if (UNI && (ngroups % (2 * NT)) == 0) {
@@ -271,7 +273,7 @@ __device__ __forceinline__ void sweep_dense2(A *tile, const DevGate &g, const EX
 // permutation with phases (Swap, CX / CZ-like blocks with phase gates folded in): pure data movement plus at
 // most one complex multiply per amplitude; column j goes to row perm[j]
 template <typename A, bool UNI, int NT, typename EX>
-__device__ __forceinline__ void sweep_mono2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+QIPB_HD void sweep_mono2(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
     const u32 perm = g.perm, phmask = g.phmask;
     const Cf<A> c0 = coef<A>(g, 0), c1 = coef<A>(g, 1), c2 = coef<A>(g, 2), c3 = coef<A>(g, 3);
@@ -307,14 +309,14 @@ __device__ __forceinline__ void sweep_mono2(A *tile, const DevGate &g, const EX 
 // applies the correspondingly permuted matrix M'[i][j] = M[i ^ R][j ^ R] instead (8 registers per lane).
 template <typename A> struct LowBits { static constexpr int value = sizeof(A) == 16 ? 3 : 4; };
 
-template <typename A> __device__ __forceinline__ void cswap(const bool c, A &u, A &v) {
+template <typename A> QIPB_HD void cswap(const bool c, A &u, A &v) {
     const A t = c ? v : u;
     v = c ? u : v;
     u = t;
 }
 
 template <typename A, bool UNI, int NT, int MK, typename EX>
-__device__ __forceinline__ void sweep_dense2_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+QIPB_HD void sweep_dense2_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     constexpr int LOWB = LowBits<A>::value;
     const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
     const int c = (g.tl[0] < LOWB) + (g.tl[1] < LOWB);
@@ -355,7 +357,7 @@ __device__ __forceinline__ void sweep_dense2_low(A *tile, const DevGate &g, cons
 }
 
 template <typename A, bool UNI, int NT, typename EX>
-__device__ __forceinline__ void sweep_dense1_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+QIPB_HD void sweep_dense1_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     constexpr int LOWB = LowBits<A>::value;
     const u32 o1 = 1u << g.tl[0];
     const bool R = (((u32)tid >> (LOWB - 1)) & 1u) != 0u;
@@ -376,7 +378,7 @@ __device__ __forceinline__ void sweep_dense1_low(A *tile, const DevGate &g, cons
 
 // ---- dense 1-qubit gate: pairs ----
 template <typename A, bool UNI, int NT, typename EX>
-__device__ __forceinline__ void sweep_dense1(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+QIPB_HD void sweep_dense1(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     const u32 o1 = 1u << g.tl[0];
     const Cf<A> m0 = coef<A>(g, 0), m1 = coef<A>(g, 1), m2 = coef<A>(g, 2), m3 = coef<A>(g, 3);
 #pragma unroll 2
@@ -396,7 +398,7 @@ __device__ __forceinline__ void sweep_dense1(A *tile, const DevGate &g, const EX
 // whose low `lo` bits never change (the stride of the sweep is a multiple of 2^lo), so the T_lo factor
 // and the stage scalar are folded once per thread; per pair only T_hi is looked up. ----
 template <typename A, bool UNI, int NT>
-__device__ __forceinline__ void sweep_dense1_stage(A *tile, const DevGate &g, const StageRef sr, u32 ngroups, int tid) {
+QIPB_HD void sweep_dense1_stage(A *tile, const DevGate &g, const StageRef sr, u32 ngroups, int tid) {
     const u32 o1 = 1u << g.tl[0];
     const u32 nm = g.nmask[0];
     const u32 sor = sr.sor, lom = sr.nlo - 1u;
@@ -465,7 +467,7 @@ __device__ __forceinline__ void sweep_dense1_stage(A *tile, const DevGate &g, co
 
 // ---- a stage on its own: one phase per element ----
 template <typename A, bool UNI, int NT, typename EX>
-__device__ __forceinline__ void sweep_stage(A *tile, const StageRef sr, const EX ex, u32 n, int tid) {
+QIPB_HD void sweep_stage(A *tile, const StageRef sr, const EX ex, u32 n, int tid) {
     const double2 *__restrict__ Th = sr.T + sr.nlo;
     const double2 SL = cmul<double2>(sr.S, sr.T[ex((u32)tid) & (sr.nlo - 1u)]);   // low bits are sweep-invariant
     const int lo = sr.lo;
@@ -495,7 +497,7 @@ __device__ __forceinline__ void sweep_stage(A *tile, const StageRef sr, const EX
 
 // ---- a lone diagonal gate (k <= 2 targets, any of them possibly outside the tile) ----
 template <typename A, bool UNI, int NT, typename EX>
-__device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX ex, u32 ngroups, u64 base, int tid) {
+QIPB_HD void sweep_diag(A *tile, const DevGate &g, const EX ex, u32 ngroups, u64 base, int tid) {
     u32 sel_out = 0;           // matrix-index bits of the targets that lie outside the tile (fixed per tile)
     for (int j = 0; j < g.k; ++j)
         if (g.tl[j] == 0xFF) sel_out |= (u32)((base >> g.tg[j]) & 1ull) << (g.k - 1 - j);
@@ -538,7 +540,7 @@ __device__ __forceinline__ void sweep_diag(A *tile, const DevGate &g, const EX e
 // its item count (tile bits - fixed positions >= 8) and at most four fixed positions -- true for every
 // production-size pass; tiny states and gates with many in-tile controls take the generic kernel.
 template <typename A, bool UNI, int NT>
-__device__ __forceinline__ void run_op(A *tile, const DevGate &g, const DevGate &next, const double2 *__restrict__ tables,
+QIPB_HD void run_op(A *tile, const DevGate &g, const DevGate &next, const double2 *__restrict__ tables,
                                        const double2 *stage_S, int gi, u64 base, int tb, u32 tsize, int tid) {
     if ((base & g.out_ctrl) != g.out_ctrl) return;
     const u32 ngroups = tsize >> g.nins;
@@ -599,6 +601,15 @@ __device__ __forceinline__ void run_op(A *tile, const DevGate &g, const DevGate 
         default: sweep_dense1<A, false, NT>(tile, g, ExpandAny(g), ngroups, tid); break;
         }
     }
+}
+
+// The op loop of every executor (the two kernels below, and the host emulation of tests/csrc/fused_emul.cu):
+//   for gi: if (!fused_op_is_skipped(g[gi])) { run_fused_op(...); barrier; }
+QIPB_HD bool fused_op_is_skipped(const DevGate &g) { return g.diag == 3; }      // stage already applied by the dense gate before it
+
+template <typename A, bool UNI, int NT>
+QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *stage_S, u64 base, u32 tsize, int tid) {
+    run_op<A, UNI, NT>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, stage_S, gi, base, f.tb, tsize, tid);
 }
 
 // BULK: tile staging with cp.async.bulk (TMA 1-D bulk copies, one per contiguous run, completion on
@@ -668,8 +679,8 @@ __global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fu
 
         // ---- run the gate list on the tile ----
         for (int gi = 0; gi < f.ngates; ++gi) {
-            if (f.g[gi].diag == 3) continue;                    // stage already applied by the dense gate before it
-            run_op<A, UNI, NT>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, stage_S, gi, base, f.tb, tsize, tid);
+            if (fused_op_is_skipped(f.g[gi])) continue;
+            run_fused_op<A, UNI, NT>(tile, f, gi, stage_S, base, tsize, tid);
             __syncthreads();
         }
 
@@ -792,10 +803,10 @@ __global__ void __launch_bounds__(RING_THREADS, 1) fused_ring_kernel(A *__restri
             mbar_wait(&full[b], (k / NBUF) & 1u);
             bool first = true;
             for (int gi = 0; gi < f.ngates; ++gi) {
-                if (f.g[gi].diag == 3) continue;                // stage already applied by the dense gate before it
+                if (fused_op_is_skipped(f.g[gi])) continue;
                 if (!first) named_bar_sync(1, RING_COMPUTE);
                 first = false;
-                run_op<A, true, RING_COMPUTE>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, stage_S[b], gi, base, f.tb, tsize, tid);
+                run_fused_op<A, true, RING_COMPUTE>(tile, f, gi, stage_S[b], base, tsize, tid);
             }
             fence_proxy_async();           // generic-proxy writes -> visible to the bulk store
             named_bar_sync(1, RING_COMPUTE);
@@ -1077,18 +1088,17 @@ int upload_tables(qipb_ctx *ctx, const std::vector<cplx> &tables, const double2 
     return QIPB_OK;
 }
 
-}  // namespace qipb
-
-using namespace qipb;
-
-extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
-                                int ngates, const qipb_gate *gates) {
-    QIPB_REQUIRE(ctx && state && gates && tile_bits, "null argument");
+// Validation and lowering of one fused pass: gate list -> device descriptors, FUSED_MAX_OPS per launch.  No CUDA
+// calls in here: `prepare(tables, f)` makes the stage tables reachable through f.tables (the library uploads them,
+// tests/csrc/fused_emul.cu points at the host vector) and `launch(f)` consumes one filled FusedArgs.
+template <typename Prepare, typename Launch>
+static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates, const qipb_gate *gates,
+                       Prepare prepare, Launch launch) {
+    QIPB_REQUIRE(gates && tile_bits, "null argument");
     QIPB_REQUIRE(nbits >= 0 && nbits <= 40, "nbits %d unsupported", nbits);
     QIPB_REQUIRE(ntile_bits >= 0 && ntile_bits <= QIPB_MAX_TILE_BITS && ntile_bits <= nbits, "tile bits %d unsupported", ntile_bits);
     QIPB_REQUIRE(ngates >= 1 && ngates <= QIPB_MAX_FUSED_GATES, "ngates %d unsupported (1..%d)", ngates, QIPB_MAX_FUSED_GATES);
     QIPB_REQUIRE(dtype == QIPB_C128 || dtype == QIPB_C64, "unknown dtype %d", dtype);
-    QIPB_CUDA(cudaSetDevice(ctx->device));
     static thread_local FusedArgs f;    // ~29 KiB: keep it off the stack
     memset(&f, 0, sizeof(f));
     f.nbits = nbits;
@@ -1145,7 +1155,7 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
         flush_run();
     }
     {
-        int rc = upload_tables(ctx, tables, &f.tables);
+        int rc = prepare(tables, f);
         if (rc) return rc;
     }
 
@@ -1250,9 +1260,25 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
             fprintf(stderr, "[qipb] fused launch: %d input gates -> %d ops (dense %d, lone diagonal %d, stages %d of which %d ride on a dense gate), tables %zu\n",
                     ngates, (int)cnt, ndense, ndiag, nst, npost, tables.size());
         }
-        int rc = dtype == QIPB_C128 ? launch_fused<double2>(ctx, (double2 *)state, f)
-                                    : launch_fused<float2>(ctx, (float2 *)state, f);
+        int rc = launch(f);
         if (rc) return rc;
     }
     return QIPB_OK;
+}
+
+}  // namespace qipb
+
+using namespace qipb;
+
+extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
+                                int ngates, const qipb_gate *gates) {
+    QIPB_REQUIRE(ctx && state, "null argument");
+    QIPB_CUDA(cudaSetDevice(ctx->device));
+    return lower_fused(
+        nbits, dtype, ntile_bits, tile_bits, ngates, gates,
+        [&](const std::vector<cplx> &tables, FusedArgs &f) { return upload_tables(ctx, tables, &f.tables); },
+        [&](const FusedArgs &f) {
+            return dtype == QIPB_C128 ? launch_fused<double2>(ctx, (double2 *)state, f)
+                                      : launch_fused<float2>(ctx, (float2 *)state, f);
+        });
 }

@@ -62,7 +62,7 @@ struct StageInfo {
 };
 
 // Product of a stage's outside-cell tables at this tile's base index (uniform per tile).
-__device__ __forceinline__ double2 stage_scalar(const StageInfo &si, const double2 *__restrict__ T, u64 base, u32 nlo, u32 nhi) {
+QIPB_HD double2 stage_scalar(const StageInfo &si, const double2 *__restrict__ T, u64 base, u32 nlo, u32 nhi) {
     double2 S = make_double2(1.0, 0.0);
     const double2 *To = T + nlo + nhi;
     for (int c = 0; c < si.nout; ++c) {

@@ -1,0 +1,153 @@
+"""CPU tier: the fused pass's C++ lowering and sweep arithmetic, executed on the host.
+
+tests/csrc/fused_emul.cu (test infrastructure, built here with nvcc) includes qip_b200/csrc/fused.cu and runs
+qipb_apply_fused's real lowering (diagonal runs -> stage tables, structured 2-qubit block forms, stages riding on a
+dense 1-qubit sweep, splitting into launches) and the real sweep functions on a host tile, "thread" by "thread".
+The passes come from the product planner (qip_b200.ops.plan) and are packed by the product's pack_pass; the result
+is compared with the numpy bit simulator (tests/bitsim.py), which applies the same BitGates one by one.
+
+Not covered here (device only): TMA staging, mbarriers, the grid loop -- tests/test_gpu_parity.py."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import bitsim
+from qip_b200 import lib as qlib
+from qip_b200 import ops
+from qip_b200.backend import pack_pass
+from qip_b200.circuits import H2, X2, haar_unitary, layered_stream, qfft_stream, rm_mat
+from qip_b200.mats import CMat, SwapMat
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc"))
+import build_emul  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emul():
+    L = ctypes.CDLL(build_emul.build())
+    L.qipb_emul_fused.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                  ctypes.c_int, ctypes.POINTER(qlib.Gate), ctypes.POINTER(ctypes.c_int)]
+    L.qipb_emul_fused.restype = ctypes.c_int
+    L.qipb_emul_last_error.restype = ctypes.c_char_p
+    return L
+
+
+def logical_gates(stream, n):
+    gates = []
+    for mats in stream:
+        for g in ops.decode_mats(mats, n):
+            s = ops.simplify(g)
+            if s is not None:
+                gates.append(s)
+    return gates
+
+
+def run_emulated(L, state, passes, n, dtype):
+    """Fused passes through the emulator, stand-alone passes through the bit simulator."""
+    code = qlib.C128 if dtype == np.complex128 else qlib.C64
+    info_total = np.zeros(8, dtype=np.int64)
+    st = np.ascontiguousarray(state, dtype=dtype)
+    for p in passes:
+        if not p.fused:
+            st = np.ascontiguousarray(bitsim.run_passes(st.astype(np.complex128), [p], n), dtype=dtype)
+            continue
+        arr, tbits = pack_pass(p)
+        info = (ctypes.c_int * 8)()
+        rc = L.qipb_emul_fused(st.ctypes.data_as(ctypes.c_void_p), n, code, len(p.tile_bits), tbits, len(p.gates), arr, info)
+        assert rc == 0, L.qipb_emul_last_error()
+        info_total += np.array(list(info))
+    return st, info_total
+
+
+def random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    return psi / np.linalg.norm(psi)
+
+
+def check(L, stream, n, seed=0, dtype=np.complex128, tile_bits=12, min_low_bits=7):
+    gates = logical_gates(stream, n)
+    passes, _ = ops.plan(gates, n, 16 if dtype == np.complex128 else 8, strategy="tile", tile_bits=tile_bits,
+                         min_low_bits=min_low_bits)
+    psi = random_state(n, seed)
+    want = bitsim.run_passes(psi.copy(), passes, n)
+    got, info = run_emulated(L, psi, passes, n, dtype)
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    err = float(np.max(np.abs(got - want))) / float(np.max(np.abs(want)))
+    assert err <= tol, err
+    return info
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("seed", range(3))
+def test_emulated_layered_passes_match_bit_simulator(emul, dtype, seed):
+    # production-shaped launches (2^12 tiles, 2 KiB runs -> the specialised sweeps): structured block forms, lone
+    # diagonal gates, clustered diagonal runs, low-bit (bank-conflict-free) sweeps
+    info = check(emul, layered_stream(14, 3, seed), 14, seed, dtype)
+    assert info[1] == info[0] >= 3 and info[4] >= 1, info
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_emulated_qfft_stages_ride_on_the_hadamard_sweeps(emul, dtype):
+    info = check(emul, qfft_stream(15), 15, 1, dtype)
+    assert info[2] >= 10 and info[3] >= 10, info
+
+
+def test_emulated_small_tiles_take_the_generic_sweeps(emul):
+    # tiny states / short runs: the non-UNI kernel variant (generic loops, ExpandAny)
+    for n, tb, low in ((6, 5, 2), (9, 8, 3), (12, 10, 4)):
+        info = check(emul, list(layered_stream(n, 2, n)) + list(qfft_stream(n)), n, n, tile_bits=tb, min_low_bits=low)
+        assert info[1] == 0, info
+
+
+def test_emulated_controls_everywhere_and_many_in_tile_controls(emul):
+    n = 14
+    rng = np.random.default_rng(4)
+    u2, u4 = haar_unitary(rng, 2), haar_unitary(rng, 4)
+    stream = [{(13, 0): CMat(X2)}, {(0, 13): CMat(X2)}, {(5, 13, 2): CMat(CMat(u2))}, {(1, 2, 12, 11): CMat(CMat(u4))},
+              {(13, 12, 11, 10, 9, 8): CMat(CMat(CMat(CMat(CMat(u2)))))}, {(12, 13, 10, 11): CMat(CMat(SwapMat(1)))},
+              {3: rm_mat(2)}, {(0, 1): CMat(rm_mat(3))}, {(13, 0): CMat(rm_mat(5))}, {(2, 7): np.diag(np.exp(1j * rng.normal(size=4)))},
+              {(6, 7): u4}, {(7, 6): u4}, {(12, 13): u4}, {(13, 11): haar_unitary(rng, 4)}, {13: u2}, {12: H2}, {11: H2}]
+    check(emul, stream, n, 2)
+    check(emul, stream, n, 3, np.complex64)
+
+
+def test_emulated_structured_forms_are_exact(emul):
+    # every structured form of a merged 2-qubit block (real, real x column phases, monomial, general) on high, low
+    # and mixed tile bits; each segment is merged into ONE block, all blocks run in one fused pass
+    n = 13
+    rng = np.random.default_rng(8)
+    for a, b in ((12, 11), (12, 0), (1, 0), (5, 9), (2, 12)):
+        qa, qb = n - 1 - a, n - 1 - b
+        segments = [[{qa: H2}, {qb: H2}, {(qa, qb): CMat(X2)}],                                     # real
+                    [{qa: rm_mat(3)}, {qb: H2}, {(qb, qa): CMat(X2)}],                             # real x column phases
+                    [{qa: rm_mat(2)}, {qb: rm_mat(5)}, {(qa, qb): CMat(X2)}, {(qa, qb): SwapMat(1)}],   # monomial
+                    [{(qa, qb): haar_unitary(rng, 4)}]]                                             # general
+        blocks = []
+        for seg in segments:
+            merged = ops.merge_blocks(logical_gates(seg, n), 2)
+            assert len(merged) == 1 and merged[0].k == 2 and not merged[0].diagonal
+            blocks.append(ops.lower(merged[0], n))
+        need = set()
+        for g in blocks:
+            need |= set(g.bits)
+        p = ops.Pass(True, blocks, ops.choose_tile(need, n, 12))
+        psi = random_state(n, a * 13 + b)
+        want = bitsim.run_passes(psi.copy(), [p], n)
+        got, info = run_emulated(emul, psi, [p], n, np.complex128)
+        assert float(np.max(np.abs(got - want))) <= 1e-13
+        assert info[4] == 3, info                          # three structured blocks, one general
+
+
+def test_emulator_reports_lowering_errors(emul):
+    g = (qlib.Gate * 1)()
+    g[0].k = 1
+    g[0].bits[0] = 12                      # non-diagonal target that is not a tile bit
+    g[0].mat[0] = 1.0
+    st = np.zeros(2 ** 13, dtype=np.complex128)
+    info = (ctypes.c_int * 8)()
+    rc = emul.qipb_emul_fused(st.ctypes.data_as(ctypes.c_void_p), 13, qlib.C128, 12, qlib.int_array(range(12)), 1, g, info)
+    assert rc != 0 and b"not a tile bit" in emul.qipb_emul_last_error()
