@@ -51,6 +51,7 @@ int qipb_set_stream(qipb_ctx *ctx, void *cuda_stream);       /* cudaStream_t; NU
 int qipb_sync(qipb_ctx *ctx);                                /* cudaStreamSynchronize          */
 unsigned long long qipb_launch_count(qipb_ctx *ctx);         /* kernels launched via this ctx  */
 unsigned long long qipb_ring_launch_count(qipb_ctx *ctx);    /* of which: persistent ring kernel of qipb_apply_fused (diagnostic) */
+unsigned long long qipb_ext_launch_count(qipb_ctx *ctx);     /* of which: fused launches with the opt-in forms (QIPB_FUSED_EXT, diagnostic) */
 
 /* ---- memory helpers for hosts without torch -------------------------------------------- */
 int qipb_dev_alloc(qipb_ctx *ctx, size_t bytes, void **out);

@@ -130,6 +130,7 @@ class B200Backend(object):
         self.ctx = _acquire_ctx(self.L, self.device.index or 0)
         self._launch_base = int(self.L.qipb_launch_count(self.ctx))
         self._ring_base = int(self.L.qipb_ring_launch_count(self.ctx))
+        self._ext_base = int(self.L.qipb_ext_launch_count(self.ctx))
         self.state = None            # torch tensor, 2^n amplitudes
         self.queue: List[Gate] = []        # logical gates, merged / lowered / planned at flush time
         self.stats = {"gates": 0, "passes": 0, "fused_passes": 0, "flushes": 0}
@@ -480,6 +481,10 @@ class B200Backend(object):
 
     def ring_launch_count(self) -> int:
         return int(self.L.qipb_ring_launch_count(self.ctx)) - self._ring_base
+
+    def ext_launch_count(self) -> int:
+        """Fused launches that took the kernel with the opt-in forms (QIPB_FUSED_EXT=1: real 1-qubit gates, paired QFT steps)."""
+        return int(self.L.qipb_ext_launch_count(self.ctx)) - self._ext_base
 
     def synchronize(self):
         self.flush()

@@ -39,6 +39,7 @@ extern "C" int qipb_create(int device, qipb_ctx **out) {
     c->scratch_bytes = 0;
     c->launches = 0;
     c->ring_launches = 0;
+    c->ext_launches = 0;
     c->tab_dev = nullptr;
     c->tab_cap = 0;
     c->tab_slot = 0;
@@ -78,6 +79,8 @@ extern "C" int qipb_sync(qipb_ctx *ctx) {
 extern "C" unsigned long long qipb_launch_count(qipb_ctx *ctx) { return ctx ? ctx->launches : 0ull; }
 
 extern "C" unsigned long long qipb_ring_launch_count(qipb_ctx *ctx) { return ctx ? ctx->ring_launches : 0ull; }
+
+extern "C" unsigned long long qipb_ext_launch_count(qipb_ctx *ctx) { return ctx ? ctx->ext_launches : 0ull; }
 
 extern "C" int qipb_dev_alloc(qipb_ctx *ctx, size_t bytes, void **out) {
     QIPB_REQUIRE(ctx && out, "null argument");

@@ -145,4 +145,5 @@ struct qipb_ctx {
     cudaEvent_t tab_ev[4];
     int tab_slot;
     double2 *kron_table;           // init.cu: product of the low-bit feed groups, 2^12 entries
+    unsigned long long ext_launches;   // fused launches that took the EXT kernel (opt-in forms, fused.cu)
 };

@@ -465,6 +465,142 @@ QIPB_HD void sweep_dense1_stage(A *tile, const DevGate &g, const StageRef sr, u3
     }
 }
 
+// ---- EXT sweeps (opt-in, QIPB_FUSED_EXT=1; run by the EXT instantiation of the kernel only) ----
+// Exact cheaper forms of dense 1-qubit gates.  The sweeps are FP64-issue / shared-memory bound, and a QFT is n
+// Hadamard sweeps each followed by its controlled phases (qip/qfft.py:33-39), so two things pay:
+//   MK1_REAL  a real 2x2 matrix (H, X, Ry): 8 FP64 instructions per pair instead of 16;
+//   QFT pair  two consecutive "Hadamard + stage" steps on tile bits a and b in ONE sweep over groups of four
+//             amplitudes (a radix-4 butterfly): half the shared-memory traffic of two sweeps and 52 instead of
+//             2 x 52 FP64 instructions per group (the Hadamard scales fold into the phase factors).
+// Coefficient layout of MK1_REAL: r00, r01, r10, r11 in the first four real slots of m (amplitude precision);
+// phmask != 0 marks s * [[1, 1], [1, -1]] exactly (only r00 = s is read by the paired sweep).
+template <typename A, bool UNI, int NT, typename EX>
+QIPB_HD void sweep_real1(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
+    typedef typename amp_traits<A>::real R;
+    const u32 o1 = 1u << g.tl[0];
+    const R m0 = rcoef<A>(g, 0), m1 = rcoef<A>(g, 1), m2 = rcoef<A>(g, 2), m3 = rcoef<A>(g, 3);
+#pragma unroll 2
+    QIPB_SWEEP(w, ngroups) {
+        A *p = tile + ex(w);
+        const A a0 = p[0], a1 = p[o1];
+        A r0, r1;
+        r0.x = fma(m1, a1.x, m0 * a0.x);
+        r0.y = fma(m1, a1.y, m0 * a0.y);
+        r1.x = fma(m3, a1.x, m2 * a0.x);
+        r1.y = fma(m3, a1.y, m2 * a0.y);
+        p[0] = r0;
+        p[o1] = r1;
+    }
+}
+
+// real 1-qubit gate + the stage controlled by exactly its target bit (host guarantees: sr.sor == 1 << g.tl[0],
+// no other fixed position, ngroups a multiple of 4 * NT)
+template <typename A, int NT>
+QIPB_HD void sweep_real1_stage(A *tile, const DevGate &g, const StageRef sr, u32 ngroups, int tid) {
+    typedef typename amp_traits<A>::real R;
+    const u32 o1 = 1u << g.tl[0];
+    const u32 nm = g.nmask[0];
+    const u32 lom = sr.nlo - 1u;
+    const R m0 = rcoef<A>(g, 0), m1 = rcoef<A>(g, 1), m2 = rcoef<A>(g, 2), m3 = rcoef<A>(g, 3);
+    const double2 *__restrict__ Th = sr.T + sr.nlo;
+    const u32 e_first = (u32)tid + ((u32)tid & nm);
+    const double2 SL1 = cmul<double2>(sr.S, sr.T[(e_first | o1) & lom]);
+    const int lo = sr.lo;
+#pragma unroll 1
+    for (u32 it = 0, nit = ngroups / (4 * NT), w = tid; it < nit; ++it, w += 4 * NT) {
+        A *p[4];
+        A a0[4], a1[4];
+        double2 th[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u32 wq = w + q * NT;
+            const u32 e = wq + (wq & nm);
+            p[q] = tile + e;
+            a0[q] = p[q][0];
+            a1[q] = p[q][o1];
+            th[q] = Th[(e | o1) >> lo];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double2 ph = cmul<double2>(SL1, th[q]);
+            A r0, r1;
+            r0.x = fma(m1, a1[q].x, m0 * a0[q].x);
+            r0.y = fma(m1, a1[q].y, m0 * a0[q].y);
+            r1.x = fma(m3, a1[q].x, m2 * a0[q].x);
+            r1.y = fma(m3, a1[q].y, m2 * a0[q].y);
+            p[q][0] = r0;
+            p[q][o1] = cmul<A>(ph, r1);
+        }
+    }
+}
+
+// Two QFT steps in one sweep.  Members of a group: x[ab] with a = the bit of the first Hadamard (ga, stage sa),
+// b = the bit of the second (gb, stage sb).  With s = s_a * s_b and PA / PB the stage phases at a member's index:
+//   u0 = x00 + x10, u1 = x01 + x11, w10 = (x00 - x10) PA(10), w11 = (x01 - x11) PA(11)
+//   z00 = s (u0 + u1)   z01 = s PB(01) (u0 - u1)   z10 = s (w10 + w11)   z11 = s PB(11) (w10 - w11)
+// which is H_a, stage a (on members with a = 1), H_b, stage b (on members with b = 1) applied in that order.
+// Host guarantees: both gates are s * [[1, 1], [1, -1]] without controls, both stages are controlled by exactly
+// their gate's target bit and have no outside controls, both targets sit above the bank-conflict bits, and
+// ngroups (= tile / 4) is a multiple of NT.  A thread's tile indices keep their low `lo` bits over the sweep, so
+// the low-cell table factor, the tile scalar and the Hadamard scales are folded once per thread.
+template <typename A, int NT>
+QIPB_HD void sweep_qft2(A *tile, const DevGate &ga, const StageRef sa, const DevGate &gb, const StageRef sb, u32 ngroups, int tid) {
+    typedef typename amp_traits<A>::real R;
+    const u32 pa = ga.tl[0], pb = gb.tl[0];
+    const u32 oa = 1u << pa, ob = 1u << pb;
+    const u32 nm0 = ~((1u << (pa < pb ? pa : pb)) - 1u), nm1 = ~((1u << (pa < pb ? pb : pa)) - 1u);
+    const R s = rcoef<A>(ga, 0) * rcoef<A>(gb, 0);
+    const u32 lom = sa.nlo - 1u;
+    const int lo = sa.lo;
+    const double2 *__restrict__ Tha = sa.T + sa.nlo;
+    const double2 *__restrict__ Thb = sb.T + sb.nlo;
+    u32 e0 = (u32)tid;
+    e0 += e0 & nm0;
+    e0 += e0 & nm1;
+    const double2 A10 = cmul<double2>(sa.S, sa.T[(e0 | oa) & lom]);
+    const double2 A11 = cmul<double2>(sa.S, sa.T[(e0 | oa | ob) & lom]);
+    double2 B01 = cmul<double2>(sb.S, sb.T[(e0 | ob) & lom]);
+    double2 B11 = cmul<double2>(sb.S, sb.T[(e0 | oa | ob) & lom]);
+    B01.x *= (double)s;
+    B01.y *= (double)s;
+    B11.x *= (double)s;
+    B11.y *= (double)s;
+#pragma unroll 1
+    for (u32 it = 0, nit = ngroups / NT, w = tid; it < nit; ++it, w += NT) {
+        u32 e = w;
+        e += e & nm0;
+        e += e & nm1;
+        A *p = tile + e;
+        const A x00 = p[0], x01 = p[ob], x10 = p[oa], x11 = p[oa + ob];
+        const double2 ta0 = Tha[(e | oa) >> lo], ta1 = Tha[(e | oa | ob) >> lo];
+        const double2 tb0 = Thb[(e | ob) >> lo], tb1 = Thb[(e | oa | ob) >> lo];
+        A u0, u1, d0, d1;
+        u0.x = x00.x + x10.x;
+        u0.y = x00.y + x10.y;
+        u1.x = x01.x + x11.x;
+        u1.y = x01.y + x11.y;
+        d0.x = x00.x - x10.x;
+        d0.y = x00.y - x10.y;
+        d1.x = x01.x - x11.x;
+        d1.y = x01.y - x11.y;
+        const A w10 = cmul<A>(cmul<double2>(A10, ta0), d0);
+        const A w11 = cmul<A>(cmul<double2>(A11, ta1), d1);
+        A z00, z10, t01, t11;
+        z00.x = s * (u0.x + u1.x);
+        z00.y = s * (u0.y + u1.y);
+        z10.x = s * (w10.x + w11.x);
+        z10.y = s * (w10.y + w11.y);
+        t01.x = u0.x - u1.x;
+        t01.y = u0.y - u1.y;
+        t11.x = w10.x - w11.x;
+        t11.y = w10.y - w11.y;
+        p[0] = z00;
+        p[ob] = cmul<A>(cmul<double2>(B01, tb0), t01);
+        p[oa] = z10;
+        p[oa + ob] = cmul<A>(cmul<double2>(B11, tb1), t11);
+    }
+}
+
 // ---- a stage on its own: one phase per element ----
 template <typename A, bool UNI, int NT, typename EX>
 QIPB_HD void sweep_stage(A *tile, const StageRef sr, const EX ex, u32 n, int tid) {
@@ -605,17 +741,46 @@ QIPB_HD void run_op(A *tile, const DevGate &g, const DevGate &next, const double
 
 // The op loop of every executor (the two kernels below, and the host emulation of tests/csrc/fused_emul.cu):
 //   for gi: if (!fused_op_is_skipped(g[gi])) { run_fused_op(...); barrier; }
-QIPB_HD bool fused_op_is_skipped(const DevGate &g) { return g.diag == 3; }      // stage already applied by the dense gate before it
+// EXT: the kernel instantiation that also knows the opt-in forms (real 1-qubit gates, paired QFT steps); the host
+// launches it only for passes that carry such ops (fused_has_ext), so the default kernels stay as measured.
+template <bool EXT>
+QIPB_HD bool fused_op_is_skipped(const DevGate &g) {
+    return g.diag == 3 || (EXT && g.post == 3);   // stage applied by the dense gate before it / second Hadamard of a QFT pair
+}
 
-template <typename A, bool UNI, int NT>
+static inline bool fused_has_ext(const FusedArgs &f) {
+    for (int gi = 0; gi < f.ngates; ++gi) {
+        const DevGate &g = f.g[gi];
+        if (g.post >= 2 || (!g.diag && g.k == 1 && g.mk == MK1_REAL)) return true;
+    }
+    return false;
+}
+
+template <typename A, bool UNI, int NT, bool EXT>
 QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *stage_S, u64 base, u32 tsize, int tid) {
+    if (EXT) {
+        const DevGate &g = f.g[gi];
+        if (g.post == 2) {                                      // ops gi .. gi+3 = H_a, stage a, H_b, stage b
+            sweep_qft2<A, NT>(tile, g, stage_ref(f.g[gi + 1], f.tables, stage_S[gi + 1], f.tb), f.g[gi + 2],
+                              stage_ref(f.g[gi + 3], f.tables, stage_S[gi + 3], f.tb), tsize >> 2, tid);
+            return;
+        }
+        if (!g.diag && g.k == 1 && g.mk == MK1_REAL) {         // host: no controls inside the tile, target above the low bits
+            if ((base & g.out_ctrl) != g.out_ctrl) return;
+            if (g.post == 1 && (base & f.g[gi + 1].out_ctrl) == f.g[gi + 1].out_ctrl)
+                sweep_real1_stage<A, NT>(tile, g, stage_ref(f.g[gi + 1], f.tables, stage_S[gi + 1], f.tb), tsize >> 1, tid);
+            else
+                sweep_real1<A, UNI, NT>(tile, g, Expand<1>(g), tsize >> 1, tid);
+            return;
+        }
+    }
     run_op<A, UNI, NT>(tile, f.g[gi], f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, stage_S, gi, base, f.tb, tsize, tid);
 }
 
 // BULK: tile staging with cp.async.bulk (TMA 1-D bulk copies, one per contiguous run, completion on
 // an mbarrier) instead of LDG/STS through registers.  Requires runs of >= 16 bytes.
 // NT threads per CTA: 256 for 2^12-amplitude tiles, 128 for 2^11 (twice as many CTAs per SM on the same shared memory)
-template <typename A, bool BULK, bool UNI, int NT>
+template <typename A, bool BULK, bool UNI, int NT, bool EXT>
 __global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
@@ -679,8 +844,8 @@ __global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fu
 
         // ---- run the gate list on the tile ----
         for (int gi = 0; gi < f.ngates; ++gi) {
-            if (fused_op_is_skipped(f.g[gi])) continue;
-            run_fused_op<A, UNI, NT>(tile, f, gi, stage_S, base, tsize, tid);
+            if (fused_op_is_skipped<EXT>(f.g[gi])) continue;
+            run_fused_op<A, UNI, NT, EXT>(tile, f, gi, stage_S, base, tsize, tid);
             __syncthreads();
         }
 
@@ -803,16 +968,23 @@ __global__ void __launch_bounds__(RING_THREADS, 1) fused_ring_kernel(A *__restri
             mbar_wait(&full[b], (k / NBUF) & 1u);
             bool first = true;
             for (int gi = 0; gi < f.ngates; ++gi) {
-                if (fused_op_is_skipped(f.g[gi])) continue;
+                if (fused_op_is_skipped<false>(f.g[gi])) continue;
                 if (!first) named_bar_sync(1, RING_COMPUTE);
                 first = false;
-                run_fused_op<A, true, RING_COMPUTE>(tile, f, gi, stage_S[b], base, tsize, tid);
+                run_fused_op<A, true, RING_COMPUTE, false>(tile, f, gi, stage_S[b], base, tsize, tid);
             }
             fence_proxy_async();           // generic-proxy writes -> visible to the bulk store
             named_bar_sync(1, RING_COMPUTE);
             if (tid == 0) mbar_arrive(&done[b]);
         }
     }
+}
+
+static bool ext_enabled() {
+    // opt-in until measured on B200 (round 2): real 1-qubit forms and paired QFT steps (EXT sweeps); read per call
+    // so that tests can toggle it.  Numerics are covered on the CPU tier by tests/test_fused_emul.py.
+    const char *e = getenv("QIPB_FUSED_EXT");
+    return e && atoi(e) != 0;
 }
 
 static bool ring_enabled() {
@@ -904,10 +1076,10 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
     // UNI: all specialised sweeps (<= 4 fixed positions) have a multiple of the CTA size as item count
     const bool half = bulk && f.tb == 11;                      // 2^11 tiles: 128-thread CTAs
     const bool uni = launch_is_uni(f, sizeof(A));
-#define QIPB_LAUNCH_FUSED(B, U, T)                                                                                          \
-    do {                                                                                                                    \
-        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        fused_kernel<A, B, U, T><<<(unsigned)grid, T, smem, ctx->stream>>>(state, f);                                       \
+#define QIPB_LAUNCH_FUSED(B, U, T, X)                                                                                          \
+    do {                                                                                                                       \
+        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U, T, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        fused_kernel<A, B, U, T, X><<<(unsigned)grid, T, smem, ctx->stream>>>(state, f);                                       \
     } while (0)
     if (uni && !half && ring_enabled() && f.ntiles >= 4ull * (u64)ctx->sm_count && (tsize_runs(f) <= 128)) {
         constexpr int NBUF = sizeof(A) == 16 ? 3 : 6;
@@ -915,10 +1087,13 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
         QIPB_CUDA(cudaFuncSetAttribute(fused_ring_kernel<A, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         fused_ring_kernel<A, NBUF><<<(unsigned)ctx->sm_count, RING_THREADS, rsmem, ctx->stream>>>(state, f);
         ctx->ring_launches++;
-    } else if (half) QIPB_LAUNCH_FUSED(true, true, 128);
-    else if (uni) QIPB_LAUNCH_FUSED(true, true, 256);
-    else if (bulk) QIPB_LAUNCH_FUSED(true, false, 256);
-    else QIPB_LAUNCH_FUSED(false, false, 256);
+    } else if (half) QIPB_LAUNCH_FUSED(true, true, 128, false);
+    else if (uni && fused_has_ext(f)) {                        // the host marks EXT ops only for this launch shape
+        QIPB_LAUNCH_FUSED(true, true, 256, true);
+        ctx->ext_launches++;
+    } else if (uni) QIPB_LAUNCH_FUSED(true, true, 256, false);
+    else if (bulk) QIPB_LAUNCH_FUSED(true, false, 256, false);
+    else QIPB_LAUNCH_FUSED(false, false, 256, false);
 #undef QIPB_LAUNCH_FUSED
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
@@ -1247,6 +1422,40 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                     nx.diag = 3;
                 }
             }
+        // opt-in forms (QIPB_FUSED_EXT=1): real dense 1-qubit gates and paired QFT steps, only for the launch shape
+        // of the specialised kernel (2^12 tiles, 256 threads) and only where the EXT sweeps' preconditions hold
+        if (ext_enabled() && !ring_enabled() && launch_is_uni(f, dtype == QIPB_C128 ? 16 : 8) && f.tb == 12) {
+            const int lowb = dtype == QIPB_C128 ? 3 : 4;       // LowBits<A>: targets below take the bank-conflict-free sweeps
+            for (size_t oi = 0; oi < cnt; ++oi) {
+                DevGate &d = f.g[oi];
+                const Op &o = ops[first + oi];
+                if (o.stage || d.diag || d.k != 1 || d.nins != 1 || d.tl[0] < lowb) continue;
+                const double *mat = gates[o.gate].mat;         // row-major complex 2x2
+                if (mat[1] != 0.0 || mat[3] != 0.0 || mat[5] != 0.0 || mat[7] != 0.0) continue;
+                if (d.post == 1 && f.g[oi + 1].in_or != (1u << d.tl[0])) continue;   // stage not controlled by exactly the target
+                d.mk = MK1_REAL;
+                d.phmask = (mat[0] == mat[2] && mat[0] == mat[4] && mat[0] == -mat[6] && mat[0] != 0.0) ? 1 : 0;
+                if (dtype == QIPB_C64) {
+                    float *mr = reinterpret_cast<float *>(d.m);
+                    for (int e = 0; e < 4; ++e) mr[e] = (float)mat[2 * e];
+                } else {
+                    double *mr = reinterpret_cast<double *>(d.m);
+                    for (int e = 0; e < 4; ++e) mr[e] = mat[2 * e];
+                }
+            }
+            for (size_t oi = 0; oi + 3 < cnt;) {
+                DevGate &a = f.g[oi], &sa = f.g[oi + 1], &b = f.g[oi + 2], &sb = f.g[oi + 3];
+                const bool pair = a.post == 1 && b.post == 1 && a.mk == MK1_REAL && b.mk == MK1_REAL && a.phmask && b.phmask &&
+                                  a.tl[0] != b.tl[0] && sa.diag == 3 && sb.diag == 3 && sa.out_ctrl == 0 && sb.out_ctrl == 0;
+                if (pair) {
+                    a.post = 2;
+                    b.post = 3;
+                    oi += 4;
+                } else {
+                    ++oi;
+                }
+            }
+        }
         f.nstages = 0;
         for (size_t oi = 0; oi < cnt; ++oi) f.nstages += f.g[oi].diag >= 2;
         if (getenv("QIPB_DEBUG")) {

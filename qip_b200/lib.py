@@ -17,7 +17,7 @@ MAX_DENSE_K, MAX_BIG_K, MAX_TILE_BITS, MAX_FUSED_GATES = 4, 10, 12, 280
 
 EXPORTS = [
     "qipb_version", "qipb_last_error", "qipb_create", "qipb_destroy", "qipb_set_stream", "qipb_sync",
-    "qipb_launch_count", "qipb_ring_launch_count", "qipb_dev_alloc", "qipb_dev_free", "qipb_memcpy_h2d", "qipb_memcpy_d2h",
+    "qipb_launch_count", "qipb_ring_launch_count", "qipb_ext_launch_count", "qipb_dev_alloc", "qipb_dev_free", "qipb_memcpy_h2d", "qipb_memcpy_d2h",
     "qipb_init_basis", "qipb_init_kron", "qipb_apply_matrix", "qipb_apply_swap", "qipb_apply_fused",
     "qipb_func_xor", "qipb_probabilities", "qipb_collapse", "qipb_reduce", "qipb_add_range",
     "qipb_ipc_export", "qipb_ipc_open", "qipb_ipc_close", "qipb_peer_swap", "qipb_peer_swap_bit", "qipb_peer_remap", "qipb_peer_gate1",
@@ -69,6 +69,8 @@ def load():
     L.qipb_launch_count.restype = ctypes.c_ulonglong
     L.qipb_ring_launch_count.argtypes = [vp]
     L.qipb_ring_launch_count.restype = ctypes.c_ulonglong
+    L.qipb_ext_launch_count.argtypes = [vp]
+    L.qipb_ext_launch_count.restype = ctypes.c_ulonglong
     L.qipb_dev_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
     L.qipb_dev_free.argtypes = [vp, vp]
     L.qipb_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
@@ -92,7 +94,7 @@ def load():
     L.qipb_peer_gate1.argtypes = [vp, vp, vp, ci, u64, u64, dblp, ci, u64]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("qipb_last_error", "qipb_launch_count", "qipb_ring_launch_count", "qipb_version"):
+        if name not in ("qipb_last_error", "qipb_launch_count", "qipb_ring_launch_count", "qipb_ext_launch_count", "qipb_version"):
             fn.restype = ci
     _lib = L
     return L

@@ -23,7 +23,7 @@ void set_error(const char *fmt, ...) {       // the library's copy lives in api.
 
 namespace {
 
-template <typename A, bool UNI, int NT>
+template <typename A, bool UNI, int NT, bool EXT>
 void emulate_launch(A *state, const FusedArgs &f) {
     const u32 tsize = 1u << f.tb;
     std::vector<A> tile(tsize);
@@ -40,9 +40,9 @@ void emulate_launch(A *state, const FusedArgs &f) {
         if (f.nstages)
             for (int tid = 0; tid < NT; ++tid) stage_scalars<NT>(f, base, stage_S.data(), tid);
         for (int gi = 0; gi < f.ngates; ++gi) {
-            if (fused_op_is_skipped(f.g[gi])) continue;
+            if (fused_op_is_skipped<EXT>(f.g[gi])) continue;
             for (int tid = 0; tid < NT; ++tid)
-                run_fused_op<A, UNI, NT>(tile.data(), f, gi, stage_S.data(), base, tsize, tid);
+                run_fused_op<A, UNI, NT, EXT>(tile.data(), f, gi, stage_S.data(), base, tsize, tid);
         }
         for (u32 e = 0; e < tsize; ++e) state[base + offset_of(e)] = tile[e];
     }
@@ -63,16 +63,20 @@ int emulate(A *state, const FusedArgs &f, int *info) {
         info[5] += g.post == 2;
         info[6] += (!g.diag && g.k == 1 && g.mk == MK1_REAL);
     }
-    if (half) emulate_launch<A, true, 128>(state, f);
-    else if (uni) emulate_launch<A, true, 256>(state, f);
-    else emulate_launch<A, false, 256>(state, f);
+    // the same choice of kernel instantiation as launch_fused (qip_b200/csrc/fused.cu)
+    if (half) emulate_launch<A, true, 128, false>(state, f);
+    else if (uni && fused_has_ext(f)) {
+        info[7] += 1;
+        emulate_launch<A, true, 256, true>(state, f);
+    } else if (uni) emulate_launch<A, true, 256, false>(state, f);
+    else emulate_launch<A, false, 256, false>(state, f);
     return QIPB_OK;
 }
 
 }  // namespace
 
 // info[0] launches, [1] of which take the specialised (UNI) sweeps, [2] stages, [3] stages riding on a dense 1-qubit
-// sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates
+// sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates, [7] launches of the EXT kernel
 extern "C" int qipb_emul_fused(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
                                const qipb_gate *gates, int *info) {
     QIPB_REQUIRE(host_state && info, "null argument");

@@ -151,3 +151,32 @@ def test_emulator_reports_lowering_errors(emul):
     info = (ctypes.c_int * 8)()
     rc = emul.qipb_emul_fused(st.ctypes.data_as(ctypes.c_void_p), 13, qlib.C128, 12, qlib.int_array(range(12)), 1, g, info)
     assert rc != 0 and b"not a tile bit" in emul.qipb_emul_last_error()
+
+
+# ---- the opt-in forms (QIPB_FUSED_EXT=1): real 1-qubit gates and paired QFT steps ----
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n", [13, 15, 16])
+def test_emulated_ext_qfft_pairs_two_steps_per_sweep(emul, monkeypatch, dtype, n):
+    monkeypatch.setenv("QIPB_FUSED_EXT", "1")
+    info = check(emul, qfft_stream(n), n, n, dtype)
+    assert info[5] >= 3 and info[6] >= 2 * info[5] and info[7] >= 1, info
+    monkeypatch.setenv("QIPB_FUSED_EXT", "0")
+    info = check(emul, qfft_stream(n), n, n, dtype)
+    assert info[5] == 0 and info[6] == 0 and info[7] == 0, info
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_emulated_ext_real_gates_in_layered_and_mixed_passes(emul, monkeypatch, dtype):
+    monkeypatch.setenv("QIPB_FUSED_EXT", "1")
+    n = 14
+    check(emul, layered_stream(n, 3, 5), n, 5, dtype)        # (most 1-qubit gates of a layer merge into 2-qubit blocks)
+    # real gates that are not Hadamards, a Hadamard whose stage has an outside control (no pairing), controlled
+    # real gates (general path), a QFT on a sub-register placed on high and on low tile bits
+    rng = np.random.default_rng(3)
+    ry = np.array([[np.cos(0.3), -np.sin(0.3)], [np.sin(0.3), np.cos(0.3)]])
+    stream = [{0: ry}, {1: X2}, {(2, 3): CMat(ry)}, {13: ry}, {12: H2}, {5: H2}]
+    stream += [{(q, 5): CMat(rm_mat(2 + q % 3))} for q in (0, 1, 2, 9)]
+    stream += [{6: H2}] + [{(q, 6): CMat(rm_mat(3))} for q in (7, 8, 10)]
+    stream += list(qfft_stream(6, first_qubit=1)) + list(qfft_stream(5, first_qubit=9)) + [{(0, 4): haar_unitary(rng, 4)}]
+    info = check(emul, stream, n, 6, dtype)
+    assert info[6] >= 3, info
