@@ -443,10 +443,67 @@ def choose_tile(required, nbits: int, tile_bits: int):
     return tuple(sorted(tile))
 
 
+def _PACK_1Q() -> bool:
+    import os
+    return os.environ.get("QIPB_PACK_1Q", "1") != "0"          # tuning knob for profiling runs
+
+
 def _ncoef(g: BitGate) -> int:
     if g.kind == "swap":
         return 16
     return (1 << g.k) if (g.diagonal or g.k == 0) else (1 << g.k) ** 2
+
+
+def _is_diag(g: BitGate) -> bool:
+    return g.kind == "matrix" and (g.diagonal or g.k == 0)
+
+
+def pack_lone_1q(gates: Sequence[BitGate], min_run: int = 3) -> List[BitGate]:
+    """Inside ONE fused pass: tensor pairs of un-controlled dense 1-qubit gates on different bits into one dense
+    2-qubit block.  Every gate of a pass is a sweep over the tile in shared memory; two lone Hadamards cost two
+    sweeps of 16 FP64 instructions per pair, their Kronecker product is a REAL 4x4 block -- one sweep of 32 per group
+    of four (fused.cu MK_REAL) and half the shared-memory traffic and barriers.  Exact up to the rounding of the
+    products of matrix entries.  Gate B joins an earlier gate A when nothing between them touches B's bit (B may
+    slide back).  A 1-qubit gate that is directly followed by a run of >= `min_run` diagonal gates is left alone:
+    the kernel applies that run on the gate's own sweep (a QFT step)."""
+    out: List[BitGate] = []
+    open_idx: List[int] = []                       # positions in `out` of lone gates still waiting for a partner
+    n = len(gates)
+
+    def rides(i: int) -> bool:
+        j = i + 1
+        while j < n and _is_diag(gates[j]):
+            j += 1
+        return j - (i + 1) >= min_run
+
+    for i, g in enumerate(gates):
+        lone = g.kind == "matrix" and g.k == 1 and not g.diagonal and g.ctrl_mask == 0 and not rides(i)
+        if lone:
+            bit = 1 << g.bits[0]
+            partner = None
+            for idx in reversed(open_idx):
+                a = out[idx]
+                if a.bits[0] == g.bits[0]:
+                    continue
+                blocked = False
+                for h in out[idx + 1:]:
+                    hm = h.ctrl_mask
+                    for b in h.bits:
+                        hm |= 1 << b
+                    if hm & bit:
+                        blocked = True
+                        break
+                if not blocked:
+                    partner = idx
+                    break
+            if partner is not None:
+                a = out[partner]
+                out[partner] = BitGate("matrix", (a.bits[0], g.bits[0]), 0, np.ascontiguousarray(np.kron(a.mat, g.mat)), False)
+                open_idx.remove(partner)
+                continue
+            open_idx.append(len(out))
+        out.append(g)
+    return out
 
 
 def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_bits: int = 12,
@@ -468,7 +525,7 @@ def plan_passes(gates: Sequence[BitGate], nbits: int, amp_bytes: int = 16, tile_
         solo = sum(gate_bytes(g, nbits, amp_bytes) for g in cur)
         fused_cost = 2.0 * amp_bytes * 2.0 ** nbits
         if len(cur) >= 2 and enable and fused_cost < solo:
-            passes.append(Pass(True, cur, choose_tile(need, nbits, tb)))
+            passes.append(Pass(True, pack_lone_1q(cur) if _PACK_1Q() else cur, choose_tile(need, nbits, tb)))
         else:
             passes.extend(Pass(False, [g]) for g in cur)
         cur, need, ncoefs = [], set(), 0

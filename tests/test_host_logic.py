@@ -291,3 +291,44 @@ def test_sink_lone_diagonals_only_reorders_commuting_gates():
     # directly followed by them (H0 + 5, H1 + 4, H2 + 3 phases = the first 15 gates of a 6-qubit QFFT)
     q = [s for mats in qfft_stream(6, rev=False) for s in (ops.simplify(g) for g in ops.decode_mats(mats, 6)) if s is not None]
     assert [id(g) for g in ops.sink_lone_diagonals(q)[:15]] == [id(g) for g in q[:15]]
+
+
+def test_pack_lone_1q_tensors_commuting_gates_only():
+    from qip_b200.circuits import haar_unitary
+    # inside one pass: pairs of un-controlled dense 1-qubit gates become one 2-qubit block; the state is unchanged
+    n = 8
+    rng = np.random.default_rng(11)
+    for trial in range(30):
+        gates = []
+        for _ in range(14):
+            kind = int(rng.integers(0, 5))
+            a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+            if kind == 0:
+                gates.append(ops.BitGate("matrix", (a,), 0, haar_unitary(rng, 2), False))
+            elif kind == 1:
+                gates.append(ops.BitGate("matrix", (a,), 0, H2.astype(np.complex128), False))
+            elif kind == 2:
+                gates.append(ops.BitGate("matrix", (a, b), 0, haar_unitary(rng, 4), False))
+            elif kind == 3:
+                gates.append(ops.BitGate("matrix", (a,), 1 << b, haar_unitary(rng, 2), False))            # controlled: never packed
+            else:
+                gates.append(ops.BitGate("matrix", (), (1 << a) | (1 << b), np.array([[np.exp(0.3j)]]), True))
+        packed = ops.pack_lone_1q(gates)
+        assert len(packed) <= len(gates)
+        psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        a_state, b_state = psi.copy(), psi.copy()
+        for g in gates:
+            a_state = bitsim.apply_bitgate(a_state, g, n)
+        for g in packed:
+            b_state = bitsim.apply_bitgate(b_state, g, n)
+        assert float(np.max(np.abs(a_state - b_state))) <= 1e-13
+    # two Hadamards with nothing in between on the second one's bit -> one REAL block
+    two = ops.pack_lone_1q([ops.BitGate("matrix", (3,), 0, H2.astype(np.complex128), False),
+                            ops.BitGate("matrix", (), 1 << 3, np.array([[1j]]), True),
+                            ops.BitGate("matrix", (5,), 0, H2.astype(np.complex128), False)])
+    assert len(two) == 2 and two[0].bits == (3, 5) and not two[0].mat.imag.any()
+    # a QFT step (H followed by its run of controlled phases) keeps its Hadamard: the kernel rides the run on its sweep
+    q = [s for mats in qfft_stream(10, rev=False) for s in (ops.simplify(g) for g in ops.decode_mats(mats, 10)) if s is not None]
+    q = [ops.lower(g, 10) for g in ops.merge_blocks(q, 2, cost_aware=True)]
+    kept = ops.pack_lone_1q(q)
+    assert [id(g) for g in kept[:35]] == [id(g) for g in q[:35]] and sum(g.k == 2 and not g.diagonal for g in kept) <= 2
