@@ -214,6 +214,7 @@ static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits,
         g.tbit[k - 1 - j] = (unsigned char)bits[j];
     }
     QIPB_REQUIRE((ctrl_mask & tmask) == 0, "control mask overlaps target bits");
+    QIPB_REQUIRE(nbits == 64 || (ctrl_mask >> nbits) == 0, "control mask outside the %d local bits", nbits);
     const u64 fixed = tmask | ctrl_mask;
     for (int b = 0; b < nbits; ++b)
         if ((fixed >> b) & 1ull) g.ins[g.nins++] = (unsigned char)b;
@@ -282,6 +283,7 @@ extern "C" int qipb_apply_swap(qipb_ctx *ctx, void *state, int nbits, int dtype,
     QIPB_REQUIRE(ctx && state, "null argument");
     QIPB_REQUIRE(bit_a >= 0 && bit_a < nbits && bit_b >= 0 && bit_b < nbits && bit_a != bit_b, "bad swap bits %d,%d", bit_a, bit_b);
     QIPB_REQUIRE(!(ctrl_mask & ((1ull << bit_a) | (1ull << bit_b))), "control mask overlaps swap bits");
+    QIPB_REQUIRE(nbits >= 2 && nbits <= 40 && (ctrl_mask >> nbits) == 0, "control mask outside the %d local bits", nbits);
     QIPB_CUDA(cudaSetDevice(ctx->device));
     GateArgs<1> g;
     memset(&g, 0, sizeof(g));

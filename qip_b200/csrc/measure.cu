@@ -241,6 +241,7 @@ extern "C" int qipb_collapse(qipb_ctx *ctx, void *state, int nbits, int dtype, u
     QIPB_CUDA(cudaSetDevice(ctx->device));
     const u64 n = 1ull << nbits;
     const u64 blocks = (n + 256ull * 4 - 1) / (256ull * 4);
+    QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
     if (dtype == QIPB_C128) collapse_kernel<double2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)state, n, mask, want, scale);
     else if (dtype == QIPB_C64) collapse_kernel<float2, 4><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)state, n, mask, want, scale);
     else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
@@ -262,6 +263,7 @@ extern "C" int qipb_reduce(qipb_ctx *ctx, const void *src, void *dst, int nbits,
     if (rc) return rc;
     const u64 nout = 1ull << nrest;
     const u64 blocks = (nout + 255) / 256;
+    QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
     if (dtype == QIPB_C128) reduce_kernel<double2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const double2 *)src, (double2 *)dst, nout, want, scale, spread);
     else if (dtype == QIPB_C64) reduce_kernel<float2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const float2 *)src, (float2 *)dst, nout, want, scale, spread);
     else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
@@ -275,6 +277,7 @@ extern "C" int qipb_add_range(qipb_ctx *ctx, void *state, int dtype, uint64_t st
     QIPB_CUDA(cudaSetDevice(ctx->device));
     if (count == 0) return QIPB_OK;
     const u64 blocks = (count + 255) / 256;
+    QIPB_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
     if (dtype == QIPB_C128) add_range_kernel<double2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)state + start, (const double2 *)data_dev, count);
     else if (dtype == QIPB_C64) add_range_kernel<float2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)state + start, (const float2 *)data_dev, count);
     else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
