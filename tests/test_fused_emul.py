@@ -180,3 +180,66 @@ def test_emulated_ext_real_gates_in_layered_and_mixed_passes(emul, monkeypatch, 
     stream += list(qfft_stream(6, first_qubit=1)) + list(qfft_stream(5, first_qubit=9)) + [{(0, 4): haar_unitary(rng, 4)}]
     info = check(emul, stream, n, 6, dtype)
     assert info[6] >= 3, info
+
+
+# ---- randomised passes: every gate shape the C ABI accepts, any tile-bit set, both kernels' op limits ----
+def _random_pass(rng, n, tb, lowrun, ngates):
+    tile = list(range(lowrun)) + sorted(int(b) for b in rng.choice(np.arange(lowrun, n), size=tb - lowrun, replace=False))
+    gates = []
+
+    def ctrl(exclude, nctrl):
+        others = [b for b in range(n) if b not in exclude]
+        cm = 0
+        for c in rng.choice(others, size=min(nctrl, len(others)), replace=False):
+            cm |= 1 << int(c)
+        return cm
+
+    for _ in range(ngates):
+        kind = int(rng.integers(0, 8))
+        nctrl = int(rng.choice([0, 0, 0, 1, 1, 2, 3]))
+        if kind == 7:                                          # swap of two tile bits, possibly controlled
+            t = [int(x) for x in rng.choice(tile, size=2, replace=False)]
+            gates.append(ops.BitGate("swap", tuple(t), ctrl(t, nctrl)))
+            continue
+        diag = kind >= 4
+        if kind <= 1:                                          # dense 1-qubit (general / Hadamard)
+            t = [int(rng.choice(tile))]
+            mat = haar_unitary(rng, 2) if kind == 0 else H2.astype(np.complex128)
+        elif kind <= 3:                                        # dense 2-qubit (general / real)
+            t = [int(x) for x in rng.choice(tile, size=2, replace=False)]
+            mat = haar_unitary(rng, 4)
+            if kind == 3:
+                mat = np.real(mat) + 0j
+        elif kind == 4:                                        # controlled scalar phase (what Rm / C(Rm) simplify to)
+            t, mat, nctrl = [], np.array([[np.exp(1j * rng.normal())]]), max(1, nctrl)
+        elif kind == 5:                                        # diagonal gates on ANY bits, inside or outside the tile
+            t, mat = [int(rng.integers(0, n))], np.diag(np.exp(1j * rng.normal(size=2)))
+        else:
+            t, mat = [int(x) for x in rng.choice(n, size=2, replace=False)], np.diag(np.exp(1j * rng.normal(size=4)))
+        gates.append(ops.BitGate("matrix", tuple(t), ctrl(t, nctrl), np.ascontiguousarray(mat, dtype=np.complex128), diag))
+    return ops.Pass(True, gates, tuple(tile))
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_emulated_random_passes(emul, monkeypatch, seed):
+    rng = np.random.default_rng(1000 + seed)
+    mode = seed % 4
+    if mode == 0:                                              # production shape: 2^12 tiles, long runs
+        n, tb, lowrun = int(rng.choice([13, 14])), 12, int(rng.choice([5, 6, 7, 8]))
+    elif mode == 1:                                            # 2^11 tiles (128-thread CTAs)
+        n, tb, lowrun = int(rng.choice([12, 13])), 11, int(rng.choice([5, 6, 7]))
+    elif mode == 2:                                            # tiny states, any tile
+        n = int(rng.integers(3, 11))
+        tb = int(rng.integers(2, n + 1))
+        lowrun = int(rng.integers(0, tb + 1))
+    else:                                                      # short runs (no TMA staging), or one single tile
+        n, tb, lowrun = (13, 12, int(rng.choice([0, 2, 4]))) if seed % 8 == 3 else (12, 12, 12)
+    ngates = int(rng.choice([2, 5, 15, 60, 130]))              # 130 > FUSED_MAX_OPS: split into several launches
+    dtype = np.complex128 if seed % 3 else np.complex64
+    monkeypatch.setenv("QIPB_FUSED_EXT", str(seed % 2))
+    p = _random_pass(rng, n, tb, lowrun, ngates)
+    psi = random_state(n, seed)
+    want = bitsim.run_passes(psi.copy(), [p], n)
+    got, _ = run_emulated(emul, psi, [p], n, dtype)
+    err = float(np.max(np.abs(got - want))) / float(np.max(np.abs(want)))
+    assert err <= (1e-12 if dtype == np.complex128 else 5e-5), err
