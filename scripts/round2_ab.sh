@@ -1,0 +1,32 @@
+#!/bin/bash
+# GPU-side, first call of round 2: decide the knobs that were written and CPU-validated while no GPU time was left.
+#   1. GPU tier (includes tests/test_zz_gpu_ext.py: the EXT kernel on the device)
+#   2. A/B on the same box: QIPB_FUSED_EXT (real 1-qubit sweeps, two QFT steps per sweep) and QIPB_PACK_1Q
+#      (lone 1-qubit gates tensored inside a pass) on both workloads at 33 qubits
+#   3. ncu --set full of the EXT kernel inside a QFT (30 qubits) for the sweep-level numbers
+# Usage: gpurun --timeout 1500 -- 'bash scripts/round2_ab.sh r02'
+R=${1:-r02}
+O=gpurun_out
+mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q > $O/${R}_pytest_gpu.log 2>&1; tail -3 $O/${R}_pytest_gpu.log
+for wl in qft layered; do
+ for ext in 0 1; do
+  for pack in 1 0; do
+   [ "$wl" = qft ] && [ "$pack" = 0 ] && continue
+   f=$O/${R}_ab_${wl}_ext${ext}_pack${pack}.json
+   QIPB_FUSED_EXT=$ext QIPB_PACK_1Q=$pack timeout 400 python bench.py --workload $wl --steps 4 --warmup 3 --no-micro --no-cpu > $f 2> $O/${R}_ab.err
+   python - <<PY
+import json
+try:
+    d = json.load(open("$f"))
+    print("$wl ext=$ext pack=$pack  ms/step=%.1f  e2e_ms=%.1f  passes=%s" % (d["ms_per_step"], d["e2e"]["ms_per_step"], d["config"]["stats"].get("passes")),
+          {k: (x["launches"], round(x["ms_total"] / x["launches"], 1), round(x["GBps"])) for k, x in d["kernels"].items()})
+except Exception as e:
+    print("$wl ext=$ext pack=$pack FAILED", e); print(open("$O/${R}_ab.err").read()[-1500:])
+PY
+  done
+ done
+done
+QIPB_FUSED_EXT=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 2 -c 2 -o $O/${R}_prof_fused_ext_qft \
+    python bench.py --workload qft --qubits 30 --steps 1 --warmup 1 --no-micro --no-cpu > /dev/null 2>> $O/${R}_ab.err
+ls -la $O | tail -12
