@@ -115,6 +115,15 @@ typedef struct {
 int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits,
                      const int *tile_bits, int ngates, const qipb_gate *gates);
 
+/* qipb_apply_fused_fill: the same pass applied to the ALL-ONES vector; the buffer's previous content is never
+ * read.  A product state of one-qubit feeds v_b is prod_b diag(v_b[0], v_b[1]) . ones, so a caller that leads the
+ * gate list with those diagonal gates gets "kron-product init (qip/backend.py:88-101) + first gate pass" in one
+ * write-only sweep of HBM.  Returns 3 (unsupported, nothing launched, the caller initialises the buffer and uses
+ * qipb_apply_fused) unless the tile has 2^12 amplitudes in runs of >= 512 bytes and the list starts with a run of
+ * >= 3 un-controlled diagonal gates.                                                                            */
+int qipb_apply_fused_fill(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits,
+                          const int *tile_bits, int ngates, const qipb_gate *gates);
+
 /* ---- func_apply -----------------------------------------------------------------------------
  * Replaces func_apply (qip/ext/func_apply.pyx:11-112): |x>|q>|r> -> |x>|f(x) xor q>|r>, in
  * place (the map is an involution on q for fixed x, so amplitudes are swapped pairwise).

@@ -19,6 +19,7 @@ Differences from the reference that are deliberate ("quirks"):
     rejected -- sharding is done by qip_b200.sharded instead.
 """
 import ctypes
+import os
 import math
 import random
 from typing import Callable, List, Optional, Sequence
@@ -98,11 +99,26 @@ def pack_pass(p: Pass):
     return packed
 
 
+def pack_fill_pass(factors, p: Pass):
+    """The C arguments of qipb_apply_fused_fill: one diagonal 1-qubit gate diag(v_b[0], v_b[1]) per index bit b (their
+    product applied to the all-ones vector IS the product state), followed by the gates of the fused pass `p`."""
+    n = len(factors)
+    body, tbits = pack_pass(p)
+    arr = (_lib.Gate * (n + len(p.gates)))()
+    for b, (v0, v1) in enumerate(factors):
+        arr[b].k, arr[b].diagonal, arr[b].ctrl_mask = 1, 1, 0
+        arr[b].bits[0] = b
+        arr[b].mat[0], arr[b].mat[1], arr[b].mat[6], arr[b].mat[7] = v0.real, v0.imag, v1.real, v1.imag
+    ctypes.memmove(ctypes.addressof(arr) + n * ctypes.sizeof(_lib.Gate), body, len(p.gates) * ctypes.sizeof(_lib.Gate))
+    return arr, tbits
+
+
 class B200Backend(object):
     """StateType implementation on one B200 (see module docstring)."""
 
     def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
-                 strategy: str = "auto", relabel_swaps: bool = True, host_state_max_qubits: int = _HOST_STATE_MAX_QUBITS):
+                 strategy: str = "auto", relabel_swaps: bool = True, host_state_max_qubits: int = _HOST_STATE_MAX_QUBITS,
+                 lazy_init=None):
         torch = _torch()
         self.L = _lib.load()
         if not torch.cuda.is_available():
@@ -132,6 +148,8 @@ class B200Backend(object):
         self._ring_base = int(self.L.qipb_ring_launch_count(self.ctx))
         self._ext_base = int(self.L.qipb_ext_launch_count(self.ctx))
         self.state = None            # torch tensor, 2^n amplitudes
+        self._pending_init = None    # deferred product-state init (QIPB_LAZY_INIT=1): (per-bit factors, kron arguments)
+        self.lazy_init = os.environ.get("QIPB_LAZY_INIT", "0") == "1" if lazy_init is None else bool(lazy_init)
         self.queue: List[Gate] = []        # logical gates, merged / lowered / planned at flush time
         self.stats = {"gates": 0, "passes": 0, "fused_passes": 0, "flushes": 0}
         self.profile = None          # list of (kernel label, algorithmic bytes, start event, end event) when enabled
@@ -182,12 +200,65 @@ class B200Backend(object):
             if not vgroups:                                    # only one-hot feeds: a basis state
                 _lib.check(self.L.qipb_init_basis(self.ctx, self._ptr(), n, self.code, fixed_value))
                 return
-            dev_feeds = feeds_to_device(vfeeds, self.device)
-            glen = _lib.int_array([len(g) for g in vgroups])
-            gbits = _lib.int_array([n - 1 - q for g in vgroups for q in g])
-            _lib.check(self.L.qipb_init_kron(self.ctx, self._ptr(), n, self.code, len(vgroups), glen, gbits,
-                                             ctypes.c_void_p(dev_feeds.data_ptr()), fixed_mask, fixed_value, 0))
-            self._keepalive = dev_feeds
+            if self.lazy_init and self.fuse:
+                # a product of one-qubit feeds stays virtual until the first flush: the first fused pass then WRITES
+                # its tiles from the per-bit factors instead of loading an initial state from HBM (qipb_apply_fused_fill)
+                factors = product_state_factors(vgroups, vfeeds, fixed_mask, fixed_value, n)
+                if factors is not None:
+                    self._pending_init = (factors, (vgroups, vfeeds, fixed_mask, fixed_value))
+                    return
+            self._launch_kron(vgroups, vfeeds, fixed_mask, fixed_value)
+
+    def _launch_kron(self, vgroups, vfeeds, fixed_mask, fixed_value):
+        n = self.n
+        dev_feeds = feeds_to_device(vfeeds, self.device)
+        glen = _lib.int_array([len(g) for g in vgroups])
+        gbits = _lib.int_array([n - 1 - q for g in vgroups for q in g])
+        _lib.check(self.L.qipb_init_kron(self.ctx, self._ptr(), n, self.code, len(vgroups), glen, gbits,
+                                         ctypes.c_void_p(dev_feeds.data_ptr()), fixed_mask, fixed_value, 0))
+        self._keepalive = dev_feeds
+
+    def _materialise_init(self):
+        """Build the deferred initial state with the stand-alone kron kernel (nothing fused it into a gate pass)."""
+        if self._pending_init is None:
+            return
+        torch = _torch()
+        _, args = self._pending_init
+        self._pending_init = None
+        with torch.cuda.device(self.device):
+            self._stream()
+            self._launch_kron(*args)
+
+    def _fill_first_pass(self, passes):
+        """Deferred product-state init + first fused pass in one write-only sweep.  The pass is led by one diagonal
+        1-qubit gate diag(v_b[0], v_b[1]) per index bit and applied to the all-ones vector.  Returns the passes that
+        are still to run (all of them, after a stand-alone init, when the library cannot serve the request)."""
+        torch = _torch()
+        factors, _ = self._pending_init
+        n = self.n
+        p = passes[0] if passes else None
+        if p is not None and p.fused and n + len(p.gates) <= _lib.MAX_FUSED_GATES:
+            arr, tbits = pack_fill_pass(factors, p)
+            with torch.cuda.device(self.device):
+                self._stream()
+                if self.profile is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                rc = self.L.qipb_apply_fused_fill(self.ctx, self._ptr(), n, self.code, len(p.tile_bits), tbits,
+                                                  n + len(p.gates), arr)
+                if rc == 0:
+                    if self.profile is not None:
+                        e1.record()
+                        self.profile.append(("fused_kernel[fill]", float(self.amp_bytes) * 2.0 ** n, e0, e1))
+                    self._pending_init = None
+                    self.stats["passes"] += 1
+                    self.stats["fused_passes"] += 1
+                    self.stats["fill_passes"] = self.stats.get("fill_passes", 0) + 1
+                    return passes[1:]
+                if rc != _lib.ERR_UNSUPPORTED:
+                    _lib.check(rc)
+        self._materialise_init()
+        return passes
 
     # ------------------------------------------------------------------ gate path
     def kronselect_dot(self, mats, input_offset: int = 0, output_offset: int = 0) -> None:
@@ -225,6 +296,7 @@ class B200Backend(object):
     def flush(self) -> None:
         """Execute every queued gate.  Called before anything reads or measures the state."""
         if not self.queue:
+            self._materialise_init()
             return
         cache, key = self.plan_cache if self.plan_cache is not None else (None, None)
         self.plan_cache = None
@@ -247,6 +319,8 @@ class B200Backend(object):
             if cache is not None:
                 cache[key] = (pos_before, passes, chosen, tuple(self.pos), self.stats.get("relabels", 0) - r0)
         self.stats["strategy_" + chosen] = self.stats.get("strategy_" + chosen, 0) + 1
+        if self._pending_init is not None:
+            passes = self._fill_first_pass(passes)
         self._run_passes(passes)
         self.stats["flushes"] += 1
 
@@ -537,6 +611,27 @@ def split_feeds(groups, feed_list, n, bit_of):
         if q not in fed:
             fixed_mask |= 1 << bit_of(q)
     return vgroups, vfeeds, fixed_mask, fixed_value
+
+
+def product_state_factors(vgroups, vfeeds, fixed_mask, fixed_value, n):
+    """Per index bit b the pair (v_b[0], v_b[1]) with state = (x)_b v_b, for an initial state whose vector feeds are
+    all ONE-qubit host vectors (plus one-hot / un-fed qubits, which only fix bits: split_feeds); None otherwise.
+    Bit of qubit q is n-1-q (the canonical layout a state is created in)."""
+    torch = _torch() if any(not isinstance(f, (np.ndarray, list, tuple)) for f in vfeeds) else None
+    factors = [None] * n
+    for g, f in zip(vgroups, vfeeds):
+        if len(g) != 1:
+            return None
+        if torch is not None and (isinstance(f, DeviceState) or isinstance(f, torch.Tensor)):
+            return None                                    # device-resident feed: no host round trip for it
+        v = np.asarray(f, dtype=np.complex128).reshape(-1)
+        factors[n - 1 - g[0]] = (complex(v[0]), complex(v[1]))
+    for b in range(n):
+        if (fixed_mask >> b) & 1:
+            factors[b] = (0j, 1 + 0j) if (fixed_value >> b) & 1 else (1 + 0j, 0j)
+    if any(f is None for f in factors):
+        return None
+    return factors
 
 
 def feeds_to_device(vfeeds, device):

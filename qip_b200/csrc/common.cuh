@@ -20,9 +20,9 @@ template <typename A> struct amp_traits;
 template <> struct amp_traits<double2> { typedef double real; };
 template <> struct amp_traits<float2>  { typedef float  real; };
 
-template <typename A> __device__ __forceinline__ A make_amp(typename amp_traits<A>::real x, typename amp_traits<A>::real y);
-template <> __device__ __forceinline__ double2 make_amp<double2>(double x, double y) { return make_double2(x, y); }
-template <> __device__ __forceinline__ float2  make_amp<float2>(float x, float y)    { return make_float2(x, y); }
+template <typename A> QIPB_HD A make_amp(typename amp_traits<A>::real x, typename amp_traits<A>::real y);
+template <> QIPB_HD double2 make_amp<double2>(double x, double y) { return make_double2(x, y); }
+template <> QIPB_HD float2  make_amp<float2>(float x, float y)    { return make_float2(x, y); }
 
 // acc += m * a, with m a (double) matrix coefficient converted to the amplitude precision.
 template <typename A>
@@ -91,6 +91,7 @@ void set_error(const char *fmt, ...);
 #define QIPB_OK 0
 #define QIPB_ERR_ARG 1
 #define QIPB_ERR_CUDA 2
+#define QIPB_ERR_UNSUPPORTED 3      // the request is valid but this entry point cannot serve it (caller falls back); nothing was launched
 #define QIPB_CUDA(call)                                                                  \
     do {                                                                                 \
         cudaError_t e__ = (call);                                                        \

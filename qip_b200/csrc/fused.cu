@@ -601,6 +601,24 @@ QIPB_HD void sweep_qft2(A *tile, const DevGate &ga, const StageRef sa, const Dev
     }
 }
 
+// Fill mode (EXT kernel, qipb_apply_fused_fill): the pass acts on the all-ones vector instead of the buffer's
+// content, and its first op is a stage without controls -- the tile is WRITTEN from the phase tables instead of being
+// loaded from HBM.  A product state of one-qubit feeds is exactly that: prod_b diag(v_b[0], v_b[1]) . ones
+// (CythonBackend.make_state's kron product, qip/backend.py:88-101, for one-qubit groups), so the initial state of a
+// run() never travels through HBM before the first gate pass reads it.
+template <typename A, int NT>
+QIPB_HD void sweep_stage_fill(A *tile, const StageRef sr, u32 n, int tid) {
+    typedef typename amp_traits<A>::real R;
+    const double2 *__restrict__ Th = sr.T + sr.nlo;
+    const double2 SL = cmul<double2>(sr.S, sr.T[(u32)tid & (sr.nlo - 1u)]);   // NT is a multiple of 2^lo: low bits are sweep-invariant
+    const int lo = sr.lo;
+#pragma unroll 4
+    for (u32 x = tid; x < n; x += NT) {
+        const double2 v = cmul<double2>(SL, Th[x >> lo]);
+        tile[x] = make_amp<A>((R)v.x, (R)v.y);
+    }
+}
+
 // ---- a stage on its own: one phase per element ----
 template <typename A, bool UNI, int NT, typename EX>
 QIPB_HD void sweep_stage(A *tile, const StageRef sr, const EX ex, u32 n, int tid) {
@@ -751,7 +769,7 @@ QIPB_HD bool fused_op_is_skipped(const DevGate &g) {
 static inline bool fused_has_ext(const FusedArgs &f) {
     for (int gi = 0; gi < f.ngates; ++gi) {
         const DevGate &g = f.g[gi];
-        if (g.post >= 2 || (!g.diag && g.k == 1 && g.mk == MK1_REAL)) return true;
+        if (g.post >= 2 || g.diag == 5 || (!g.diag && g.k == 1 && g.mk == MK1_REAL)) return true;
     }
     return false;
 }
@@ -760,6 +778,10 @@ template <typename A, bool UNI, int NT, bool EXT>
 QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *stage_S, u64 base, u32 tsize, int tid) {
     if (EXT) {
         const DevGate &g = f.g[gi];
+        if (g.diag == 5) {                                      // fill mode: op 0 writes the tile (no controls, host-checked)
+            sweep_stage_fill<A, NT>(tile, stage_ref(g, f.tables, stage_S[gi], f.tb), tsize, tid);
+            return;
+        }
         if (g.post == 2) {                                      // ops gi .. gi+3 = H_a, stage a, H_b, stage b
             sweep_qft2<A, NT>(tile, g, stage_ref(f.g[gi + 1], f.tables, stage_S[gi + 1], f.tb), f.g[gi + 2],
                               stage_ref(f.g[gi + 3], f.tables, stage_S[gi + 3], f.tb), tsize >> 2, tid);
@@ -806,7 +828,10 @@ __global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fu
         for (int j = 0; j < f.tb; ++j) base = insert_zero(base, f.tbit[j]);
 
         // ---- stage the tile: runs of 2^lowrun consecutive amplitudes ----
-        if (BULK) {
+        if (EXT && f.g[0].diag == 5) {                          // fill mode: nothing is loaded, op 0 writes the tile
+            if (tid < 32) stage_scalars<32>(f, base, stage_S, tid);
+            __syncthreads();
+        } else if (BULK) {
             if (tid < 32) {
                 // no __syncwarp here: complete_tx may precede expect_tx (the phase cannot complete before
                 // lane 0 arrives), and a warp-level sync makes ptxas give up warp-uniform descriptor loads
@@ -1266,9 +1291,11 @@ int upload_tables(qipb_ctx *ctx, const std::vector<cplx> &tables, const double2 
 // Validation and lowering of one fused pass: gate list -> device descriptors, FUSED_MAX_OPS per launch.  No CUDA
 // calls in here: `prepare(tables, f)` makes the stage tables reachable through f.tables (the library uploads them,
 // tests/csrc/fused_emul.cu points at the host vector) and `launch(f)` consumes one filled FusedArgs.
+// fill: the pass acts on the all-ones vector (qipb_apply_fused_fill); the first op must then be a stage without
+// controls, executed by the EXT kernel in fill mode -- otherwise QIPB_ERR_UNSUPPORTED and nothing is launched.
 template <typename Prepare, typename Launch>
 static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates, const qipb_gate *gates,
-                       Prepare prepare, Launch launch) {
+                       Prepare prepare, Launch launch, bool fill = false) {
     QIPB_REQUIRE(gates && tile_bits, "null argument");
     QIPB_REQUIRE(nbits >= 0 && nbits <= 40, "nbits %d unsupported", nbits);
     QIPB_REQUIRE(ntile_bits >= 0 && ntile_bits <= QIPB_MAX_TILE_BITS && ntile_bits <= nbits, "tile bits %d unsupported", ntile_bits);
@@ -1328,6 +1355,13 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
             }
         }
         flush_run();
+    }
+    if (fill) {
+        const bool shape_ok = launch_is_uni(f, dtype == QIPB_C128 ? 16 : 8) && f.tb == 12 && !ring_enabled();
+        if (!shape_ok || ops.empty() || !ops[0].stage || ops[0].common != 0) {
+            set_error("fill mode needs 2^12-amplitude tiles with runs of >= 512 bytes and a leading run of un-controlled diagonal gates");
+            return QIPB_ERR_UNSUPPORTED;
+        }
     }
     {
         int rc = prepare(tables, f);
@@ -1414,6 +1448,7 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                 }
             }
         }
+        if (fill && first == 0) f.g[0].diag = 5;               // written, not multiplied (sweep_stage_fill)
         if (post_enabled())
             for (size_t oi = 0; oi + 1 < cnt; ++oi) {
                 DevGate &d = f.g[oi], &nx = f.g[oi + 1];
@@ -1479,8 +1514,8 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
 
 using namespace qipb;
 
-extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
-                                int ngates, const qipb_gate *gates) {
+static int apply_fused_impl(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
+                            int ngates, const qipb_gate *gates, bool fill) {
     QIPB_REQUIRE(ctx && state, "null argument");
     QIPB_CUDA(cudaSetDevice(ctx->device));
     return lower_fused(
@@ -1489,5 +1524,16 @@ extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype
         [&](const FusedArgs &f) {
             return dtype == QIPB_C128 ? launch_fused<double2>(ctx, (double2 *)state, f)
                                       : launch_fused<float2>(ctx, (float2 *)state, f);
-        });
+        },
+        fill);
+}
+
+extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
+                                int ngates, const qipb_gate *gates) {
+    return apply_fused_impl(ctx, state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, false);
+}
+
+extern "C" int qipb_apply_fused_fill(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
+                                     int ngates, const qipb_gate *gates) {
+    return apply_fused_impl(ctx, state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, true);
 }

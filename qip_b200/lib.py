@@ -13,12 +13,13 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libqipb200.so")
 
 C128, C64 = 0, 1
+ERR_UNSUPPORTED = 3          # a valid request this entry point cannot serve; nothing was launched (qipb_apply_fused_fill)
 MAX_DENSE_K, MAX_BIG_K, MAX_TILE_BITS, MAX_FUSED_GATES = 4, 10, 12, 280
 
 EXPORTS = [
     "qipb_version", "qipb_last_error", "qipb_create", "qipb_destroy", "qipb_set_stream", "qipb_sync",
     "qipb_launch_count", "qipb_ring_launch_count", "qipb_ext_launch_count", "qipb_dev_alloc", "qipb_dev_free", "qipb_memcpy_h2d", "qipb_memcpy_d2h",
-    "qipb_init_basis", "qipb_init_kron", "qipb_apply_matrix", "qipb_apply_swap", "qipb_apply_fused",
+    "qipb_init_basis", "qipb_init_kron", "qipb_apply_matrix", "qipb_apply_swap", "qipb_apply_fused", "qipb_apply_fused_fill",
     "qipb_func_xor", "qipb_probabilities", "qipb_collapse", "qipb_reduce", "qipb_add_range",
     "qipb_ipc_export", "qipb_ipc_open", "qipb_ipc_close", "qipb_peer_swap", "qipb_peer_swap_bit", "qipb_peer_remap", "qipb_peer_gate1",
 ]
@@ -80,6 +81,7 @@ def load():
     L.qipb_apply_matrix.argtypes = [vp, vp, ci, ci, ci, i32p, dblp, u64, ci]
     L.qipb_apply_swap.argtypes = [vp, vp, ci, ci, ci, ci, u64]
     L.qipb_apply_fused.argtypes = [vp, vp, ci, ci, ci, i32p, ci, ctypes.POINTER(Gate)]
+    L.qipb_apply_fused_fill.argtypes = [vp, vp, ci, ci, ci, i32p, ci, ctypes.POINTER(Gate)]
     L.qipb_func_xor.argtypes = [vp, vp, ci, ci, ci, i32p, ci, i32p, vp, u64]
     L.qipb_probabilities.argtypes = [vp, vp, ci, ci, ci, i32p, i32p, u64, u64, vp]
     L.qipb_collapse.argtypes = [vp, vp, ci, ci, u64, u64, ctypes.c_double]

@@ -3,6 +3,7 @@
 #   1. GPU tier (includes tests/test_zz_gpu_ext.py: the EXT kernel on the device)
 #   2. A/B on the same box: QIPB_FUSED_EXT (real 1-qubit sweeps, two QFT steps per sweep) and QIPB_PACK_1Q
 #      (lone 1-qubit gates tensored inside a pass) on both workloads at 33 qubits
+#      and QIPB_LAZY_INIT (product-state init fused into the first pass) on the e2e path
 #   3. ncu --set full of the EXT kernel inside a QFT (30 qubits) for the sweep-level numbers
 # Usage: gpurun --timeout 1500 -- 'bash scripts/round2_ab.sh r02'
 R=${1:-r02}
@@ -26,6 +27,18 @@ except Exception as e:
 PY
   done
  done
+done
+for lazy in 0 1; do
+ f=$O/${R}_ab_lazy${lazy}.json
+ QIPB_LAZY_INIT=$lazy timeout 400 python bench.py --steps 3 --warmup 3 --no-micro --no-cpu > $f 2>> $O/${R}_ab.err
+ python - <<PY
+import json
+try:
+    d = json.load(open("$f"))
+    print("lazy_init=$lazy  e2e_ms=%.1f" % d["e2e"]["ms_per_step"], d["e2e"]["breakdown_untimed_step"])
+except Exception as e:
+    print("lazy=$lazy FAILED", e)
+PY
 done
 QIPB_FUSED_EXT=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 2 -c 2 -o $O/${R}_prof_fused_ext_qft \
     python bench.py --workload qft --qubits 30 --steps 1 --warmup 1 --no-micro --no-cpu > /dev/null 2>> $O/${R}_ab.err

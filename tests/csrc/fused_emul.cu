@@ -8,6 +8,7 @@
 // separated by __syncthreads in the kernel, so sequential execution is equivalent).  What it does NOT cover is
 // what only exists on the device: TMA staging, mbarriers, the grid loop.  The CPU tier uses it to check the
 // lowering and the sweep arithmetic against the numpy bit simulator (tests/test_fused_emul.py).
+#include <math.h>
 #include <stdarg.h>
 #include "../../qip_b200/csrc/fused.cu"
 
@@ -36,7 +37,9 @@ void emulate_launch(A *state, const FusedArgs &f) {
             for (int j = 0; j < f.tb; ++j) off |= (u64)((e >> j) & 1u) << f.tbit[j];
             return off;
         };
-        for (u32 e = 0; e < tsize; ++e) tile[e] = state[base + offset_of(e)];
+        const bool fill = EXT && f.g[0].diag == 5;             // fill mode: the tile is written by op 0, nothing is loaded
+        for (u32 e = 0; e < tsize; ++e)
+            tile[e] = fill ? make_amp<A>(NAN, NAN) : state[base + offset_of(e)];
         if (f.nstages)
             for (int tid = 0; tid < NT; ++tid) stage_scalars<NT>(f, base, stage_S.data(), tid);
         for (int gi = 0; gi < f.ngates; ++gi) {
@@ -77,8 +80,8 @@ int emulate(A *state, const FusedArgs &f, int *info) {
 
 // info[0] launches, [1] of which take the specialised (UNI) sweeps, [2] stages, [3] stages riding on a dense 1-qubit
 // sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates, [7] launches of the EXT kernel
-extern "C" int qipb_emul_fused(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
-                               const qipb_gate *gates, int *info) {
+static int emul_impl(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
+                     const qipb_gate *gates, int *info, bool fill) {
     QIPB_REQUIRE(host_state && info, "null argument");
     for (int i = 0; i < 8; ++i) info[i] = 0;
     return lower_fused(
@@ -89,7 +92,19 @@ extern "C" int qipb_emul_fused(void *host_state, int nbits, int dtype, int ntile
         },
         [&](const FusedArgs &f) {
             return dtype == QIPB_C128 ? emulate<double2>((double2 *)host_state, f, info) : emulate<float2>((float2 *)host_state, f, info);
-        });
+        },
+        fill);
+}
+
+extern "C" int qipb_emul_fused(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
+                               const qipb_gate *gates, int *info) {
+    return emul_impl(host_state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, info, false);
+}
+
+// qipb_apply_fused_fill on the host: the state's previous content must not matter
+extern "C" int qipb_emul_fused_fill(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
+                                    const qipb_gate *gates, int *info) {
+    return emul_impl(host_state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, info, true);
 }
 
 extern "C" const char *qipb_emul_last_error(void) { return qipb::g_emul_err; }

@@ -31,6 +31,8 @@ def emul():
     L.qipb_emul_fused.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                   ctypes.c_int, ctypes.POINTER(qlib.Gate), ctypes.POINTER(ctypes.c_int)]
     L.qipb_emul_fused.restype = ctypes.c_int
+    L.qipb_emul_fused_fill.argtypes = L.qipb_emul_fused.argtypes
+    L.qipb_emul_fused_fill.restype = ctypes.c_int
     L.qipb_emul_last_error.restype = ctypes.c_char_p
     return L
 
@@ -243,3 +245,69 @@ def test_emulated_random_passes(emul, monkeypatch, seed):
     got, _ = run_emulated(emul, psi, [p], n, dtype)
     err = float(np.max(np.abs(got - want))) / float(np.max(np.abs(want)))
     assert err <= (1e-12 if dtype == np.complex128 else 5e-5), err
+
+
+# ---- fill mode (qipb_apply_fused_fill): product-state init + first pass in one write-only sweep ----
+def _fill_args(factors, p):
+    """What B200Backend._fill_first_pass hands to the library (the product's own packing)."""
+    from qip_b200.backend import pack_fill_pass
+    arr, tbits = pack_fill_pass(factors, p)
+    return arr, tbits, len(factors) + len(p.gates)
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("seed", range(4))
+def test_emulated_fill_mode_builds_the_product_state_inside_the_first_pass(emul, dtype, seed):
+    from qip_b200.backend import product_state_factors, split_feeds
+    n = 14
+    rng = np.random.default_rng(seed)
+    # one-qubit vector feeds, a one-hot int feed on three qubits, two un-fed qubits (|0>)
+    qubits = [int(q) for q in rng.permutation(n)]
+    hot_group, unfed, vec = qubits[:3], qubits[3:5], qubits[5:]
+    groups = [[q] for q in vec] + [hot_group]
+    feeds = [rng.normal(size=2) + 1j * rng.normal(size=2) for _ in vec] + [5]
+    vgroups, vfeeds, fmask, fval = split_feeds(groups, feeds, n, lambda q: n - 1 - q)
+    factors = product_state_factors(vgroups, vfeeds, fmask, fval, n)
+    assert factors is not None and len(factors) == n
+    psi = np.ones(1, dtype=np.complex128)
+    for b in range(n - 1, -1, -1):                         # index bit b: most significant first
+        psi = np.kron(psi, np.array(factors[b]))
+    want0 = orc_state(n, groups, feeds)
+    assert float(np.max(np.abs(psi - want0))) <= 1e-13 * float(np.max(np.abs(want0)))
+    stream = list(layered_stream(n, 1, seed)) if seed % 2 else list(qfft_stream(n))
+    gates = logical_gates(stream, n)
+    passes, _ = ops.plan(gates, n, 16 if dtype == np.complex128 else 8, strategy="tile")
+    assert passes[0].fused
+    want = bitsim.run_passes(psi.copy(), passes[:1], n)
+    st = np.full(2 ** n, np.nan + 1j * np.nan, dtype=dtype)            # the buffer's content must never be read
+    arr, tbits, ng = _fill_args(factors, passes[0])
+    info = (ctypes.c_int * 8)()
+    rc = emul.qipb_emul_fused_fill(st.ctypes.data_as(ctypes.c_void_p), n, qlib.C128 if dtype == np.complex128 else qlib.C64,
+                                   len(passes[0].tile_bits), tbits, ng, arr, info)
+    assert rc == 0, emul.qipb_emul_last_error()
+    assert info[7] >= 1
+    err = float(np.max(np.abs(st - want))) / float(np.max(np.abs(want)))
+    assert err <= (1e-12 if dtype == np.complex128 else 2e-5), err
+
+
+def orc_state(n, groups, feeds):
+    from oracle import oracle as orc
+    hot = np.zeros(2 ** 3)
+    feeds = [f if not isinstance(f, int) else np.eye(2 ** 3)[f] for f in feeds]
+    return orc.OracleBackend.make_state(n, groups, feeds).get_state()
+
+
+def test_emulated_fill_mode_refuses_what_it_cannot_serve(emul):
+    from qip_b200.backend import product_state_factors
+    # multi-qubit vector groups and device-resident feeds are not product-of-one-qubit states
+    assert product_state_factors([[0, 1]], [np.ones(4) / 2], 0b1100, 0, 4) is None
+    n = 14
+    factors = [(1 + 0j, 0j)] * n
+    # a small tile (2^10): the library answers "unsupported" (3) and launches nothing
+    g = ops.BitGate("matrix", (3,), 0, H2.astype(np.complex128), False)
+    p = ops.Pass(True, [g, g], tuple(range(10)))
+    arr, tbits, ng = _fill_args(factors, p)
+    st = np.zeros(2 ** n, dtype=np.complex128)
+    info = (ctypes.c_int * 8)()
+    rc = emul.qipb_emul_fused_fill(st.ctypes.data_as(ctypes.c_void_p), n, qlib.C128, 10, tbits, ng, arr, info)
+    assert rc == qlib.ERR_UNSUPPORTED and info[0] == 0 and not st.any()

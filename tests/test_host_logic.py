@@ -332,3 +332,94 @@ def test_pack_lone_1q_tensors_commuting_gates_only():
     q = [ops.lower(g, 10) for g in ops.merge_blocks(q, 2, cost_aware=True)]
     kept = ops.pack_lone_1q(q)
     assert [id(g) for g in kept[:35]] == [id(g) for g in q[:35]] and sum(g.k == 2 and not g.diagonal for g in kept) <= 2
+
+
+class _RecordingLib(object):
+    """Stands in for libqipb200 in host-logic tests: every entry point records its call and returns a status."""
+
+    def __init__(self, fill_status=0):
+        self.calls = []
+        self.fill_status = fill_status
+
+    def __getattr__(self, name):
+        if not name.startswith("qipb_"):
+            raise AttributeError(name)
+
+        def call(*args):
+            self.calls.append((name, args))
+            if name == "qipb_apply_fused_fill":
+                return self.fill_status
+            if name.endswith("_count"):
+                return 0
+            return 0
+        return call
+
+    def names(self):
+        return [c[0] for c in self.calls if c[0] not in ("qipb_set_stream",)]
+
+
+def _host_only_b200(n, fill_status=0, monkeypatch=None):
+    """A B200Backend whose device side is cut off (recording library, CPU tensor as the buffer): the real
+    _init_state / kronselect_dot / flush / _fill_first_pass control flow runs."""
+    import torch
+    from qip_b200 import backend as be
+    b = object.__new__(be.B200Backend)
+    b.L = _RecordingLib(fill_status)
+    b.n, b.code, b.tdtype, b.amp_bytes, b.np_dtype = n, 0, torch.complex128, 16, np.dtype(np.complex128)
+    b.device = -1                                  # torch.cuda.device(-1) is a no-op context
+    b.fuse, b.strategy, b.tile_bits, b.min_low_bits = True, "tile", 12, 7
+    b.relabel_swaps, b.pos = True, [n - 1 - q for q in range(n)]
+    b.ctx, b.state, b.queue, b.plan_cache, b.profile = None, None, [], None, None
+    b.stats = {"gates": 0, "passes": 0, "fused_passes": 0, "flushes": 0}
+    b._pending_init, b.lazy_init = None, True
+    b.host_state_max_qubits = 30
+    b._stream = lambda: None
+    monkeypatch.setattr(be, "feeds_to_device", lambda vfeeds, device: torch.zeros(4, dtype=torch.complex128))
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: torch.zeros(8, dtype=torch.complex128))
+    return b
+
+
+def test_lazy_product_state_init_rides_on_the_first_fused_pass(monkeypatch):
+    n = 14
+    groups = [[q] for q in range(n - 2)] + [[n - 2, n - 1]]
+    feeds = [np.array([0.6, 0.8j]) for _ in range(n - 2)] + [2]            # one-qubit vectors + a one-hot pair
+    stream = list(layered_stream(n, 2, 3))
+    # 1. supported: no stand-alone init, the first pass goes through qipb_apply_fused_fill with n extra gates
+    b = _host_only_b200(n, 0, monkeypatch)
+    b._init_state(groups, feeds)
+    assert b._pending_init is not None and b.L.names() == []
+    for mats in stream:
+        b.kronselect_dot(mats)
+    b.flush()
+    names = b.L.names()
+    assert names[0] == "qipb_apply_fused_fill" and "qipb_init_kron" not in names and b._pending_init is None
+    fill_args = b.L.calls[[c[0] for c in b.L.calls].index("qipb_apply_fused_fill")][1]
+    assert fill_args[2] == n and fill_args[6] > n and b.stats["fill_passes"] == 1
+    assert b.stats["passes"] == len([x for x in names if x.startswith("qipb_apply")])
+    # 2. the library cannot serve it (status 3): stand-alone init first, then every pass the ordinary way
+    b = _host_only_b200(n, 3, monkeypatch)
+    b._init_state(groups, feeds)
+    for mats in stream:
+        b.kronselect_dot(mats)
+    b.flush()
+    names = b.L.names()
+    assert names[:3] == ["qipb_apply_fused_fill", "qipb_init_kron", "qipb_apply_fused"] and b._pending_init is None
+    assert "fill_passes" not in b.stats
+    # 3. nothing queued when the state is observed: stand-alone init
+    b = _host_only_b200(n, 0, monkeypatch)
+    b._init_state(groups, feeds)
+    b.flush()
+    assert b.L.names() == ["qipb_init_kron"] and b._pending_init is None
+    # 4. an entangled (multi-qubit vector) feed is initialised at once
+    b = _host_only_b200(n, 0, monkeypatch)
+    b._init_state([[0, 1]] + [[q] for q in range(2, n)], [np.ones(4) / 2] + [np.array([1.0, 0.0])] * (n - 2))
+    assert b._pending_init is None and b.L.names() == ["qipb_init_kron"]
+    # 5. any other library error in fill mode is raised, not swallowed
+    from qip_b200 import lib as qlib
+    b = _host_only_b200(n, 1, monkeypatch)
+    monkeypatch.setattr(qlib, "check", lambda rc: (_ for _ in ()).throw(qlib.QipbError("boom")) if rc else None)
+    b._init_state(groups, feeds)
+    for mats in stream:
+        b.kronselect_dot(mats)
+    with pytest.raises(qlib.QipbError):
+        b.flush()

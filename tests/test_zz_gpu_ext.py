@@ -55,3 +55,37 @@ def test_ext_real_gates_and_unpaired_steps_match_oracle(monkeypatch, statetype, 
     assert g.ext_launch_count() >= 1
     assert float(np.max(np.abs(a - b))) / float(np.max(np.abs(b))) <= tol
     g.close()
+
+
+@pytest.mark.parametrize("statetype,tol", [(np.complex128, 1e-12), (np.complex64, 1e-5)])
+@pytest.mark.parametrize("workload", ["layered", "qft"])
+def test_lazy_product_state_init_is_fused_into_the_first_pass(monkeypatch, statetype, tol, workload):
+    # QIPB_LAZY_INIT=1: a product of one-qubit feeds (+ one-hot and un-fed qubits) is never written by an init kernel;
+    # the first fused pass builds its tiles from the per-bit factors (qipb_apply_fused_fill)
+    from qip_b200 import B200Backend
+    monkeypatch.setenv("QIPB_LAZY_INIT", "1")
+    n = 16
+    rng = np.random.default_rng(9)
+    qubits = [int(q) for q in rng.permutation(n)]
+    hot_group, vec = qubits[:3], qubits[5:]                    # qubits[3:5] stay un-fed
+    groups = [[q] for q in vec] + [hot_group]
+    vfeeds = []
+    for _ in vec:
+        v = rng.normal(size=2) + 1j * rng.normal(size=2)
+        vfeeds.append(v / np.linalg.norm(v))
+    stream = list(layered_stream(n, 2, 5)) if workload == "layered" else list(qfft_stream(n))
+    g = B200Backend.make_state(n, groups, vfeeds + [5], statetype=statetype, strategy="tile")
+    c = orc.OracleBackend.make_state(n, groups, vfeeds + [np.eye(8)[5]])
+    for mats in stream:
+        g.kronselect_dot(mats)
+        c.kronselect_dot(mats)
+    a, b = np.asarray(g.get_state()), c.get_state()
+    assert g.stats.get("fill_passes", 0) == 1 and g.ext_launch_count() >= 1
+    assert float(np.max(np.abs(a - b))) / float(np.max(np.abs(b))) <= tol
+    g.close()
+    # observed before any gate: the stand-alone init kernel builds it
+    g = B200Backend.make_state(n, groups, vfeeds + [5], statetype=statetype)
+    c = orc.OracleBackend.make_state(n, groups, vfeeds + [np.eye(8)[5]])
+    assert float(np.max(np.abs(np.asarray(g.get_state()) - c.get_state()))) <= tol
+    assert "fill_passes" not in g.stats
+    g.close()
