@@ -312,7 +312,8 @@ class B200Backend(object):
             r0 = self.stats.get("relabels", 0)
             gates = self._relabel(self.queue)
             self.queue = []
-            if not gates:
+            if not gates:                              # only relabelled swaps were queued
+                self._materialise_init()
                 return
             passes, chosen = plan(gates, self.n, self.amp_bytes, fuse=self.fuse, tile_bits=self.tile_bits,
                                   min_low_bits=self.min_low_bits, strategy=self.strategy)

@@ -1,0 +1,122 @@
+"""CPU tier: the real qip_b200.backend.B200Backend driven end to end on the host.
+
+tests/hostlib.py swaps libqipb200 for a host double (fused passes -> the emulator built from the product's own
+fused.cu; every other entry point restated in numpy from include/qip_b200.h) and torch.cuda for no-ops, so the
+backend's own logic -- eager validation, lazy queue, swap relabelling + canonicalisation, planning, both measurement
+bit orders, sampling scan, func_apply bit maps, range access, reduce_measure, the lazy product-state init -- replays
+the golden op streams recorded from the unmodified reference without a GPU.  The GPU tier runs the same streams on
+the device (tests/test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+import hostlib
+import replay
+from qip_b200.circuits import layered_stream, qfft_stream
+
+META, STREAMS, ARRAYS = replay.load_streams()
+NO_SAMPLING = [i for i, s in enumerate(STREAMS)
+               if not any(op["op"] in ("measure", "soft_measure", "reduce_measure") for op in s["ops"])]
+
+
+def _make(**kw):
+    from qip_b200 import B200Backend
+
+    def make(n, groups, feeds, statetype=np.complex128):
+        return B200Backend.make_state(n, groups, feeds, statetype=statetype, **kw)
+    return make
+
+
+@pytest.mark.parametrize("i", range(len(STREAMS)), ids=[s["label"] for s in STREAMS])
+def test_backend_replays_golden_stream_on_host(monkeypatch, i):
+    hostlib.install(monkeypatch)
+    assert replay.replay(STREAMS[i], ARRAYS, _make(), tol=1e-12)
+
+
+@pytest.mark.parametrize("i", range(0, len(STREAMS), 3), ids=[STREAMS[i]["label"] for i in range(0, len(STREAMS), 3)])
+def test_backend_replays_golden_stream_on_host_unfused_and_lazy_init(monkeypatch, i):
+    hostlib.install(monkeypatch)
+    assert replay.replay(STREAMS[i], ARRAYS, _make(fuse=False), tol=1e-12)
+    assert replay.replay(STREAMS[i], ARRAYS, _make(lazy_init=True), tol=1e-12)
+
+
+@pytest.mark.parametrize("i", NO_SAMPLING[::4], ids=[STREAMS[i]["label"] for i in NO_SAMPLING[::4]])
+def test_backend_replays_golden_stream_on_host_complex64(monkeypatch, i):
+    hostlib.install(monkeypatch)
+    assert replay.replay(STREAMS[i], ARRAYS, _make(), tol=1e-5, statetype=np.complex64)
+
+
+@pytest.mark.parametrize("workload", ["layered", "qft"])
+def test_backend_lazy_init_takes_the_fill_path_at_production_tile_size(monkeypatch, workload):
+    # 14 qubits: 2^12-amplitude tiles with 2 KiB runs -> the library serves qipb_apply_fused_fill; the result equals
+    # the eagerly initialised run and no stand-alone init kernel is launched
+    from oracle import oracle as orc
+    L = hostlib.install(monkeypatch)
+    n = 14
+    rng = np.random.default_rng(2)
+    groups = [[q] for q in range(n - 3)] + [[n - 2, n - 3]]          # qubit n-1 stays un-fed
+    feeds = []
+    for _ in range(n - 3):
+        v = rng.normal(size=2) + 1j * rng.normal(size=2)
+        feeds.append(v / np.linalg.norm(v))
+    stream = list(layered_stream(n, 2, 1)) if workload == "layered" else list(qfft_stream(n))
+    b = _make(lazy_init=True, strategy="tile")(n, groups, feeds + [2])
+    c = orc.OracleBackend.make_state(n, groups, feeds + [np.eye(4)[2]])
+    for mats in stream:
+        b.kronselect_dot(mats)
+        c.kronselect_dot(mats)
+    got = np.asarray(b.get_state())
+    assert b.stats.get("fill_passes") == 1 and "apply_fused_fill" in L.log and "init_kron" not in L.log
+    assert float(np.max(np.abs(got - c.get_state()))) <= 1e-12
+    probs = b.measure_probabilities(np.array([3, 0, 9], dtype=np.int32))
+    assert np.allclose(probs, c.measure_probabilities([3, 0, 9]), rtol=0, atol=1e-13)
+    b.close()
+
+
+def test_compiled_circuit_replays_through_the_real_backend_with_cached_plans(monkeypatch):
+    # qip_b200.graph.CompiledCircuit -> B200Backend.apply_gates (plan cache) / func_apply / measure / measure_probabilities,
+    # three replays with different feed values; every replay equals the oracle run of the same ops
+    import random
+    from oracle import oracle as orc
+    from qip_b200 import B200Backend
+    from qip_b200.graph import CompiledCircuit
+    from qip_b200.mats import SwapMat
+    hostlib.install(monkeypatch)
+    n = 13
+    groups = [[q] for q in range(n)]
+    f = lambda x: (5 * x + 3) % 8
+    seg1 = list(layered_stream(n, 2, 4)) + [{(0, n - 1): SwapMat(1)}]
+    seg2 = list(qfft_stream(6, first_qubit=2))
+    ops_c = ([("k", m) for m in seg1] + [("f", [0, 1, 2], [7, 9, 11], f)] + [("k", m) for m in seg2] +
+             [("p", [4, 0, 12]), ("m", [1, 6])] + [("k", m) for m in layered_stream(n, 1, 6)])
+    rng = np.random.default_rng(0)
+
+    def feeds():
+        out = []
+        for _ in range(n):
+            v = rng.normal(size=2) + 1j * rng.normal(size=2)
+            out.append(v / np.linalg.norm(v))
+        return out
+    first = feeds()
+    circ = CompiledCircuit.from_ops(n, groups, first, ops_c)
+    for replay_no, lazy in enumerate((False, True, True)):
+        fl = first if replay_no == 0 else feeds()
+        c = orc.OracleBackend.make_state(n, groups, fl)
+        for m in seg1:
+            c.kronselect_dot(m)
+        c.func_apply([0, 1, 2], [7, 9, 11], f)
+        for m in seg2:
+            c.kronselect_dot(m)
+        want_p = c.measure_probabilities([4, 0, 12])
+        random.seed(7)
+        want_m = c.measure([1, 6])
+        for m in layered_stream(n, 1, 6):
+            c.kronselect_dot(m)
+        random.seed(7)
+        state, classic = circ.run(feed={(q,): v for q, v in enumerate(fl)}, lazy_init=lazy)
+        ip, im = len(seg1) + 1 + len(seg2), len(seg1) + 2 + len(seg2)
+        assert np.allclose(classic[ip], want_p, rtol=0, atol=1e-13)
+        assert classic[im][0] == want_m[0] and abs(classic[im][1] - want_m[1]) <= 1e-13
+        assert float(np.max(np.abs(np.asarray(state) - c.get_state()))) <= 1e-12
+        if lazy:
+            assert circ.last_stats.get("fill_passes") == 1
+    assert len(circ._plans) == 3                      # one cached plan per gate segment, shared by all replays
