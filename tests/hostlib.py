@@ -287,3 +287,231 @@ def install(monkeypatch):
     monkeypatch.setattr(be, "_torch", lambda: fake)
     monkeypatch.setattr(be, "_CTX_POOL", {}, raising=False)
     return L
+
+
+# ======================================================================================================
+# Multi-"GPU" double: P virtual ranks = P threads of ONE process running the real ShardedB200Backend (SPMD).
+# Shards are host buffers; "peer memory" is simply the other thread's buffer (same address space), so the
+# qipb_peer_* kernels are restated in numpy on both buffers; torch.distributed's collectives are thread
+# rendezvous.  The product brackets every peer kernel with a barrier (ShardedB200Backend._sync_all), which is
+# what makes the concurrent halves of a pair race-free here exactly as on the device.
+import threading  # noqa: E402
+
+
+def _insert_zero(v, p):
+    lo = v & ((1 << p) - 1)
+    return ((v >> p) << (p + 1)) | lo
+
+
+class _PeerMixin(object):
+    _bufs = {}
+
+    def qipb_dev_alloc(self, ctx, nbytes, out):
+        buf = np.zeros(int(nbytes), dtype=np.uint8)
+        addr = buf.ctypes.data
+        _PeerMixin._bufs[addr] = buf
+        out._obj.value = addr
+        return 0
+
+    def qipb_dev_free(self, ctx, ptr):
+        _PeerMixin._bufs.pop(_addr(ptr), None)
+        return 0
+
+    def qipb_ipc_export(self, ctx, ptr, handle_out):
+        raw = int(_addr(ptr)).to_bytes(8, "little") + bytes(56)
+        ctypes.memmove(handle_out, raw, 64)
+        return 0
+
+    def qipb_ipc_open(self, ctx, handle, out):
+        out._obj.value = int.from_bytes(bytes(handle)[:8], "little")
+        return 0
+
+    def qipb_ipc_close(self, ctx, ptr):
+        return 0
+
+    def qipb_peer_swap(self, ctx, local, peer, code, local_off, peer_off, count):
+        dt = np.complex128 if code == qlib.C128 else np.complex64
+        it = np.dtype(dt).itemsize
+        a = _view(_addr(local) + int(local_off) * it, int(count), dt)
+        b = _view(_addr(peer) + int(peer_off) * it, int(count), dt)
+        tmp = a.copy()
+        a[:] = b
+        b[:] = tmp
+        return 0
+
+    def qipb_peer_swap_bit(self, ctx, local, peer, nbits, code, lbit, my_g, w_begin, count):
+        self.log.append("peer_swap_bit")
+        a, b = _amps(local, nbits, code), _amps(peer, nbits, code)
+        w = np.arange(int(w_begin), int(w_begin) + int(count), dtype=np.int64)
+        base = _insert_zero(w, lbit)
+        li = base | ((1 - my_g) << lbit)
+        pi = base | (my_g << lbit)
+        tmp = a[li].copy()
+        a[li] = b[pi]
+        b[pi] = tmp
+        return 0
+
+    def qipb_peer_remap(self, ctx, local, peers, nbits, code, g, lbits, my_value):
+        self.log.append("peer_remap")
+        a = _amps(local, nbits, code)
+        lb = _ints(lbits, g)
+        half = 1 << (nbits - g - 1)
+        for slot in range((1 << g) - 1):
+            bval = my_value ^ (slot + 1)
+            peer = _amps(peers[bval], nbits, code)
+            lsel = sum(((bval >> t) & 1) << lb[t] for t in range(g))
+            psel = sum(((my_value >> t) & 1) << lb[t] for t in range(g))
+            base = np.arange(half, dtype=np.int64) + (0 if my_value < bval else half)
+            for p in sorted(lb):
+                base = _insert_zero(base, p)
+            tmp = a[base | lsel].copy()
+            a[base | lsel] = peer[base | psel]
+            peer[base | psel] = tmp
+        return 0
+
+    def qipb_peer_gate1(self, ctx, local, peer, code, off, count, mat, local_is_hi, ctrl_mask):
+        self.log.append("peer_gate1")
+        dt = np.complex128 if code == qlib.C128 else np.complex64
+        it = np.dtype(dt).itemsize
+        idx = np.arange(int(off), int(off) + int(count), dtype=np.int64)
+        on = (idx & int(ctrl_mask)) == int(ctrl_mask)
+        l = _view(_addr(local) + int(off) * it, int(count), dt)
+        p = _view(_addr(peer) + int(off) * it, int(count), dt)
+        m = [complex(mat[2 * e], mat[2 * e + 1]) for e in range(4)]
+        lo, hi = (p, l) if local_is_hi else (l, p)
+        r0 = m[0] * lo + m[1] * hi
+        r1 = m[2] * lo + m[3] * hi
+        lo[on], hi[on] = r0[on].astype(dt), r1[on].astype(dt)
+        return 0
+
+
+class ShardedHostLib(_PeerMixin, HostLib):
+    pass
+
+
+class ThreadDist(object):
+    """torch.distributed for P threads of one process (the subset ShardedB200Backend uses)."""
+
+    def __init__(self, P):
+        self.P = P
+        self.bar = threading.Barrier(P, timeout=120)
+        self.local = threading.local()
+        self.slots = [None] * P
+
+    def is_initialized(self):
+        return True
+
+    def get_rank(self):
+        return self.local.rank
+
+    def get_world_size(self):
+        return self.P
+
+    def barrier(self):
+        self.bar.wait()
+
+    def _exchange(self, obj):
+        self.slots[self.local.rank] = obj
+        self.bar.wait()
+        got = list(self.slots)
+        self.bar.wait()
+        return got
+
+    def all_gather_object(self, out, obj):
+        import pickle
+        out[:] = [pickle.loads(b) for b in self._exchange(pickle.dumps(obj))]     # objects travel by value, as over the wire
+
+    def all_reduce(self, t, op=None):
+        got = self._exchange(t.clone())
+        total = got[0].clone()
+        for x in got[1:]:
+            total += x
+        t.copy_(total)
+
+    def broadcast(self, t, src):
+        got = self._exchange(t.clone())
+        t.copy_(got[src])
+
+    def all_gather(self, parts, t):
+        got = self._exchange(t.clone())
+        for dst, src in zip(parts, got):
+            dst.copy_(src)
+
+
+class _PerThreadDict(object):
+    """The module-level shard pool of qip_b200.sharded is per PROCESS; virtual ranks are threads, so every thread
+    gets its own."""
+
+    def __init__(self):
+        self.local = threading.local()
+
+    def _d(self):
+        if not hasattr(self.local, "d"):
+            self.local.d = {}
+        return self.local.d
+
+    def pop(self, *a):
+        return self._d().pop(*a)
+
+    def keys(self):
+        return self._d().keys()
+
+    def __setitem__(self, k, v):
+        self._d()[k] = v
+
+    def __contains__(self, k):
+        return k in self._d()
+
+    def __bool__(self):
+        return bool(self._d())
+
+    def __len__(self):
+        return len(self._d())
+
+
+def run_virtual_ranks(monkeypatch, P, body):
+    """Run body(rank) on P virtual ranks with the real ShardedB200Backend available; re-raises the first failure."""
+    import torch
+    import torch.distributed as tdist
+    from qip_b200 import backend as be
+    from qip_b200 import sharded as sh
+    L = ShardedHostLib()
+    monkeypatch.setattr(qlib, "load", lambda: L)
+    monkeypatch.setattr(qlib, "check", lambda rc: (_ for _ in ()).throw(qlib.QipbError("libqipb200: " + L.err.decode())) if rc else None)
+    fake = _FakeTorch(torch)
+    monkeypatch.setattr(be, "_torch", lambda: fake)
+    monkeypatch.setattr(sh, "_torch", lambda: fake)
+    monkeypatch.setattr(be, "_CTX_POOL", {}, raising=False)
+    monkeypatch.setattr(sh, "_SHARD_POOL", _PerThreadDict())
+    td = ThreadDist(P)
+    for name in ("is_initialized", "get_rank", "get_world_size", "barrier", "all_gather_object", "all_reduce",
+                 "broadcast", "all_gather"):
+        monkeypatch.setattr(tdist, name, getattr(td, name))
+
+    def wrap_shard(self, ptr):
+        self.ptr = ptr
+        dt = np.complex128 if self.amp_bytes == 16 else np.complex64
+        self.eng.state = torch.from_numpy(_view(ptr, 1 << self.nl, dt))
+        assert self.eng.state.data_ptr() == ptr.value
+    monkeypatch.setattr(sh.ShardedB200Backend, "_wrap_shard", wrap_shard)
+
+    errors = [None] * P
+
+    def runner(rank):
+        td.local.rank = rank
+        try:
+            body(rank)
+        except BaseException as e:                 # noqa: BLE001 -- reported to the test below
+            errors[rank] = e
+            td.bar.abort()
+    threads = [threading.Thread(target=runner, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    real = [e for e in errors if e is not None and not isinstance(e, threading.BrokenBarrierError)]
+    if real:
+        raise real[0]
+    if any(errors):
+        raise [e for e in errors if e is not None][0]
+    return L

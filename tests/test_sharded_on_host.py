@@ -1,0 +1,120 @@
+"""CPU tier: the real qip_b200.sharded.ShardedB200Backend on P = 2, 4, 8 VIRTUAL ranks (threads of one process).
+
+tests/hostlib.py supplies the doubles: host buffers as shards, the other thread's buffer as peer memory (the
+qipb_peer_* kernels restated in numpy), thread rendezvous for torch.distributed, the fused-pass emulator for the
+rank-local passes.  What runs is the product's own multi-GPU host code -- lazy layout choice, kron init per shard,
+the scheduler (defer_global, exchanges, multi-bit remaps, peer gates), rank-local merging / planning / launching,
+measurement across shards, func_apply, range access, canonicalisation, shard pooling, the compiled-circuit program
+cache -- against the CPU oracle.  The multi-GPU box runs the same scenario over NVLink (tests/dist_gpu_worker.py)."""
+import random
+
+import numpy as np
+import pytest
+
+import hostlib
+from oracle import oracle as orc
+from qip_b200.circuits import H2, X2, haar_unitary, layered_stream, qfft_stream, rm_mat
+from qip_b200.mats import CMat, SwapMat
+
+
+def _check(name, got, want, tol=1e-12):
+    err = float(np.max(np.abs(np.asarray(got) - np.asarray(want)))) / max(1e-300, float(np.max(np.abs(want))))
+    assert err <= tol, (name, err)
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_sharded_backend_matches_oracle_on_virtual_ranks(monkeypatch, P):
+    from qip_b200.sharded import ShardedB200Backend
+    n = 11
+    rng = np.random.default_rng(5)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    groups, feeds = [list(range(n))], [psi]
+    rngu = np.random.default_rng(6)
+    extra = [{(0, 5): CMat(X2)}, {(1, 0, 6): CMat(CMat(haar_unitary(rngu, 2)))}, {0: rm_mat(3)},
+             {(1, 0): CMat(rm_mat(2))}, {(0, 7): SwapMat(1)}, {(0, 1): haar_unitary(rngu, 4)},
+             {(10, 0, 3): CMat(SwapMat(1))}, {0: H2}, {(2, 9, 0): haar_unitary(rngu, 8)}]
+    cases = {"layered": list(layered_stream(n, 3, 2)), "qfft": list(qfft_stream(n)), "mixed": extra}
+
+    def body(rank):
+        for name, ops_ in cases.items():
+            for fuse, peer in ((True, False), (False, False), (True, True)):
+                g = ShardedB200Backend.make_state(n, groups, feeds, statetype=np.complex128, fuse=fuse, peer_gates=peer,
+                                                  tile_bits=5, min_low_bits=2)
+                c = orc.OracleBackend.make_state(n, groups, feeds)
+                for mats in ops_:
+                    g.kronselect_dot(mats)
+                    c.kronselect_dot(mats)
+                for idx in ([0], [n - 1, 0], [3, 1, 7], list(range(n))):
+                    _check(name + " probs", g.measure_probabilities(np.array(idx, dtype=np.int32)), c.measure_probabilities(idx), 1e-13)
+                ia, pa = g.measure_probabilities(np.array([0, 4, 9], dtype=np.int32), top_k=3)
+                ib, pb = c.measure_probabilities([0, 4, 9], top_k=3)
+                assert ia == ib
+                assert abs(g.total_prob() - 1.0) < 1e-12
+                _check(name + " state", g.get_state(), c.get_state())
+                random.seed(3)
+                mg, pg = g.measure(np.array([0, 6], dtype=np.int32))
+                random.seed(3)
+                mc, pc = c.measure([0, 6])
+                assert mg == mc and abs(pg - pc) < 1e-13
+                _check(name + " collapsed", g.get_state(), c.get_state())
+                f = lambda x: (3 * x + 1) % 4
+                g.func_apply([0, 5, 2], [1, 8], f)
+                c.func_apply([0, 5, 2], [1, 8], f)
+                _check(name + " func", g.get_state(), c.get_state())
+                _check(name + " range", g.get_relative_range(100, 1300), c.get_relative_range(100, 1300))
+                g.addto_relative_range(1016, 1032, np.arange(16) * (0.5 + 0.25j))
+                c.addto_relative_range(1016, 1032, np.arange(16) * (0.5 + 0.25j))
+                g.overwrite_relative_range(5, 9, np.array([1, 2, 3, 4], dtype=np.complex128))
+                c.overwrite_relative_range(5, 9, np.array([1, 2, 3, 4], dtype=np.complex128))
+                _check(name + " range writes", g.get_state(), c.get_state())
+                random.seed(4)
+                mg, pg = g.reduce_measure(np.array([0, 7, 3], dtype=np.int32))
+                random.seed(4)
+                mc, pc = c.reduce_measure([0, 7, 3])
+                assert mg == mc and abs(pg - pc) < 1e-12 * max(1.0, pc) and g.n == c.n == n - 3
+                _check(name + " reduced", g.get_state(), c.get_state())
+                g.close()
+        # kron-product init per shard, one-hot feeds, empty feed
+        g = ShardedB200Backend.make_state(n, [[3, 0, 9], [1, 2], [10, 8, 4, 5]], [6, np.array([0.5, 0.5j, -0.5, 0.5]), 9])
+        c = orc.OracleBackend.make_state(n, [[3, 0, 9], [1, 2], [10, 8, 4, 5]], [np.eye(8)[6], np.array([0.5, 0.5j, -0.5, 0.5]), np.eye(16)[9]])
+        _check("one-hot feeds", g.get_state(), c.get_state(), 1e-15)
+        g.close()
+        g = ShardedB200Backend.make_state(n, [], [])
+        want = np.zeros(2 ** n)
+        want[0] = 1
+        assert np.array_equal(g.get_state(), want)
+        g.close()
+
+    hostlib.run_virtual_ranks(monkeypatch, P, body)
+
+
+@pytest.mark.parametrize("P", [2, 8])
+def test_compiled_circuit_replays_on_virtual_ranks_with_cached_programs(monkeypatch, P):
+    from qip_b200.graph import CompiledCircuit
+    from qip_b200.sharded import ShardedB200Backend
+    n = 11
+    rng = np.random.default_rng(1)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    groups, feeds = [list(range(n))], [psi]
+    seg = list(layered_stream(n, 2, 4)) + list(qfft_stream(n))
+    tail = list(layered_stream(n, 1, 8))
+    ops_c = [("k", m) for m in seg] + [("p", [0, n - 1, 5])] + [("k", m) for m in tail]
+    c = orc.OracleBackend.make_state(n, groups, feeds)
+    for m in seg:
+        c.kronselect_dot(m)
+    want_p = c.measure_probabilities([0, n - 1, 5])
+    for m in tail:
+        c.kronselect_dot(m)
+    want_state = c.get_state()
+
+    def body(rank):
+        circ = CompiledCircuit.from_ops(n, groups, feeds, ops_c)          # one compiled circuit (and cache) per rank/process
+        for replay_no in range(3):
+            state, classic = circ.run(backend_constructor=ShardedB200Backend.make_state, tile_bits=5, min_low_bits=2)
+            _check("compiled state", state, want_state)
+            _check("compiled probs", classic[len(seg)], want_p, 1e-13)
+            assert circ.last_stats.get("cached_flushes", 0) == (0 if replay_no == 0 else 2), circ.last_stats
+
+    hostlib.run_virtual_ranks(monkeypatch, P, body)
