@@ -118,3 +118,37 @@ def test_compiled_circuit_replays_on_virtual_ranks_with_cached_programs(monkeypa
             assert circ.last_stats.get("cached_flushes", 0) == (0 if replay_no == 0 else 2), circ.last_stats
 
     hostlib.run_virtual_ranks(monkeypatch, P, body)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_sharded_backend_at_production_tile_size_on_virtual_ranks(monkeypatch, P):
+    # shards of 2^13 amplitudes, default tile shape (2^12-amplitude tiles, 2 KiB runs): the rank-local passes take the
+    # specialised sweeps of the fused kernel (through the emulator); QFFT against its closed form sqrt(N) * ifft
+    from qip_b200.sharded import ShardedB200Backend
+    n = 13 + int(np.log2(P))
+    rng = np.random.default_rng(n)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    want_qft = np.fft.ifft(psi) * np.sqrt(2 ** n)
+    c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+    layer = list(layered_stream(n, 2, 3))
+    for m in layer:
+        c.kronselect_dot(m)
+    want_layered = c.get_state()
+
+    def body(rank):
+        g = ShardedB200Backend.make_state(n, [list(range(n))], [psi])
+        for m in qfft_stream(n):
+            g.kronselect_dot(m)
+        _check("qfft", g.get_state(), want_qft)
+        assert g.stats["exchanges"] >= 1
+        g.close()
+        g = ShardedB200Backend.make_state(n, [list(range(n))], [psi])
+        for m in layer:
+            g.kronselect_dot(m)
+        g.flush()
+        _check("layered", g.get_state(), want_layered)
+        g.close()
+
+    L = hostlib.run_virtual_ranks(monkeypatch, P, body)
+    assert "apply_fused" in L.log and ("peer_remap" in L.log or "peer_swap_bit" in L.log)
