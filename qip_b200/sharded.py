@@ -372,7 +372,9 @@ class ShardedB200Backend(object):
                 self.stats["cached_flushes"] = self.stats.get("cached_flushes", 0) + 1
                 self._run_program(program)
                 return
-        program = self._compile_and_run(sp.schedule(gates, self.layout, peer_gates=self.peer_gates))
+        program = self._compile_and_run(sp.schedule(gates, self.layout, peer_gates=self.peer_gates,
+                                                    count_passes=lambda batch: len(self._plan_local(batch)),
+                                                    tile_bits=self.eng.tile_bits, min_low_bits=self.eng.min_low_bits))
         if ckey is not None:
             cache[ckey] = (program, tuple(self.layout.pos))
 

@@ -167,8 +167,13 @@ def defer_global(gates: Sequence[Gate], lay: Layout) -> List[Gate]:
     matching of 2-qubit gates) then needs ONE multi-bit exchange instead of one per first use: all local
     work first, one remap that brings every rank-bit qubit in (the victims are finished for this flush),
     then the postponed tail.  Relabelling swaps are tracked on a copy of the layout; `lay` is not changed."""
+    return [g for part in split_global(gates, lay) for g in part]
+
+
+def split_global(gates: Sequence[Gate], lay: Layout) -> Tuple[List[Gate], List[Gate]]:
+    """(purely local gates, postponed gates) of defer_global, each in its original relative order."""
     if lay.G == 0 or len(gates) < 2:
-        return list(gates)
+        return list(gates), []
     sim = lay.copy()
     now: List[Gate] = []
     later: List[Gate] = []
@@ -189,17 +194,113 @@ def defer_global(gates: Sequence[Gate], lay: Layout) -> List[Gate]:
         if relabel:
             sim.swap_qubits(g.targets[0], g.targets[1])
         now.append(g)
-    return now + later
+    return now, later
 
 
-def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates: bool = False) -> List[object]:
+def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates: bool = False,
+             count_passes=None, tile_bits: int = 12, min_low_bits: int = 7) -> List[object]:
     """Turn logical gates into rank-independent actions; `lay` is updated in place.
     peer_gates: run a dense 1-qubit gate on a rank bit as one fused compute+exchange kernel when its
     qubit is never needed locally afterwards.  Off by default: the fused kernel moves one shard per
-    direction, an Exchange followed by a local gate only half a shard (measured on B200)."""
+    direction, an Exchange followed by a local gate only half a shard (measured on B200).
+    count_passes(list[BitGate]) -> int: the executor's real pass planner, used to confirm a hoisted exchange
+    (see choose_prefetch) before it replaces the base schedule; without it only the estimate decides."""
+    now, later = split_global(gates, lay)
+    base = now + later
+    at = choose_prefetch(base, len(now), lay, top_window, peer_gates, count_passes, tile_bits, min_low_bits)
+    return _schedule_ordered(base, lay, top_window, peer_gates, prefetch_at=at)
+
+
+# Cost of moving g rank bits in one remap, in units of one fused pass over a shard (measured on B200 at 33 local
+# qubits: a pass 60-80 ms, a 1-bit exchange ~100 ms, a 3-bit remap 155 ms; profiles/r01_bench_*_n8.json).
+def _move_cost(g: int) -> float:
+    return 2.6 * (1.0 - 2.0 ** (-g))
+
+
+def _estimate(actions: Sequence[object], nl: int, tile_bits: int = 12, min_low_bits: int = 7) -> float:
+    """Cheap, rank-independent estimate of a schedule: fused passes (the bit-set grouping of ops.plan_passes on the
+    non-diagonal target positions, no matrices touched) plus the moves."""
+    cost = 0.0
+    tb = min(tile_bits, nl)
+    low = set(range(min(min_low_bits, tb)))
+    need: set = set()
+    open_pass = False
+    for a in actions:
+        if isinstance(a, Apply):
+            bits = set() if a.gate.diagonal or len(a.gate.bits) == 0 else {b for b in a.gate.bits if b < nl}
+        elif isinstance(a, LocalSwap):
+            bits = {a.a, a.b}
+        else:
+            cost += 1.0 if open_pass else 0.0
+            open_pass, need = False, set()
+            cost += _move_cost(len(a.pairs)) if isinstance(a, MultiExchange) else _move_cost(1)
+            continue
+        if len(bits) > 2:                                      # wide gates run stand-alone: one sweep each
+            cost += (1.0 if open_pass else 0.0) + 1.0
+            open_pass, need = False, set()
+            continue
+        nn = need | bits
+        if open_pass and len(nn | low) > tb:
+            cost += 1.0
+            nn = set(bits)
+        need, open_pass = nn, True
+    return cost + (1.0 if open_pass else 0.0)
+
+
+def _real_cost(actions: Sequence[object], nl: int, rank: int, count_passes) -> float:
+    cost = 0.0
+    for step in compile_program(actions, nl, rank, lambda batch: [None] * count_passes(batch)):
+        if isinstance(step, tuple):
+            cost += len(step[1])
+        else:
+            cost += _move_cost(len(step.pairs)) if isinstance(step, MultiExchange) else _move_cost(1)
+    return cost
+
+
+def choose_prefetch(base: Sequence[Gate], n_now: int, lay: Layout, top_window: int = 8, peer_gates: bool = False,
+                    count_passes=None, tile_bits: int = 12, min_low_bits: int = 7) -> Optional[int]:
+    """Where (index into `base` = local gates + postponed tail of defer_global) the ONE multi-bit exchange of a flush
+    should run, or None for "right before the first gate that needs it" (the base schedule).
+
+    Hoisting: the exchange may run earlier, after a prefix of the local gates, when the qubits it evicts are finished
+    by then; the postponed gates then share passes with the rest of the local work instead of needing passes of their
+    own (QFT over 2^G shards: 6 passes + one remap instead of 6 + remap + 1).  Candidate cut points are scheduled on a
+    copy of the layout and ranked with a cheap pass-count estimate; the best one replaces the base schedule only if it
+    is strictly cheaper -- and, when the executor's planner is available, only if the real pass counts confirm it."""
+    if lay.G == 0 or n_now == 0 or n_now == len(base) or peer_gates:
+        return None
+    import os
+    if os.environ.get("QIPB_SHARD_HOIST", "1") == "0":        # tuning knob for profiling runs
+        return None
+    nl = lay.nl
+    base_actions = _schedule_ordered(base, lay.copy(), top_window, peer_gates)
+    best_cost, best = _estimate(base_actions, nl, tile_bits, min_low_bits), None
+    ncand = 8
+    for cut in sorted({(n_now * k) // ncand for k in range(ncand)}):
+        try:
+            acts = _schedule_ordered(base, lay.copy(), top_window, peer_gates, prefetch_at=cut)
+        except ValueError:
+            continue
+        c = _estimate(acts, nl, tile_bits, min_low_bits)
+        if c < best_cost - 1e-9:
+            best_cost, best = c, cut
+    base_cost = _estimate(base_actions, nl, tile_bits, min_low_bits)
+    if best is None or count_passes is None or base_cost - best_cost >= 1.0 - 1e-9:
+        return best                                            # a whole pass saved: clear enough without re-planning
+    rank = (1 << lay.G) - 1                                   # every control on a rank bit satisfied: no gate drops out
+    hoisted = _schedule_ordered(base, lay.copy(), top_window, peer_gates, prefetch_at=best)
+    if _real_cost(hoisted, nl, rank, count_passes) < _real_cost(base_actions, nl, rank, count_passes) - 1e-9:
+        return best
+    return None
+
+
+def _schedule_ordered(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates: bool = False,
+                      prefetch_at: Optional[int] = None) -> List[object]:
+    """The scheduling loop proper on a fixed gate order; `lay` is updated in place.  prefetch_at: index of the gate in
+    front of which every rank-bit qubit with a later non-diagonal use is brought in (victims: qubits of the top local
+    window that are not needed again, Belady-style like any other exchange)."""
     nl = lay.nl
     actions: List[object] = []
-    gates = defer_global(gates, lay)
 
     def nondiag_targets(g: Gate):
         if g.kind == "swap":
@@ -215,6 +316,19 @@ def schedule(gates: Sequence[Gate], lay: Layout, top_window: int = 8, peer_gates
         return 1 << 30
 
     for i, g in enumerate(gates):
+        if prefetch_at is not None and i == prefetch_at and lay.G > 0:
+            wanted = sorted((q for q in range(lay.n) if lay.is_global(q) and next_use(q, i) < (1 << 30)),
+                            key=lambda q: next_use(q, i))
+            window = [lay.qubit_at(p) for p in range(nl - 1, max(-1, nl - 1 - top_window), -1)]
+            taken = set()
+            for q in wanted:
+                cands = [v for v in window if v not in taken and next_use(v, i) >= (1 << 30)]    # finished qubits only
+                if not cands:
+                    break
+                victim = cands[0]
+                taken.add(victim)
+                actions.append(Exchange(lay.pos[q], lay.pos[victim]))
+                lay.swap_qubits(q, victim)
         if g.kind == "swap" and not g.controls:
             lay.swap_qubits(g.targets[0], g.targets[1])          # pure relabel
             continue

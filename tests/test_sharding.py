@@ -324,3 +324,88 @@ def test_sharded_flush_caches_the_rank_local_program_of_compiled_segments(gbits)
     b.apply_gates(seg_a, caches[0], ("seg", 0))    # the next flush is cacheable again
     b.flush()
     assert len(caches[0]) == 3
+
+
+@pytest.mark.parametrize("gbits", [1, 2, 3])
+def test_hoisted_exchange_saves_the_tail_pass_of_a_sharded_qft(gbits, monkeypatch):
+    # shardplan.choose_prefetch: the rank-bit qubits of a QFT come in right after the first passes (their victims are
+    # finished by then), so their Hadamards share the remaining passes instead of needing one more sweep after the remap
+    from qip_b200.ops import merge_bitgates, plan_passes
+    n, tb, low = 13, 5, 2
+    nl = n - gbits
+    gates = logical_gates(list(qfft_stream(n)), n)
+
+    def plan_local(batch):
+        return plan_passes(merge_bitgates(batch, 2), nl, 16, tile_bits=min(tb, nl), min_low_bits=low)
+
+    def program_cost(hoist):
+        monkeypatch.setenv("QIPB_SHARD_HOIST", hoist)
+        lay = sp.Layout(n, gbits)
+        sp.choose_initial_layout(gates, lay)
+        start = lay.copy()
+        actions = sp.schedule(gates, lay, count_passes=lambda b: len(plan_local(b)), tile_bits=tb, min_low_bits=low)
+        prog = sp.compile_program(actions, nl, (1 << gbits) - 1, plan_local)
+        passes = sum(len(st[1]) for st in prog if isinstance(st, tuple))
+        moves = sum(1 for st in prog if not isinstance(st, tuple))
+        return passes, moves, actions, start, lay
+
+    base_passes, base_moves, _, _, _ = program_cost("0")
+    passes, moves, actions, start, lay = program_cost("1")
+    assert moves == base_moves == 1 and passes <= base_passes, (passes, base_passes)
+    if gbits == 1:
+        assert passes < base_passes                    # (with more rank bits the last local pass of this small case has room)
+    # and it is still the QFT: virtual shards, rank-local planned programs, against the in-order simulator
+    rng = np.random.default_rng(gbits)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    vs = shardsim.VirtualShards(_permuted(psi, start), gbits)
+    vs.run_planned(actions, tile_bits=tb, min_low_bits=low)
+    vs.run_planned(sp.canonicalise(lay), tile_bits=tb, min_low_bits=low)
+    assert lay.canonical()
+    assert float(np.max(np.abs(vs.gather() - reference_state(psi, gates, n)))) <= 1e-12
+
+
+@pytest.mark.parametrize("gbits", [1, 2, 3])
+@pytest.mark.parametrize("seed", range(6))
+def test_hoisted_schedules_of_layered_circuits_are_the_circuit(gbits, seed):
+    # layer after layer on one evolving layout (what the benchmark does): whatever choose_prefetch decides, the
+    # result is the circuit and a layer still needs at most one move
+    n, tb, low = 10, 5, 2
+    lay = sp.Layout(n, gbits)
+    rng = np.random.default_rng(seed)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    vs = shardsim.VirtualShards(psi, gbits)
+    want = psi.copy()
+    hoisted = 0
+    for layer in range(4):
+        gates = logical_gates(list(layered_stream(n, 1, 10 * seed + layer)), n)
+        actions = sp.schedule(gates, lay, tile_bits=tb, min_low_bits=low)
+        moves = [i for i, a in enumerate(actions) if isinstance(a, (sp.Exchange, sp.MultiExchange))]
+        assert len(moves) <= 1
+        hoisted += bool(moves) and any(isinstance(a, sp.Apply) for a in actions[:moves[0]]) and moves[0] < len(actions) - 12
+        vs.run_planned(actions, tile_bits=tb, min_low_bits=low)
+        want = reference_state(want, gates, n)
+    vs.run_planned(sp.canonicalise(lay), tile_bits=tb, min_low_bits=low)
+    assert float(np.max(np.abs(vs.gather() - want))) <= 1e-12
+
+
+def test_hoisted_exchange_at_benchmark_size_36_qubits_on_8_shards(monkeypatch):
+    # planning only (no state): BASELINE configs[4] -- 6 fused passes + ONE 3-bit remap instead of 6 + remap + 1
+    from qip_b200.ops import merge_bitgates, plan_passes
+    n, gbits = 36, 3
+    nl = n - gbits
+    gates = logical_gates(list(qfft_stream(n)), n)
+
+    def plan_local(batch):
+        return plan_passes(merge_bitgates(batch, 2), nl, 16)
+
+    shape = {}
+    for hoist in ("0", "1"):
+        monkeypatch.setenv("QIPB_SHARD_HOIST", hoist)
+        lay = sp.Layout(n, gbits)
+        sp.choose_initial_layout(gates, lay)
+        prog = sp.compile_program(sp.schedule(gates, lay, count_passes=lambda b: len(plan_local(b))), nl, 7, plan_local)
+        shape[hoist] = (sum(len(st[1]) for st in prog if isinstance(st, tuple)),
+                        [len(st.pairs) for st in prog if isinstance(st, sp.MultiExchange)])
+    assert shape["0"] == (7, [3]) and shape["1"] == (6, [3]), shape
