@@ -614,10 +614,12 @@ def split_feeds(groups, feed_list, n, bit_of):
     return vgroups, vfeeds, fixed_mask, fixed_value
 
 
-def product_state_factors(vgroups, vfeeds, fixed_mask, fixed_value, n):
+def product_state_factors(vgroups, vfeeds, fixed_mask, fixed_value, n, bit_of=None):
     """Per index bit b the pair (v_b[0], v_b[1]) with state = (x)_b v_b, for an initial state whose vector feeds are
     all ONE-qubit host vectors (plus one-hot / un-fed qubits, which only fix bits: split_feeds); None otherwise.
-    Bit of qubit q is n-1-q (the canonical layout a state is created in)."""
+    Bit of qubit q is bit_of(q), by default n-1-q (the canonical layout a state is created in)."""
+    if bit_of is None:
+        bit_of = lambda q: n - 1 - q
     torch = _torch() if any(not isinstance(f, (np.ndarray, list, tuple)) for f in vfeeds) else None
     factors = [None] * n
     for g, f in zip(vgroups, vfeeds):
@@ -626,7 +628,7 @@ def product_state_factors(vgroups, vfeeds, fixed_mask, fixed_value, n):
         if torch is not None and (isinstance(f, DeviceState) or isinstance(f, torch.Tensor)):
             return None                                    # device-resident feed: no host round trip for it
         v = np.asarray(f, dtype=np.complex128).reshape(-1)
-        factors[n - 1 - g[0]] = (complex(v[0]), complex(v[1]))
+        factors[bit_of(g[0])] = (complex(v[0]), complex(v[1]))
     for b in range(n):
         if (fixed_mask >> b) & 1:
             factors[b] = (0j, 1 + 0j) if (fixed_value >> b) & 1 else (1 + 0j, 0j)

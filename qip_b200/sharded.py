@@ -13,6 +13,7 @@ torch.distributed supplies rendezvous, handle exchange, the stream-ordered barri
 kernels and the histogram all-reduce; it never carries amplitudes.
 """
 import ctypes
+import os
 import math
 import random
 from typing import List, Optional
@@ -45,7 +46,7 @@ _SHARD_POOL = {}        # (device index, bytes, world size) -> (ptr, peers)
 
 class ShardedB200Backend(object):
     def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
-                 peer_gates: bool = False, lazy_layout: bool = True):
+                 peer_gates: bool = False, lazy_layout: bool = True, lazy_init=None):
         torch = _torch()
         import torch.distributed as dist
         if not dist.is_initialized():
@@ -72,6 +73,8 @@ class ShardedB200Backend(object):
         self.peer_gates = peer_gates
         self.lazy_layout = lazy_layout
         self._pending_init = None       # (groups, feeds): the state is built at the first flush
+        self._virtual_init = None       # (per-local-bit factors, kron arguments): product state not yet written (lazy_init)
+        self.lazy_init = os.environ.get("QIPB_LAZY_INIT", "0") == "1" if lazy_init is None else bool(lazy_init)
         self.stats = {"gates": 0, "exchanges": 0, "peer_gates": 0, "nvlink_bytes_out": 0}
         # shard memory comes from cudaMalloc (qipb_dev_alloc) so that its IPC handle maps it exactly
         self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -204,12 +207,41 @@ class ShardedB200Backend(object):
             _lib.check(self.L.qipb_init_basis(self.ctx, self.ptr, nl, self.code,
                                               (fixed_value & ((1 << nl) - 1)) if mine else -1))
             return
+        kron_args = (vgroups, vfeeds, fixed_mask, fixed_value, list(pos))
+        if self.lazy_init and self.fuse:
+            # product of one-qubit feeds: kept virtual; the first rank-local fused pass writes its tiles from the per-bit
+            # factors (qipb_apply_fused_fill).  The factors of the rank bits are a scalar of this shard.
+            from .backend import product_state_factors
+            factors = product_state_factors(vgroups, vfeeds, fixed_mask, fixed_value, n, lambda q: pos[q])
+            if factors is not None:
+                scalar = 1.0 + 0j
+                for b in range(nl, n):
+                    scalar *= factors[b][(self.rank >> (b - nl)) & 1]
+                local = list(factors[:nl])
+                local[0] = (local[0][0] * scalar, local[0][1] * scalar)
+                self._virtual_init = (local, kron_args)
+                return
+        self._launch_kron(*kron_args)
+
+    def _launch_kron(self, vgroups, vfeeds, fixed_mask, fixed_value, pos):
+        from .backend import feeds_to_device
         dev_feeds = feeds_to_device(vfeeds, self.device)
-        _lib.check(self.L.qipb_init_kron(self.ctx, self.ptr, nl, self.code, len(vgroups),
+        _lib.check(self.L.qipb_init_kron(self.ctx, self.ptr, self.nl, self.code, len(vgroups),
                                          _lib.int_array([len(g) for g in vgroups]),
                                          _lib.int_array([pos[q] for g in vgroups for q in g]),
                                          ctypes.c_void_p(dev_feeds.data_ptr()), fixed_mask, fixed_value, self.rank))
         self._keep = dev_feeds
+
+    def _materialise_virtual(self):
+        """Build a still-virtual product state with the stand-alone kron kernel."""
+        if self._virtual_init is None:
+            return
+        torch = _torch()
+        _, kron_args = self._virtual_init
+        self._virtual_init = None
+        with torch.cuda.device(self.device):
+            self._stream()
+            self._launch_kron(*kron_args)
 
     # ------------------------------------------------------------------ gates
     def apply_gates(self, gates, cache=None, key=None) -> None:
@@ -240,6 +272,31 @@ class ShardedB200Backend(object):
             batch = merge_bitgates(batch, 2)
         return plan_passes(batch, self.nl, self.amp_bytes, tile_bits=self.eng.tile_bits,
                            min_low_bits=self.eng.min_low_bits, enable=self.fuse)
+
+    def _fill_first_pass(self, passes):
+        """Virtual product state + first rank-local fused pass in one write-only sweep (B200Backend._fill_first_pass)."""
+        from .backend import pack_fill_pass
+        torch = _torch()
+        factors, _ = self._virtual_init
+        p = passes[0]
+        if self.nl + len(p.gates) <= _lib.MAX_FUSED_GATES:
+            arr, tbits = pack_fill_pass(factors, p)
+            if self.eng.profile is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            rc = self.L.qipb_apply_fused_fill(self.ctx, self.ptr, self.nl, self.code, len(p.tile_bits), tbits,
+                                              self.nl + len(p.gates), arr)
+            if rc == 0:
+                if self.eng.profile is not None:
+                    e1.record()
+                    self.eng.profile.append(("fused_kernel[fill]", float(self.amp_bytes) * 2.0 ** self.nl, e0, e1))
+                self._virtual_init = None
+                self.stats["fill_passes"] = self.stats.get("fill_passes", 0) + 1
+                return passes[1:]
+            if rc != _lib.ERR_UNSUPPORTED:
+                _lib.check(rc)
+        self._materialise_virtual()
+        return passes
 
     def _run_passes(self, passes):
         torch = _torch()
@@ -325,6 +382,11 @@ class ShardedB200Backend(object):
         self.stats["nvlink_bytes_out"] += self.amp_bytes * half
 
     def _run_step(self, a):
+        if self._virtual_init is not None:
+            if isinstance(a, tuple) and a[1] and a[1][0].fused:
+                a = ("local", self._fill_first_pass(a[1]))
+            else:
+                self._materialise_virtual()
         if isinstance(a, tuple):
             self._run_passes(a[1])
         elif isinstance(a, sp.Exchange):
@@ -356,6 +418,7 @@ class ShardedB200Backend(object):
         cache, keys = self._seg_cache, self._seg_keys
         self._seg_cache, self._seg_keys = None, []
         if not self.queue:
+            self._materialise_virtual()
             return
         gates = list(self.queue)
         self.queue = []
@@ -371,12 +434,14 @@ class ShardedB200Backend(object):
                 self.layout.pos = list(pos_after)
                 self.stats["cached_flushes"] = self.stats.get("cached_flushes", 0) + 1
                 self._run_program(program)
+                self._materialise_virtual()
                 return
         program = self._compile_and_run(sp.schedule(gates, self.layout, peer_gates=self.peer_gates,
                                                     count_passes=lambda batch: len(self._plan_local(batch)),
                                                     tile_bits=self.eng.tile_bits, min_low_bits=self.eng.min_low_bits))
         if ckey is not None:
             cache[ckey] = (program, tuple(self.layout.pos))
+        self._materialise_virtual()                 # nothing ran (only relabelled swaps were queued)
 
     def func_apply(self, reg1_indices, reg2_indices, func, input_offset: int = 0, output_offset: int = 0) -> None:
         torch = _torch()

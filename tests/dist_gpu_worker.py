@@ -125,6 +125,23 @@ def main():
         assert circ.last_stats.get("cached_flushes", 0) == (0 if replay == 0 else 2), circ.last_stats
     if rank == 0:
         print("OK compiled circuit replays (cached sharded programs)")
+    # lazy product-state init on every rank (QIPB_LAZY_INIT): the first rank-local fused pass writes its tiles
+    nb = 16 + int(np.log2(world))
+    pgroups = [[q] for q in range(nb)]
+    pfeeds = []
+    for _ in range(nb):
+        v = rng.normal(size=2) + 1j * rng.normal(size=2)
+        pfeeds.append(v / np.linalg.norm(v))
+    g = ShardedB200Backend.make_state(nb, pgroups, pfeeds, lazy_init=True)
+    c = orc.OracleBackend.make_state(nb, pgroups, pfeeds)
+    for mats in layered_stream(nb, 2, 6):
+        g.kronselect_dot(mats)
+        c.kronselect_dot(mats)
+    check("lazy init", g.get_state(), c.get_state())
+    assert g.stats.get("fill_passes") == 1, g.stats
+    g.close()
+    if rank == 0:
+        print("OK lazy product-state init (fill pass)")
     # production-size shards (2^24 amplitudes each: the specialised fused kernels, the multi-bit remap): QFFT of
     # a basis state |j> against its closed form e^{+2 pi i j k / N} / sqrt(N)
     G = int(np.log2(world))

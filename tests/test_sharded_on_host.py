@@ -152,3 +152,39 @@ def test_sharded_backend_at_production_tile_size_on_virtual_ranks(monkeypatch, P
 
     L = hostlib.run_virtual_ranks(monkeypatch, P, body)
     assert "apply_fused" in L.log and ("peer_remap" in L.log or "peer_swap_bit" in L.log)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("workload", ["layered", "qft"])
+def test_sharded_lazy_product_state_init_on_virtual_ranks(monkeypatch, P, workload):
+    # QIPB_LAZY_INIT: every rank keeps its slice of a product state virtual (the rank bits' factors become a scalar of
+    # the shard) and the first rank-local fused pass writes its tiles instead of loading them
+    from qip_b200.sharded import ShardedB200Backend
+    n = 13 + int(np.log2(P))
+    rng = np.random.default_rng(3)
+    groups = [[q] for q in range(n - 3)] + [[n - 1, n - 3]]              # qubit n-2 stays un-fed
+    feeds = []
+    for _ in range(n - 3):
+        v = rng.normal(size=2) + 1j * rng.normal(size=2)
+        feeds.append(v / np.linalg.norm(v))
+    stream = list(layered_stream(n, 2, 1)) if workload == "layered" else list(qfft_stream(n))
+    c = orc.OracleBackend.make_state(n, groups, feeds + [np.eye(4)[1]])
+    want0 = c.get_state().copy()
+    for m in stream:
+        c.kronselect_dot(m)
+    want = c.get_state()
+
+    def body(rank):
+        g = ShardedB200Backend.make_state(n, groups, feeds + [1], lazy_init=True)
+        for m in stream:
+            g.kronselect_dot(m)
+        _check("lazy " + workload, g.get_state(), want)
+        assert g.stats.get("fill_passes") == 1, g.stats
+        g.close()
+        g = ShardedB200Backend.make_state(n, groups, feeds + [1], lazy_init=True)     # observed before any gate
+        _check("lazy, no gates", g.get_state(), want0, 1e-15)
+        assert "fill_passes" not in g.stats
+        g.close()
+
+    L = hostlib.run_virtual_ranks(monkeypatch, P, body)
+    assert L.log.count("apply_fused_fill") == P and L.log.count("init_kron") == P
