@@ -255,7 +255,7 @@ def _host_only_backend(n, gbits, rank, tile_bits=5, min_low_bits=2):
     b.fuse, b.peer_gates, b.amp_bytes = True, False, 16
     b.eng = types.SimpleNamespace(tile_bits=tile_bits, min_low_bits=min_low_bits)
     b.stats = {"gates": 0}
-    b._pending_init = None
+    b._pending_init, b._virtual_init, b.lazy_init = None, None, False
     b.device = -1                                   # torch.cuda.device(-1) is a no-op context
     b._stream = lambda: None
     b.programs = []                                 # one list of launched steps per flush
