@@ -120,3 +120,12 @@ def test_compiled_circuit_replays_through_the_real_backend_with_cached_plans(mon
         if lazy:
             assert circ.last_stats.get("fill_passes") == 1
     assert len(circ._plans) == 3                      # one cached plan per gate segment, shared by all replays
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_sessions_through_the_real_backend_on_host(monkeypatch, seed):
+    import fuzzlib
+    from qip_b200 import B200Backend
+    hostlib.install(monkeypatch)
+    n = 5 + seed % 9
+    fuzzlib.session(B200Backend.make_state, seed, n, lazy_init=bool(seed % 2), fuse=bool(seed % 5))

@@ -188,3 +188,17 @@ def test_sharded_lazy_product_state_init_on_virtual_ranks(monkeypatch, P, worklo
 
     L = hostlib.run_virtual_ranks(monkeypatch, P, body)
     assert L.log.count("apply_fused_fill") == P and L.log.count("init_kron") == P
+
+
+@pytest.mark.parametrize("seed", range(9))
+def test_random_sessions_through_the_real_sharded_backend_on_virtual_ranks(monkeypatch, seed):
+    import fuzzlib
+    from qip_b200.sharded import ShardedB200Backend
+    P = [2, 4, 8][seed % 3]
+    n = int(np.log2(P)) + 5 + seed % 4
+
+    def body(rank):
+        fuzzlib.session(ShardedB200Backend.make_state, 100 + seed, n, lazy_init=bool(seed % 2), fuse=bool(seed % 5),
+                        peer_gates=(seed % 4 == 0), tile_bits=5, min_low_bits=2)
+
+    hostlib.run_virtual_ranks(monkeypatch, P, body)
