@@ -8,7 +8,9 @@ from oracle import oracle as orc
 from qip_b200.circuits import H2, X2, haar_unitary, layered_stream, qfft_stream, rm_mat
 from qip_b200.mats import CMat
 
-pytestmark = pytest.mark.gpu
+# first run of these kernels on a device happens at the end of the round: bound every test (pytest-timeout, whole
+# process on expiry -- this file sorts last, so nothing else is cut off)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 
 
 def _rand_state(rng, n):
