@@ -42,4 +42,5 @@ PY
 done
 QIPB_FUSED_EXT=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 2 -c 2 -o $O/${R}_prof_fused_ext_qft \
     python bench.py --workload qft --qubits 30 --steps 1 --warmup 1 --no-micro --no-cpu > /dev/null 2>> $O/${R}_ab.err
+timeout 300 python scripts/l2_block_probe.py --qubits 28 > $O/${R}_l2_block_probe.txt 2>&1; cat $O/${R}_l2_block_probe.txt
 ls -la $O | tail -12
