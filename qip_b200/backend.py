@@ -394,7 +394,7 @@ class B200Backend(object):
         self.flush()
         with torch.cuda.device(self.device):
             self._stream()
-            dev_table = torch.from_numpy(table).to(self.device)
+            dev_table = device_table(func, table, self.device)
             _lib.check(self.L.qipb_func_xor(self.ctx, self._ptr(), n, self.code, len(reg1),
                                             _lib.int_array([self.pos[q] for q in reg1]), len(reg2),
                                             _lib.int_array([self.pos[q] for q in reg2]),
@@ -704,6 +704,26 @@ def top_probabilities(probs_big_endian, top_k):
     k = min(int(top_k), len(probs))
     order = np.argsort(-probs, kind="stable")[:k]
     return [int(i) for i in order], [float(probs[i]) for i in order]
+
+
+def device_table(func, table: np.ndarray, device):
+    """The int64 table of `func` on `device`.  Functions that carry their table (qip_b200.functions.tabulated, the
+    table functions of compiled circuits) keep the uploaded copy, so an iterated circuit -- Grover re-applies the same two
+    oracles every iteration (examples/grovers_iterative.py:20-39), 1 GiB of table each at 27 search qubits -- uploads
+    it once instead of once per application."""
+    torch = _torch()
+    carried = getattr(func, "table", None)
+    if isinstance(carried, np.ndarray) and carried.shape == table.shape:
+        cached = getattr(func, "_device_table", None)
+        if cached is not None and cached[0] == str(device) and cached[1].shape[0] == table.shape[0]:
+            return cached[1]
+        dev = torch.from_numpy(table).to(device)
+        try:
+            func._device_table = (str(device), dev)
+        except AttributeError:
+            pass
+        return dev
+    return torch.from_numpy(table).to(device)
 
 
 def tabulate(func, nbits_in: int) -> np.ndarray:

@@ -154,10 +154,9 @@ class CompiledCircuit(object):
                 b.apply_gates(op[1], self._plans, (kind, i))
             elif op[0] == "func":
                 _, reg1, reg2, func = op
-                if i not in self._tables:
-                    self._tables[i] = tabulate(func, len(reg1))
-                table = self._tables[i]
-                b.func_apply(np.array(reg1, dtype=np.int32), np.array(reg2, dtype=np.int32), _TableFunc(table))
+                if i not in self._tables:                      # tabulated once; the function object also keeps the device copy
+                    self._tables[i] = _TableFunc(tabulate(func, len(reg1)))
+                b.func_apply(np.array(reg1, dtype=np.int32), np.array(reg2, dtype=np.int32), self._tables[i])
             elif op[0] == "measure":
                 results[op[2]] = b.measure(np.array(op[1], dtype=np.int32))
             else:

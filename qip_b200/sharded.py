@@ -477,7 +477,8 @@ class ShardedB200Backend(object):
                 r1bits.append(p)
         with torch.cuda.device(self.device):
             self._stream()
-            dev_table = torch.from_numpy(table).to(self.device)
+            from .backend import device_table
+            dev_table = device_table(func, table, self.device)
             _lib.check(self.L.qipb_func_xor(self.ctx, self.ptr, self.nl, self.code, len(reg1), _lib.int_array(r1bits),
                                             len(reg2), _lib.int_array([self.layout.pos[q] for q in reg2]),
                                             ctypes.c_void_p(dev_table.data_ptr()), x_fixed))

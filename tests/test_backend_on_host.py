@@ -129,3 +129,32 @@ def test_random_sessions_through_the_real_backend_on_host(monkeypatch, seed):
     hostlib.install(monkeypatch)
     n = 5 + seed % 9
     fuzzlib.session(B200Backend.make_state, seed, n, lazy_init=bool(seed % 2), fuse=bool(seed % 5))
+
+
+def test_function_tables_are_uploaded_once_per_function_object(monkeypatch):
+    # Grover re-applies the same oracles every iteration: a function that carries its table keeps the device copy
+    from qip_b200 import B200Backend
+    from qip_b200 import backend as be
+    from qip_b200.functions import equals, tabulated
+    hostlib.install(monkeypatch)
+    uploads = []
+    real = be.device_table
+
+    def counting(func, table, device):
+        before = getattr(func, "_device_table", None)
+        out = real(func, table, device)
+        if getattr(func, "_device_table", None) is not before or not hasattr(func, "table"):
+            uploads.append(1)
+        return out
+    monkeypatch.setattr(be, "device_table", counting)
+    n = 8
+    oracle_f = tabulated(equals(37), 7)
+    b = B200Backend.make_state(n, [[q] for q in range(n)], [np.array([1.0, 1.0]) / np.sqrt(2)] * n)
+    for _ in range(3):
+        b.func_apply(list(range(7)), [7], oracle_f)
+    assert len(uploads) == 1
+    b.func_apply(list(range(7)), [7], lambda x: int(x == 37))            # a plain callable: tabulated and uploaded each time
+    assert len(uploads) == 2
+    st = np.asarray(b.get_state())
+    assert abs(np.vdot(st, st) - 1.0) < 1e-12
+    b.close()
