@@ -267,8 +267,8 @@ def choose_prefetch(base: Sequence[Gate], n_now: int, lay: Layout, top_window: i
     own (QFT over 2^G shards: 6 passes + one remap instead of 6 + remap + 1).  Candidate cut points are scheduled on a
     copy of the layout and ranked with a cheap pass-count estimate; the best one replaces the base schedule only if it
     is strictly cheaper -- and, when the executor's planner is available, only if the real pass counts confirm it."""
-    if lay.G == 0 or n_now == 0 or n_now == len(base) or peer_gates:
-        return None
+    if lay.G == 0 or n_now == 0 or n_now == len(base) or peer_gates or len(base) > 20000:
+        return None                                            # (very long queues: keep the planning cost linear)
     import os
     if os.environ.get("QIPB_SHARD_HOIST", "1") == "0":        # tuning knob for profiling runs
         return None
