@@ -37,7 +37,7 @@ extern "C" {
 
 #define QIPB_MAX_DENSE_K 4     /* register-blocked dense kernels: 1..4 target bits            */
 #define QIPB_MAX_BIG_K 10      /* shared-memory dense kernel: up to 10 target bits             */
-#define QIPB_MAX_TILE_BITS 12  /* fused pass: tile of 2^12 c128 (64 KiB) / 2^13 c64 amplitudes */
+#define QIPB_MAX_TILE_BITS 12  /* fused pass: tiles of 2^12 amplitudes (64 KiB complex128, 32 KiB complex64) */
 #define QIPB_MAX_FUSED_GATES 280 /* gates per qipb_apply_fused call (runs of diagonal gates fold into stages) */
 
 typedef struct qipb_ctx qipb_ctx;
