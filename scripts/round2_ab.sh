@@ -28,6 +28,22 @@ PY
   done
  done
 done
+# with EXT the passes move towards the HBM floor, so the pass COUNT matters more: 6 contiguous low bits give 6 free bits per pass
+for lb in 6 7; do
+ for wl in qft layered; do
+  f=$O/${R}_ab_${wl}_ext1_low${lb}.json
+  QIPB_FUSED_EXT=1 QIPB_MIN_LOW_BITS=$lb timeout 400 python bench.py --workload $wl --steps 4 --warmup 3 --no-micro --no-cpu > $f 2>> $O/${R}_ab.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("$f"))
+    print("$wl ext=1 low_bits=$lb  ms/step=%.1f  passes=%s" % (d["ms_per_step"], d["config"]["stats"].get("passes")),
+          {k: (x["launches"], round(x["ms_total"] / x["launches"], 1), round(x["GBps"])) for k, x in d["kernels"].items()})
+except Exception as e:
+    print("$wl ext=1 low_bits=$lb FAILED", e)
+PY
+ done
+done
 for lazy in 0 1; do
  f=$O/${R}_ab_lazy${lazy}.json
  QIPB_LAZY_INIT=$lazy timeout 400 python bench.py --steps 3 --warmup 3 --no-micro --no-cpu > $f 2>> $O/${R}_ab.err
