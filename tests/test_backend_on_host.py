@@ -158,3 +158,11 @@ def test_function_tables_are_uploaded_once_per_function_object(monkeypatch):
     st = np.asarray(b.get_state())
     assert abs(np.vdot(st, st) - 1.0) < 1e-12
     b.close()
+
+
+def test_graft_entry_smoke_runs_on_the_host_double(monkeypatch, capsys):
+    # the driver's smoke() (one small hot-path invocation checked against the oracle) exercised end to end on the CPU tier
+    import __graft_entry__ as entry
+    hostlib.install(monkeypatch)
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
