@@ -166,3 +166,25 @@ def test_graft_entry_smoke_runs_on_the_host_double(monkeypatch, capsys):
     hostlib.install(monkeypatch)
     entry.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("workload", ["layered", "qft"])
+def test_bench_b200_arm_produces_the_contract_line_on_host_doubles(workload):
+    # bench.py itself (not only the engine) must keep working between GPU runs: its B200 arm end to end on the host doubles
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "bench_on_host.py"), "--qubits", "14", "--steps", "2", "--warmup", "1",
+                        "--workload", workload, "--no-micro", "--no-cpu"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "cpu_baseline"):
+        assert key in d, key
+    assert d["metric"] == "gate_apply_GBps" and d["n_gpus"] == 1 and d["steps"] == 2 and d["config"]["qubits"] == 14
+    assert d["gpu_launches"] >= 1 and d["roofline"]["kernel"].startswith("fused_kernel") and d["roofline"]["bound"] == "hbm"
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
