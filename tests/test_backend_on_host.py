@@ -188,3 +188,24 @@ def test_bench_b200_arm_produces_the_contract_line_on_host_doubles(workload):
     assert d["metric"] == "gate_apply_GBps" and d["n_gpus"] == 1 and d["steps"] == 2 and d["config"]["qubits"] == 14
     assert d["gpu_launches"] >= 1 and d["roofline"]["kernel"].startswith("fused_kernel") and d["roofline"]["bound"] == "hbm"
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    # bench.py --impl reference: the reference's own CPU kernels (oracle/_ref, else the C port) on a bounded sample
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "qft",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["impl"] == "reference" and d["metric"] == "gate_apply_GBps" and d["unit"] == "GB/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 exit quietly under torchrun
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
