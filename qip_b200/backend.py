@@ -646,7 +646,10 @@ def feeds_to_device(vfeeds, device):
 
     def flush_host():
         if host_run:
-            cat = np.ascontiguousarray(np.concatenate(host_run))
+            # a single host vector (a whole-register feed: 256 MiB at 24 qubits) goes up as it is -- no concatenated copy
+            cat = np.ascontiguousarray(host_run[0] if len(host_run) == 1 else np.concatenate(host_run))
+            if not cat.flags.writeable:
+                cat = cat.copy()
             parts.append(torch.from_numpy(cat).to(device))
             host_run.clear()
 

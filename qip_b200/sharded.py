@@ -42,6 +42,57 @@ class _RawCuda(object):
 # ranks hold the same sizes at the same time and a re-used shard keeps its peer mappings valid.  A request of
 # a different size first releases what is pooled (collectively).
 _SHARD_POOL = {}        # (device index, bytes, world size) -> (ptr, peers)
+# Shards of states that were dropped without close() while the pool slot of their size was taken (the reference's
+# run() never closes a state, qip/pipeline.py:248): freed collectively at the next construction / drain.
+_ORPHANS = []           # [(ptr, peers)]
+
+_HOST_STATE_MAX_QUBITS = 30     # get_state(): the whole state as a host ndarray on every rank up to here, a handle beyond
+
+
+class ShardedState(object):
+    """Array-like handle on a sharded state in canonical index order (returned by get_state() beyond 30 qubits, where
+    the whole vector does not belong in host memory): len(), .shape, slicing / indexing (every rank receives the
+    requested range; D2H of that range only), `local_shard` (this rank's device tensor).  Like every call of the sharded
+    engine, reads are collective: all ranks must make them in the same order.  The handle keeps the engine alive."""
+
+    def __init__(self, backend):
+        self.backend = backend
+        self.shape = (2 ** backend.n,)
+        self.dtype = backend.np_dtype
+
+    def __len__(self):
+        return self.shape[0]
+
+    @property
+    def local_shard(self):
+        return self.backend.eng.state
+
+    @property
+    def local_range(self):
+        b = self.backend
+        return (b.rank << b.nl, (b.rank + 1) << b.nl)
+
+    def __getitem__(self, item):
+        size = self.shape[0]
+        if isinstance(item, slice):
+            start, stop, step = item.indices(size)
+            if step > 0:
+                if stop <= start:
+                    return np.zeros(0, dtype=self.dtype)
+                return self.backend.get_relative_range(start, stop)[::step]
+            raise IndexError("negative steps are not supported on a sharded state")
+        i = int(item)
+        if i < 0:
+            i += size
+        if not (0 <= i < size):
+            raise IndexError("index out of range")
+        return self.backend.get_relative_range(i, i + 1)[0]
+
+    def __array__(self, dtype=None, copy=None):
+        if self.backend.n > 34:
+            raise ValueError("a %d-qubit state does not fit a host array; slice the handle instead" % self.backend.n)
+        a = self.backend.get_relative_range(0, self.shape[0])
+        return a.astype(dtype) if dtype is not None else a
 
 
 class ShardedB200Backend(object):
@@ -79,6 +130,8 @@ class ShardedB200Backend(object):
         # shard memory comes from cudaMalloc (qipb_dev_alloc) so that its IPC handle maps it exactly
         self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.peers = {}
+        self.ptr = None
+        self._free_orphans()
         key = self._pool_key()
         pooled = _SHARD_POOL.pop(key, None)
         if pooled is not None:
@@ -93,6 +146,22 @@ class ShardedB200Backend(object):
 
     def _pool_key(self):
         return (self.device.index or 0, (1 << self.nl) * self.amp_bytes, self.P)
+
+    def _free_orphans(self):
+        """Free the shards of states that were garbage-collected un-closed (collective: every rank runs the same
+        program, so every rank holds the same orphans at this point)."""
+        torch = _torch()
+        if not _ORPHANS:
+            return
+        torch.cuda.synchronize()
+        self._sync_all()
+        torch.cuda.synchronize()
+        while _ORPHANS:
+            ptr, peers = _ORPHANS.pop()
+            for pp in peers.values():
+                self.L.qipb_ipc_close(self.ctx, pp)
+            self.dist.barrier()
+            self.L.qipb_dev_free(self.ctx, ptr)
 
     def _drain_pool(self):
         """Release every pooled shard (all ranks call this at the same point of the program)."""
@@ -647,12 +716,14 @@ class ShardedB200Backend(object):
 
     # ------------------------------------------------------------------ state access
     def get_state(self):
-        """Canonical-order host copy of the WHOLE state on every rank (small n only)."""
+        """qip/backend.py:106-107, called unconditionally at the end of every run() (qip/pipeline.py:248).  Up to 30
+        qubits: canonical-order host copy of the WHOLE state on every rank.  Beyond: a ShardedState handle (the
+        state stays sharded in HBM, canonicalised; slices are gathered on demand), like B200Backend's DeviceState."""
         torch = _torch()
         self.flush()
-        if self.n > 30:
-            raise ValueError("get_state() of a sharded state is limited to 30 qubits; use measure_probabilities")
         self._execute(sp.canonicalise(self.layout))
+        if self.n > _HOST_STATE_MAX_QUBITS:
+            return ShardedState(self)
         parts = [torch.empty(1 << self.nl, dtype=self.eng.tdtype, device=self.device) for _ in range(self.P)]
         self.dist.all_gather(parts, self.eng.state)
         return torch.cat(parts).cpu().numpy()
@@ -721,3 +792,23 @@ class ShardedB200Backend(object):
             self.eng.state = None
             self.ptr = None
         self.eng.close()
+
+    def __del__(self):
+        """A state dropped without close() -- the reference's run() returns get_state() and forgets the backend
+        (qip/pipeline.py:248) -- must not leak its shard (up to 128 GiB plus P-1 peer mappings).  No collective may run
+        from a finaliser: the shard goes back to the pool as it is (the next user orders itself behind every rank's
+        outstanding work with its first stream-ordered barrier) or, if the slot is taken, onto the orphan list that the
+        next construction frees collectively."""
+        try:
+            if getattr(self, "ptr", None) is None:
+                return
+            key = self._pool_key()
+            if key in _SHARD_POOL:
+                _ORPHANS.append((self.ptr, self.peers))
+            else:
+                _SHARD_POOL[key] = (self.ptr, self.peers)
+            self.ptr, self.peers = None, {}
+            self.eng.state = None
+            self.eng.close()
+        except Exception:
+            pass

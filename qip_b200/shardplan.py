@@ -362,7 +362,8 @@ def _schedule_ordered(gates: Sequence[Gate], lay: Layout, top_window: int = 8, p
                 actions.append(Exchange(lay.pos[q], lay.pos[victim]))
                 lay.swap_qubits(q, victim)
         actions.append(Apply(to_phys(g, lay)))
-    return coalesce_exchanges(actions)
+    # qipb_peer_remap needs more local bits than exchanged pairs (nbits > g): tiny shards coalesce less or not at all
+    return coalesce_exchanges(actions, max_pairs=max(1, min(3, (lay.n - lay.G) - 1)))
 
 
 def coalesce_exchanges(actions: List[object], max_pairs: int = 3) -> List[object]:
@@ -453,4 +454,5 @@ def canonicalise(lay: Layout) -> List[object]:
         want = lay.n - 1 - q
         if lay.pos[q] != want:
             swap_positions(lay.pos[q], want)
-    return coalesce_exchanges(actions)
+    # qipb_peer_remap needs more local bits than exchanged pairs (nbits > g): tiny shards coalesce less or not at all
+    return coalesce_exchanges(actions, max_pairs=max(1, min(3, (lay.n - lay.G) - 1)))

@@ -465,6 +465,30 @@ class _PerThreadDict(object):
     def __bool__(self):
         return bool(self._d())
 
+
+class _PerThreadList(object):
+    """qip_b200.sharded._ORPHANS (shards of un-closed states) per virtual rank."""
+
+    def __init__(self):
+        self.local = threading.local()
+
+    def _l(self):
+        if not hasattr(self.local, "l"):
+            self.local.l = []
+        return self.local.l
+
+    def append(self, v):
+        self._l().append(v)
+
+    def pop(self, *a):
+        return self._l().pop(*a)
+
+    def __len__(self):
+        return len(self._l())
+
+    def __bool__(self):
+        return bool(self._l())
+
     def __len__(self):
         return len(self._d())
 
@@ -483,6 +507,7 @@ def run_virtual_ranks(monkeypatch, P, body):
     monkeypatch.setattr(sh, "_torch", lambda: fake)
     monkeypatch.setattr(be, "_CTX_POOL", {}, raising=False)
     monkeypatch.setattr(sh, "_SHARD_POOL", _PerThreadDict())
+    monkeypatch.setattr(sh, "_ORPHANS", _PerThreadList())
     td = ThreadDist(P)
     for name in ("is_initialized", "get_rank", "get_world_size", "barrier", "all_gather_object", "all_reduce",
                  "broadcast", "all_gather"):

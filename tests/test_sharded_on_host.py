@@ -202,3 +202,84 @@ def test_random_sessions_through_the_real_sharded_backend_on_virtual_ranks(monke
                         peer_gates=(seed % 4 == 0), tile_bits=5, min_low_bits=2)
 
     hostlib.run_virtual_ranks(monkeypatch, P, body)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_unclosed_sharded_states_do_not_leak_their_shards(monkeypatch, P):
+    # the reference's run() returns get_state() and forgets the backend (qip/pipeline.py:248): a dropped state hands its
+    # shard back (pool, or the orphan list that the next construction frees collectively) -- ADVICE r01
+    import gc
+    from qip_b200.sharded import ShardedB200Backend
+    n = 9
+
+    def body(rank):
+        for rep in range(6):
+            g = ShardedB200Backend.make_state(n, [], [], tile_bits=5, min_low_bits=2)
+            h = ShardedB200Backend.make_state(n, [], [], tile_bits=5, min_low_bits=2)      # two live states of one size
+            g.kronselect_dot({0: H2})
+            h.kronselect_dot({1: H2})
+            assert abs(g.total_prob() - 1.0) < 1e-12 and abs(h.total_prob() - 1.0) < 1e-12
+            del g, h                                                                       # never closed
+            gc.collect()
+        g = ShardedB200Backend.make_state(n, [], [], tile_bits=5, min_low_bits=2)
+        g.close()
+
+    before = set(hostlib._PeerMixin._bufs)
+    hostlib.run_virtual_ranks(monkeypatch, P, body)
+    # P ranks x (one pooled shard each) stay allocated; everything else was returned
+    left = set(hostlib._PeerMixin._bufs) - before
+    assert len(left) <= P, len(left)
+
+
+def test_get_state_of_a_large_sharded_state_is_a_lazy_handle(monkeypatch):
+    # run() calls get_state() unconditionally; beyond the host limit it must return a handle, not raise
+    from qip_b200 import sharded as sh
+    n, P = 10, 4
+    rng = np.random.default_rng(2)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+    ops_ = list(layered_stream(n, 2, 5))
+    for m in ops_:
+        c.kronselect_dot(m)
+    want = c.get_state()
+    monkeypatch.setattr(sh, "_HOST_STATE_MAX_QUBITS", 8)
+
+    def body(rank):
+        g = sh.ShardedB200Backend.make_state(n, [list(range(n))], [psi], tile_bits=5, min_low_bits=2)
+        for m in ops_:
+            g.kronselect_dot(m)
+        st = g.get_state()
+        assert isinstance(st, sh.ShardedState) and len(st) == 2 ** n and st.shape == (2 ** n,)
+        _check("slice", st[100:900], want[100:900])
+        _check("strided", st[3:700:7], want[3:700:7])
+        assert abs(st[517] - want[517]) < 1e-12 and abs(st[-1] - want[-1]) < 1e-12
+        _check("array", np.asarray(st), want)
+        lo, hi = st.local_range
+        _check("local shard", st.local_shard.numpy(), want[lo:hi])
+        g.close()
+
+    hostlib.run_virtual_ranks(monkeypatch, P, body)
+
+
+@pytest.mark.parametrize("P,nl", [(4, 2), (4, 3), (8, 2), (2, 1)])
+def test_tiny_shards_do_not_coalesce_more_exchanges_than_local_bits(monkeypatch, P, nl):
+    # qipb_peer_remap needs nbits > g; with nl <= 3 a 3-pair MultiExchange was built and failed after the
+    # layout had been mutated.  One local qubit cannot host a 2-qubit gate: a clear error, raised by the scheduler.
+    from qip_b200.sharded import ShardedB200Backend
+    G = int(np.log2(P))
+    n = G + nl
+    ops_ = [{q: H2} for q in range(n)] + [{(q, (q + 1) % n): CMat(X2)} for q in range(n)] + [{q: H2} for q in range(n)]
+    c = orc.OracleBackend.make_state(n, [], [])
+    for m in ops_:
+        c.kronselect_dot(m)
+    want = c.get_state()
+
+    def body(rank):
+        g = ShardedB200Backend.make_state(n, [], [], tile_bits=min(5, nl), min_low_bits=min(2, nl))
+        for m in ops_:
+            g.kronselect_dot(m)
+        _check("tiny shards", g.get_state(), want)
+        g.close()
+
+    hostlib.run_virtual_ranks(monkeypatch, P, body)
