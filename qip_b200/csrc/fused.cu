@@ -43,6 +43,8 @@ struct DevGate {
     unsigned char mk;       // dense 2-qubit block: MK_GENERAL / MK_REAL / MK_REALPHASE / MK_MONOMIAL (coefficient layout below)
     unsigned char phmask;   // MK_REALPHASE: columns with a non-trivial phase; MK_MONOMIAL: columns whose coefficient is not 1
     unsigned char perm;     // MK_MONOMIAL: bits 2j..2j+1 = the row that column j maps to
+    unsigned char pair;     // post == 4 (leader of a block pair, WIDE kernel): the partner is op gi + pair; its four sorted
+                            // expansion masks are nmask[2..5]
     u64 out_ctrl;           // state-index mask of controls outside the tile
     double2 m[16];
 };
@@ -295,6 +297,93 @@ QIPB_HD void sweep_mono2(A *tile, const DevGate &g, const EX ex, u32 ngroups, in
         p[dst[1]] = a1;
         p[dst[2]] = a2;
         p[dst[3]] = a3;
+    }
+}
+
+
+// ---- two disjoint dense 2-qubit blocks in ONE sweep (WIDE kernel: 128 threads, up to 168 registers) ----
+// A sweep is a round trip of the whole tile through shared memory, and with 4-5 dense blocks per pass the
+// shared-memory pipe (LDS/STS of the sweeps + the TMA traffic of the tile itself) is what bounds a layered pass
+// (~32 B per amplitude and sweep at 128 B/clk: as much as the HBM time of the tile).  Blocks on disjoint target pairs
+// commute, so two of them run on a group of 16 amplitudes held in registers: member index k = 4 * ia + ib with ia / ib
+// the matrix index of block A / B.  FP64 work is unchanged; shared-memory traffic, index arithmetic and barriers halve.
+// A monomial block (Swap, CX, phases folded in) is a phase per row plus a permutation of the STORE offsets.
+// Host guarantees (lower_fused): no in-tile controls on either block, the four targets distinct and above the
+// bank-conflict bits (so a quarter-warp always touches 8 consecutive amplitudes), ngroups = tile / 16 a multiple of NT.
+template <typename A, int MK, int STRIDE>
+QIPB_HD void pair_phase(A (&x)[16], const DevGate &g) {
+    // STRIDE 4: the block acts on ia (members s, 4 + s, 8 + s, 12 + s);  STRIDE 1: on ib (members 4 s .. 4 s + 3)
+    if (MK == MK_MONOMIAL) {
+        const u32 phmask = g.phmask;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (phmask & (1u << j)) {
+                const Cf<A> c = coef<A>(g, j);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int k = STRIDE == 4 ? 4 * j + s : 4 * s + j;
+                    x[k] = cmulc<A>(c, x[k]);
+                }
+            }
+    } else {
+        const Block2<A, MK> blk(g);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int b = STRIDE == 4 ? s : 4 * s;
+            A r[4];
+            blk.apply(x[b], x[b + STRIDE], x[b + 2 * STRIDE], x[b + 3 * STRIDE], r);
+            x[b] = r[0];
+            x[b + STRIDE] = r[1];
+            x[b + 2 * STRIDE] = r[2];
+            x[b + 3 * STRIDE] = r[3];
+        }
+    }
+}
+
+template <typename A, int STRIDE>
+QIPB_HD void pair_phase_any(A (&x)[16], const DevGate &g) {
+    switch (g.mk) {                                           // uniform: the form comes from the descriptor
+    case MK_REAL: pair_phase<A, MK_REAL, STRIDE>(x, g); break;
+    case MK_REALPHASE: pair_phase<A, MK_REALPHASE, STRIDE>(x, g); break;
+    case MK_MONOMIAL: pair_phase<A, MK_MONOMIAL, STRIDE>(x, g); break;
+    default: pair_phase<A, MK_GENERAL, STRIDE>(x, g); break;
+    }
+}
+
+template <typename A, int NT>
+QIPB_HD void sweep_pair2(A *tile, const DevGate &ga, const DevGate &gb, u32 ngroups, int tid) {
+    const u32 nm0 = ga.nmask[2], nm1 = ga.nmask[3], nm2 = ga.nmask[4], nm3 = ga.nmask[5];
+    u32 ldA[4], ldB[4], stA[4], stB[4];
+    {
+        const u32 oah = 1u << ga.tl[0], oal = 1u << ga.tl[1], obh = 1u << gb.tl[0], obl = 1u << gb.tl[1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ldA[j] = ((j & 2) ? oah : 0u) + ((j & 1) ? oal : 0u);
+            ldB[j] = ((j & 2) ? obh : 0u) + ((j & 1) ? obl : 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                         // column j of a monomial block lands in row perm[j]
+            const u32 ra = ga.mk == MK_MONOMIAL ? (ga.perm >> (2 * j)) & 3u : (u32)j;
+            const u32 rb = gb.mk == MK_MONOMIAL ? (gb.perm >> (2 * j)) & 3u : (u32)j;
+            stA[j] = ((ra & 2u) ? oah : 0u) + ((ra & 1u) ? oal : 0u);
+            stB[j] = ((rb & 2u) ? obh : 0u) + ((rb & 1u) ? obl : 0u);
+        }
+    }
+#pragma unroll 1
+    for (u32 it = 0, nit = ngroups / NT, w = tid; it < nit; ++it, w += NT) {
+        u32 e = w;
+        e += e & nm0;
+        e += e & nm1;
+        e += e & nm2;
+        e += e & nm3;
+        A *p = tile + e;
+        A x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = p[ldA[k >> 2] + ldB[k & 3]];
+        pair_phase_any<A, 4>(x, ga);
+        pair_phase_any<A, 1>(x, gb);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) p[stA[k >> 2] + stB[k & 3]] = x[k];
     }
 }
 
@@ -763,13 +852,14 @@ QIPB_HD void run_op(A *tile, const DevGate &g, const DevGate &next, const double
 // launches it only for passes that carry such ops (fused_has_ext), so the default kernels stay as measured.
 template <bool EXT>
 QIPB_HD bool fused_op_is_skipped(const DevGate &g) {
-    return g.diag == 3 || (EXT && g.post == 3);   // stage applied by the dense gate before it / second Hadamard of a QFT pair
+    // stage applied by the dense gate before it / second Hadamard of a QFT pair / second block of a block pair
+    return g.diag == 3 || (EXT && (g.post == 3 || g.post == 5));
 }
 
 static inline bool fused_has_ext(const FusedArgs &f) {
     for (int gi = 0; gi < f.ngates; ++gi) {
         const DevGate &g = f.g[gi];
-        if (g.post >= 2 || g.diag == 5 || (!g.diag && g.k == 1 && g.mk == MK1_REAL)) return true;
+        if (g.post >= 2 || g.diag == 5 || (!g.diag && g.k == 1 && g.mk == MK1_REAL)) return true;   // incl. block pairs (post 4 / 5)
     }
     return false;
 }
@@ -778,6 +868,17 @@ template <typename A, bool UNI, int NT, bool EXT>
 QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *stage_S, u64 base, u32 tsize, int tid) {
     if (EXT) {
         const DevGate &g = f.g[gi];
+        if (g.post == 4) {                                      // block pair (WIDE launches only): ops gi and gi + pair
+            const DevGate &h = f.g[gi + g.pair];
+            const bool on_a = (base & g.out_ctrl) == g.out_ctrl, on_b = (base & h.out_ctrl) == h.out_ctrl;
+            if (on_a && on_b) {
+                sweep_pair2<A, NT>(tile, g, h, tsize >> 4, tid);
+            } else if (on_a || on_b) {                          // one of them is switched off on this tile
+                const DevGate &one = on_a ? g : h;
+                run_op<A, UNI, NT>(tile, one, one, f.tables, stage_S, gi, base, f.tb, tsize, tid);
+            }
+            return;
+        }
         if (g.diag == 5) {                                      // fill mode: op 0 writes the tile (no controls, host-checked)
             sweep_stage_fill<A, NT>(tile, stage_ref(g, f.tables, stage_S[gi], f.tb), tsize, tid);
             return;
@@ -802,8 +903,11 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
 // BULK: tile staging with cp.async.bulk (TMA 1-D bulk copies, one per contiguous run, completion on
 // an mbarrier) instead of LDG/STS through registers.  Requires runs of >= 16 bytes.
 // NT threads per CTA: 256 for 2^12-amplitude tiles, 128 for 2^11 (twice as many CTAs per SM on the same shared memory)
-template <typename A, bool BULK, bool UNI, int NT, bool EXT>
-__global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+// WIDE: 2^12-amplitude tiles swept by 128 threads, still 3 (complex128) / 4 (complex64) CTAs per SM -- the register
+// budget per thread doubles (168 / 128), which is what the 16-amplitude register groups of the block pairs and the EXT
+// forms need (the 256-thread EXT kernel spilled at its 80-register cap).
+template <typename A, bool BULK, bool UNI, int NT, bool EXT, bool WIDE = false>
+__global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (WIDE ? 1 : 256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ __align__(16) double2 stage_S[FUSED_MAX_OPS + 1];
@@ -1005,11 +1109,25 @@ __global__ void __launch_bounds__(RING_THREADS, 1) fused_ring_kernel(A *__restri
     }
 }
 
+static bool wide_enabled();
 static bool ext_enabled() {
-    // opt-in until measured on B200 (round 2): real 1-qubit forms and paired QFT steps (EXT sweeps); read per call
-    // so that tests can toggle it.  Numerics are covered on the CPU tier by tests/test_fused_emul.py.
+    // real 1-qubit forms and paired QFT steps (EXT sweeps): on with the WIDE kernel (measured on B200 in round 2: QFT
+    // -8 %; the 256-thread EXT kernel spills and loses on layered passes, so without WIDE they stay opt-in); read per
+    // call so that tests can toggle it.  Numerics are covered on the CPU tier by tests/test_fused_emul.py.
     const char *e = getenv("QIPB_FUSED_EXT");
-    return e && atoi(e) != 0;
+    return e ? atoi(e) != 0 : wide_enabled();
+}
+
+static bool wide_enabled() {
+    // default ON: 2^12 tiles run by the WIDE kernel (128 threads, block pairs, EXT forms); QIPB_FUSED_WIDE=0 gives the
+    // 256-thread kernels of round 1 back (A/B runs); read per call so that tests can toggle it
+    const char *e = getenv("QIPB_FUSED_WIDE");
+    return !e || atoi(e) != 0;
+}
+
+static bool pair_enabled() {
+    const char *e = getenv("QIPB_FUSED_PAIR");                // block pairs of the WIDE kernel (default on; A/B knob, read per call)
+    return !e || atoi(e) != 0;
 }
 
 static bool ring_enabled() {
@@ -1025,6 +1143,12 @@ static inline u32 tsize_runs(const FusedArgs &f) { return 1u << (f.tb - f.lowrun
 // 2^11 with 128-thread CTAs).  Also decides whether descriptors may carry the structured matrix forms.
 static inline bool launch_is_bulk(const FusedArgs &f, size_t amp_bytes) { return (amp_bytes << f.lowrun) >= 512 && f.ntiles >= 2; }
 static inline bool launch_is_uni(const FusedArgs &f, size_t amp_bytes) { return launch_is_bulk(f, amp_bytes) && f.tb >= 11; }
+static bool wide_enabled();
+static bool ring_enabled();
+static bool pair_enabled();
+static inline bool launch_is_wide(const FusedArgs &f, size_t amp_bytes) {
+    return launch_is_uni(f, amp_bytes) && f.tb == 12 && wide_enabled() && !ring_enabled();
+}
 
 // Exact structure of a dense 4x4 block (see Block2): fills the descriptor's coefficient area in the layout of
 // the chosen form.  `put_c(slot, re, im)` / `put_r(slot, v)` write in the amplitude's precision.
@@ -1101,10 +1225,10 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
     // UNI: all specialised sweeps (<= 4 fixed positions) have a multiple of the CTA size as item count
     const bool half = bulk && f.tb == 11;                      // 2^11 tiles: 128-thread CTAs
     const bool uni = launch_is_uni(f, sizeof(A));
-#define QIPB_LAUNCH_FUSED(B, U, T, X)                                                                                          \
-    do {                                                                                                                       \
-        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U, T, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        fused_kernel<A, B, U, T, X><<<(unsigned)grid, T, smem, ctx->stream>>>(state, f);                                       \
+#define QIPB_LAUNCH_FUSED(B, U, T, X, ...)                                                                                                  \
+    do {                                                                                                                                    \
+        QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U, T, X, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fused_kernel<A, B, U, T, X, ##__VA_ARGS__><<<(unsigned)grid, T, smem, ctx->stream>>>(state, f);                                      \
     } while (0)
     if (uni && !half && ring_enabled() && f.ntiles >= 4ull * (u64)ctx->sm_count && (tsize_runs(f) <= 128)) {
         constexpr int NBUF = sizeof(A) == 16 ? 3 : 6;
@@ -1113,7 +1237,10 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
         fused_ring_kernel<A, NBUF><<<(unsigned)ctx->sm_count, RING_THREADS, rsmem, ctx->stream>>>(state, f);
         ctx->ring_launches++;
     } else if (half) QIPB_LAUNCH_FUSED(true, true, 128, false);
-    else if (uni && fused_has_ext(f)) {                        // the host marks EXT ops only for this launch shape
+    else if (launch_is_wide(f, sizeof(A))) {
+        QIPB_LAUNCH_FUSED(true, true, 128, true, true);
+        ctx->ext_launches += fused_has_ext(f) ? 1 : 0;
+    } else if (uni && fused_has_ext(f)) {                      // the host marks EXT ops only for this launch shape
         QIPB_LAUNCH_FUSED(true, true, 256, true);
         ctx->ext_launches++;
     } else if (uni) QIPB_LAUNCH_FUSED(true, true, 256, false);
@@ -1243,6 +1370,12 @@ void build_stages(const qipb_gate *gates, const std::vector<int> &run, int nbits
         o.stage = true;
         o.gate = -1;
         o.common = common;
+        o.support = 0;
+        for (size_t t = pos; t < end; ++t) {
+            const qipb_gate &g = gates[run[t]];
+            o.support |= g.ctrl_mask;
+            for (int j = 0; j < g.k; ++j) o.support |= 1ull << g.bits[j];
+        }
         o.tab_off = (u32)tables.size();
         o.nout = 0;
         tables.insert(tables.end(), T[0].begin(), T[0].end());
@@ -1488,6 +1621,54 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                     oi += 4;
                 } else {
                     ++oi;
+                }
+            }
+        }
+        // block pairs (WIDE launches): two dense 2-qubit blocks on disjoint targets share one sweep over 16-amplitude
+        // register groups (sweep_pair2).  The partner may sit later in the list: it is executed early, at the leader's
+        // position, which is exact when it commutes with every op in between -- the non-diagonal targets of either
+        // side must avoid everything the other side reads (targets and controls; diagonal ops only read).
+        if (pair_enabled() && launch_is_wide(f, dtype == QIPB_C128 ? 16 : 8)) {
+            const int lowb = dtype == QIPB_C128 ? 3 : 4;       // LowBits<A>
+            auto support = [&](size_t oi) -> u64 {
+                const Op &o = ops[first + oi];
+                if (o.stage) return o.support;
+                const qipb_gate &g = gates[o.gate];
+                u64 m = g.ctrl_mask;
+                for (int j = 0; j < g.k; ++j) m |= 1ull << g.bits[j];
+                return m;
+            };
+            auto nondiag = [&](size_t oi) -> u64 {
+                const Op &o = ops[first + oi];
+                if (o.stage) return 0;
+                const qipb_gate &g = gates[o.gate];
+                if (g.diagonal || g.k == 0) return 0;
+                u64 m = 0;
+                for (int j = 0; j < g.k; ++j) m |= 1ull << g.bits[j];
+                return m;
+            };
+            auto pairable = [&](size_t oi) {
+                const DevGate &d = f.g[oi];
+                return !ops[first + oi].stage && !d.diag && d.k == 2 && d.nins == 2 && d.post == 0 && d.in_or == 0 &&
+                       d.tl[0] != 0xFF && d.tl[1] != 0xFF && d.tl[0] >= lowb && d.tl[1] >= lowb;
+            };
+            for (size_t i = 0; i < cnt; ++i) {
+                if (!pairable(i)) continue;
+                u64 mid_support = 0, mid_nondiag = 0;
+                for (size_t j = i + 1; j < cnt && j - i < 200; ++j) {
+                    if (pairable(j) && !(nondiag(j) & (support(i) | mid_support)) && !(support(j) & (nondiag(i) | mid_nondiag))) {
+                        DevGate &a = f.g[i], &b = f.g[j];
+                        unsigned char pos4[4] = {a.tl[0], a.tl[1], b.tl[0], b.tl[1]};
+                        for (int x = 1; x < 4; ++x)
+                            for (int y = x; y > 0 && pos4[y] < pos4[y - 1]; --y) std::swap(pos4[y], pos4[y - 1]);
+                        for (int x = 0; x < 4; ++x) a.nmask[2 + x] = ~((1u << pos4[x]) - 1u);
+                        a.post = 4;
+                        a.pair = (unsigned char)(j - i);
+                        b.post = 5;
+                        break;
+                    }
+                    mid_support |= support(j);
+                    mid_nondiag |= nondiag(j);
                 }
             }
         }

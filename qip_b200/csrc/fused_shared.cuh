@@ -81,6 +81,7 @@ struct Op {
     bool stage;
     int gate;                 // !stage: index into the caller's gate list
     u64 common;               // stage: control bits shared by every gate of the stage
+    u64 support;              // stage: every bit one of its gates reads (targets and controls); pairing / commutation checks
     u32 tab_off;              // stage: offset of its tables in the table buffer
     int nout;
     std::vector<int> cells[FUSED_OUT_CELLS];

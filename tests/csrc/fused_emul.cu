@@ -65,10 +65,15 @@ int emulate(A *state, const FusedArgs &f, int *info) {
         info[4] += (!g.diag && g.k == 2 && g.mk != MK_GENERAL);
         info[5] += g.post == 2;
         info[6] += (!g.diag && g.k == 1 && g.mk == MK1_REAL);
+        info[8] += g.post == 4;
     }
     // the same choice of kernel instantiation as launch_fused (qip_b200/csrc/fused.cu)
     if (half) emulate_launch<A, true, 128, false>(state, f);
-    else if (uni && fused_has_ext(f)) {
+    else if (launch_is_wide(f, sizeof(A))) {
+        info[7] += fused_has_ext(f) ? 1 : 0;
+        info[9] += 1;
+        emulate_launch<A, true, 128, true>(state, f);
+    } else if (uni && fused_has_ext(f)) {
         info[7] += 1;
         emulate_launch<A, true, 256, true>(state, f);
     } else if (uni) emulate_launch<A, true, 256, false>(state, f);
@@ -79,11 +84,12 @@ int emulate(A *state, const FusedArgs &f, int *info) {
 }  // namespace
 
 // info[0] launches, [1] of which take the specialised (UNI) sweeps, [2] stages, [3] stages riding on a dense 1-qubit
-// sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates, [7] launches of the EXT kernel
+// sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates, [7] launches that carry EXT ops,
+// [8] block pairs (two dense 2-qubit blocks in one sweep), [9] launches of the WIDE kernel
 static int emul_impl(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
                      const qipb_gate *gates, int *info, bool fill) {
     QIPB_REQUIRE(host_state && info, "null argument");
-    for (int i = 0; i < 8; ++i) info[i] = 0;
+    for (int i = 0; i < 12; ++i) info[i] = 0;
     return lower_fused(
         nbits, dtype, ntile_bits, tile_bits, ngates, gates,
         [&](const std::vector<cplx> &tables, FusedArgs &f) {

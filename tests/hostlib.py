@@ -139,7 +139,7 @@ class HostLib(object):
 
     def _fused(self, fn, name, state, nbits, code, ntile, tile_bits, ngates, gates):
         self.log.append(name)
-        info = (ctypes.c_int * 8)()
+        info = (ctypes.c_int * 12)()
         rc = fn(_addr(state), nbits, code, ntile, tile_bits, ngates, gates, info)
         if rc:
             self.err = self.emul.qipb_emul_last_error()
