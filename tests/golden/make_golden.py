@@ -248,8 +248,8 @@ def layered_circuit(n, depth, seed):
 
 
 def record_configs():
-    # config 1: README CSwap (README.md:8-39 == tests/qiptest.py:194-228), 11 qubits, + Measure, seeds 0..7
-    for seed in range(8):
+    # config 1: README CSwap (README.md:8-39 == tests/qiptest.py:194-228), 11 qubits, + Measure, seeds 0..31
+    for seed in range(32):
         CURRENT_LABEL[0] = "config/cswap11_measure_seed%d" % seed
         random.seed(seed)
         q1, q2, q3 = Qubit(n=1), Qubit(n=5), Qubit(n=5)
