@@ -133,6 +133,10 @@ int qipb_apply_fused_fill(qipb_ctx *ctx, void *state, int nbits, int dtype, int 
  * (func_apply.pyx:97).                                                                        */
 int qipb_func_xor(qipb_ctx *ctx, void *state, int nbits, int dtype, int n1, const int *reg1_bits,
                   int n2, const int *reg2_bits, const long long *table_dev, uint64_t x_fixed);
+/* The same with a byte table, table_dev[x] = f(x) & 0xFF, for output registers of n2 <= 8 qubits: only the low n2
+ * bits of f(x) are used (func_apply.pyx:97), so the table -- read once per amplitude -- shrinks eightfold.       */
+int qipb_func_xor_u8(qipb_ctx *ctx, void *state, int nbits, int dtype, int n1, const int *reg1_bits,
+                     int n2, const int *reg2_bits, const unsigned char *table_dev, uint64_t x_fixed);
 
 /* ---- measurement -----------------------------------------------------------------------------
  * qipb_probabilities: out_dev[o] (+)= sum of |a_i|^2 over all i with (i & filter_mask) ==

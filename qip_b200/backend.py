@@ -394,11 +394,12 @@ class B200Backend(object):
         self.flush()
         with torch.cuda.device(self.device):
             self._stream()
-            dev_table = device_table(func, table, self.device)
-            _lib.check(self.L.qipb_func_xor(self.ctx, self._ptr(), n, self.code, len(reg1),
-                                            _lib.int_array([self.pos[q] for q in reg1]), len(reg2),
-                                            _lib.int_array([self.pos[q] for q in reg2]),
-                                            ctypes.c_void_p(dev_table.data_ptr()), 0))
+            dev_table, small = device_table(func, table, self.device, len(reg2))
+            entry = self.L.qipb_func_xor_u8 if small else self.L.qipb_func_xor
+            _lib.check(entry(self.ctx, self._ptr(), n, self.code, len(reg1),
+                             _lib.int_array([self.pos[q] for q in reg1]), len(reg2),
+                             _lib.int_array([self.pos[q] for q in reg2]),
+                             ctypes.c_void_p(dev_table.data_ptr()), 0))
             self._keepalive = dev_table
 
     # ------------------------------------------------------------------ measurement
@@ -709,24 +710,34 @@ def top_probabilities(probs_big_endian, top_k):
     return [int(i) for i in order], [float(probs[i]) for i in order]
 
 
-def device_table(func, table: np.ndarray, device):
-    """The int64 table of `func` on `device`.  Functions that carry their table (qip_b200.functions.tabulated, the
-    table functions of compiled circuits) keep the uploaded copy, so an iterated circuit -- Grover re-applies the same two
-    oracles every iteration (examples/grovers_iterative.py:20-39), 1 GiB of table each at 27 search qubits -- uploads
-    it once instead of once per application."""
+def device_table(func, table: np.ndarray, device, nbits_out: int = 64):
+    """The table of `func` on `device`: bytes holding f(x) & (2^nbits_out - 1) when the output register has at most 8
+    qubits (only those bits are used, qip/ext/func_apply.pyx:97 -- an eighth of the upload and of the table traffic of
+    qipb_func_xor_u8), int64 otherwise.  Functions that carry their table (qip_b200.functions.tabulated, the table
+    functions of compiled circuits) keep the uploaded copy, so an iterated circuit -- Grover re-applies the same two
+    oracles every iteration (examples/grovers_iterative.py:20-39) -- uploads it once instead of once per application.
+    Returns (device tensor, True if it is a byte table)."""
     torch = _torch()
+    small = nbits_out <= 8
+
+    def pack():
+        if small:
+            return torch.from_numpy((table & ((1 << nbits_out) - 1)).astype(np.uint8)).to(device)
+        return torch.from_numpy(table).to(device)
+
     carried = getattr(func, "table", None)
     if isinstance(carried, np.ndarray) and carried.shape == table.shape:
+        key = (str(device), nbits_out if small else 64)
         cached = getattr(func, "_device_table", None)
-        if cached is not None and cached[0] == str(device) and cached[1].shape[0] == table.shape[0]:
-            return cached[1]
-        dev = torch.from_numpy(table).to(device)
+        if cached is not None and cached[0] == key and cached[1].shape[0] == table.shape[0]:
+            return cached[1], small
+        dev = pack()
         try:
-            func._device_table = (str(device), dev)
+            func._device_table = (key, dev)
         except AttributeError:
             pass
-        return dev
-    return torch.from_numpy(table).to(device)
+        return dev, small
+    return pack(), small
 
 
 def tabulate(func, nbits_in: int) -> np.ndarray:

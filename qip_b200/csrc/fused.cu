@@ -26,6 +26,17 @@
 
 namespace qipb {
 
+// Block pairs (sweep_pair2: two disjoint dense 2-qubit blocks per sweep on 16-amplitude register groups) are compiled
+// out by default.  Measured on B200 (profiles/r02_wide_pairs.md): with both phases inlined the WIDE kernel needs more than
+// its 168 registers, ptxas then drops the warp-uniform descriptor loads of EVERY sweep of the kernel (coefficients come
+// through indexed LDC into vector registers instead of LDCU / UR operands) and spills; the pairs won 3 % on layered passes
+// and the kernel as a whole lost 5 %.  -DQIPB_ENABLE_PAIRS=1 builds them (tests/test_fused_emul.py covers the arithmetic).
+#ifndef QIPB_ENABLE_PAIRS
+#define QIPB_ENABLE_PAIRS 0
+#endif
+#ifndef QIPB_WIDE_MINB
+#define QIPB_WIDE_MINB 3
+#endif
 #define FUSED_THREADS 256
 #define FUSED_MAX_INS 12
 #define FUSED_MAX_OPS 96          // device ops per launch (a pass with more is split into several launches)
@@ -43,8 +54,8 @@ struct DevGate {
     unsigned char mk;       // dense 2-qubit block: MK_GENERAL / MK_REAL / MK_REALPHASE / MK_MONOMIAL (coefficient layout below)
     unsigned char phmask;   // MK_REALPHASE: columns with a non-trivial phase; MK_MONOMIAL: columns whose coefficient is not 1
     unsigned char perm;     // MK_MONOMIAL: bits 2j..2j+1 = the row that column j maps to
-    unsigned char pair;     // post == 4 (leader of a block pair, WIDE kernel): the partner is op gi + pair; its four sorted
-                            // expansion masks are nmask[2..5]
+    unsigned char pair;     // post == 4 (leader of a block pair, WIDE kernel; the partner is the NEXT op, post == 5): the
+                            // pair's four sorted expansion masks are nmask[2..5]
     u64 out_ctrl;           // state-index mask of controls outside the tile
     double2 m[16];
 };
@@ -310,10 +321,15 @@ QIPB_HD void sweep_mono2(A *tile, const DevGate &g, const EX ex, u32 ngroups, in
 // A monomial block (Swap, CX, phases folded in) is a phase per row plus a permutation of the STORE offsets.
 // Host guarantees (lower_fused): no in-tile controls on either block, the four targets distinct and above the
 // bank-conflict bits (so a quarter-warp always touches 8 consecutive amplitudes), ngroups = tile / 16 a multiple of NT.
-template <typename A, int MK, int STRIDE>
+// PK: the form a block takes inside a pair -- PK_GENERAL, PK_REAL (real matrix, optionally times column phases: MK_REAL /
+// MK_REALPHASE, the phase mask is a uniform branch) or PK_MONO.
+enum { PK_GENERAL = 0, PK_REAL = 1, PK_MONO = 2 };
+QIPB_HD int pair_kind(const DevGate &g) { return g.mk == MK_GENERAL ? PK_GENERAL : g.mk == MK_MONOMIAL ? PK_MONO : PK_REAL; }
+
+template <typename A, int PK, int STRIDE>
 QIPB_HD void pair_phase(A (&x)[16], const DevGate &g) {
     // STRIDE 4: the block acts on ia (members s, 4 + s, 8 + s, 12 + s);  STRIDE 1: on ib (members 4 s .. 4 s + 3)
-    if (MK == MK_MONOMIAL) {
+    if (PK == PK_MONO) {
         const u32 phmask = g.phmask;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -326,7 +342,7 @@ QIPB_HD void pair_phase(A (&x)[16], const DevGate &g) {
                 }
             }
     } else {
-        const Block2<A, MK> blk(g);
+        const Block2<A, PK == PK_GENERAL ? MK_GENERAL : MK_REALPHASE> blk(g);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const int b = STRIDE == 4 ? s : 4 * s;
@@ -340,18 +356,10 @@ QIPB_HD void pair_phase(A (&x)[16], const DevGate &g) {
     }
 }
 
-template <typename A, int STRIDE>
-QIPB_HD void pair_phase_any(A (&x)[16], const DevGate &g) {
-    switch (g.mk) {                                           // uniform: the form comes from the descriptor
-    case MK_REAL: pair_phase<A, MK_REAL, STRIDE>(x, g); break;
-    case MK_REALPHASE: pair_phase<A, MK_REALPHASE, STRIDE>(x, g); break;
-    case MK_MONOMIAL: pair_phase<A, MK_MONOMIAL, STRIDE>(x, g); break;
-    default: pair_phase<A, MK_GENERAL, STRIDE>(x, g); break;
-    }
-}
-
-template <typename A, int NT>
-QIPB_HD void sweep_pair2(A *tile, const DevGate &ga, const DevGate &gb, u32 ngroups, int tid) {
+// one loop per combination of forms: the descriptors are read with warp-uniform addresses (ga = f.g[gi], gb = f.g[gi + 1])
+// and nothing but LDS / FP64 / STS is left inside
+template <typename A, int NT, int PKA, int PKB>
+QIPB_HD void sweep_pair2_k(A *tile, const DevGate &ga, const DevGate &gb, u32 ngroups, int tid) {
     const u32 nm0 = ga.nmask[2], nm1 = ga.nmask[3], nm2 = ga.nmask[4], nm3 = ga.nmask[5];
     u32 ldA[4], ldB[4], stA[4], stB[4];
     {
@@ -363,8 +371,8 @@ QIPB_HD void sweep_pair2(A *tile, const DevGate &ga, const DevGate &gb, u32 ngro
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                         // column j of a monomial block lands in row perm[j]
-            const u32 ra = ga.mk == MK_MONOMIAL ? (ga.perm >> (2 * j)) & 3u : (u32)j;
-            const u32 rb = gb.mk == MK_MONOMIAL ? (gb.perm >> (2 * j)) & 3u : (u32)j;
+            const u32 ra = PKA == PK_MONO ? (ga.perm >> (2 * j)) & 3u : (u32)j;
+            const u32 rb = PKB == PK_MONO ? (gb.perm >> (2 * j)) & 3u : (u32)j;
             stA[j] = ((ra & 2u) ? oah : 0u) + ((ra & 1u) ? oal : 0u);
             stB[j] = ((rb & 2u) ? obh : 0u) + ((rb & 1u) ? obl : 0u);
         }
@@ -380,10 +388,28 @@ QIPB_HD void sweep_pair2(A *tile, const DevGate &ga, const DevGate &gb, u32 ngro
         A x[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = p[ldA[k >> 2] + ldB[k & 3]];
-        pair_phase_any<A, 4>(x, ga);
-        pair_phase_any<A, 1>(x, gb);
+        pair_phase<A, PKA, 4>(x, ga);
+        pair_phase<A, PKB, 1>(x, gb);
 #pragma unroll
         for (int k = 0; k < 16; ++k) p[stA[k >> 2] + stB[k & 3]] = x[k];
+    }
+}
+
+template <typename A, int NT>
+QIPB_HD void sweep_pair2(A *tile, const DevGate &ga, const DevGate &gb, u32 ngroups, int tid) {
+    const int ka = pair_kind(ga), kb = pair_kind(gb);          // uniform: the forms come from the descriptors
+    if (ka == PK_GENERAL) {
+        if (kb == PK_GENERAL) sweep_pair2_k<A, NT, PK_GENERAL, PK_GENERAL>(tile, ga, gb, ngroups, tid);
+        else if (kb == PK_REAL) sweep_pair2_k<A, NT, PK_GENERAL, PK_REAL>(tile, ga, gb, ngroups, tid);
+        else sweep_pair2_k<A, NT, PK_GENERAL, PK_MONO>(tile, ga, gb, ngroups, tid);
+    } else if (ka == PK_REAL) {
+        if (kb == PK_GENERAL) sweep_pair2_k<A, NT, PK_REAL, PK_GENERAL>(tile, ga, gb, ngroups, tid);
+        else if (kb == PK_REAL) sweep_pair2_k<A, NT, PK_REAL, PK_REAL>(tile, ga, gb, ngroups, tid);
+        else sweep_pair2_k<A, NT, PK_REAL, PK_MONO>(tile, ga, gb, ngroups, tid);
+    } else {
+        if (kb == PK_GENERAL) sweep_pair2_k<A, NT, PK_MONO, PK_GENERAL>(tile, ga, gb, ngroups, tid);
+        else if (kb == PK_REAL) sweep_pair2_k<A, NT, PK_MONO, PK_REAL>(tile, ga, gb, ngroups, tid);
+        else sweep_pair2_k<A, NT, PK_MONO, PK_MONO>(tile, ga, gb, ngroups, tid);
     }
 }
 
@@ -702,7 +728,7 @@ QIPB_HD void sweep_stage_fill(A *tile, const StageRef sr, u32 n, int tid) {
     const double2 SL = cmul<double2>(sr.S, sr.T[(u32)tid & (sr.nlo - 1u)]);   // NT is a multiple of 2^lo: low bits are sweep-invariant
     const int lo = sr.lo;
 #pragma unroll 4
-    for (u32 x = tid; x < n; x += NT) {
+    for (u32 it = 0, nit = n / NT, x = tid; it < nit; ++it, x += NT) {   // warp-uniform trip count (n is a multiple of NT)
         const double2 v = cmul<double2>(SL, Th[x >> lo]);
         tile[x] = make_amp<A>((R)v.x, (R)v.y);
     }
@@ -868,14 +894,15 @@ template <typename A, bool UNI, int NT, bool EXT>
 QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *stage_S, u64 base, u32 tsize, int tid) {
     if (EXT) {
         const DevGate &g = f.g[gi];
-        if (g.post == 4) {                                      // block pair (WIDE launches only): ops gi and gi + pair
-            const DevGate &h = f.g[gi + g.pair];
+        if (QIPB_ENABLE_PAIRS && NT == 128 && g.post == 4) {                                      // block pair (WIDE launches only): ops gi and gi + 1
+            const DevGate &h = f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi];
             const bool on_a = (base & g.out_ctrl) == g.out_ctrl, on_b = (base & h.out_ctrl) == h.out_ctrl;
             if (on_a && on_b) {
                 sweep_pair2<A, NT>(tile, g, h, tsize >> 4, tid);
-            } else if (on_a || on_b) {                          // one of them is switched off on this tile
-                const DevGate &one = on_a ? g : h;
-                run_op<A, UNI, NT>(tile, one, one, f.tables, stage_S, gi, base, f.tb, tsize, tid);
+            } else if (on_a) {                                  // the other one is switched off on this tile
+                run_op<A, UNI, NT>(tile, g, g, f.tables, stage_S, gi, base, f.tb, tsize, tid);
+            } else if (on_b) {
+                run_op<A, UNI, NT>(tile, h, h, f.tables, stage_S, gi, base, f.tb, tsize, tid);
             }
             return;
         }
@@ -907,7 +934,7 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
 // budget per thread doubles (168 / 128), which is what the 16-amplitude register groups of the block pairs and the EXT
 // forms need (the 256-thread EXT kernel spilled at its 80-register cap).
 template <typename A, bool BULK, bool UNI, int NT, bool EXT, bool WIDE = false>
-__global__ void __launch_bounds__(NT, (sizeof(A) == 16 ? 3 : 4) * (WIDE ? 1 : 256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+__global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB : 4) : (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ __align__(16) double2 stage_S[FUSED_MAX_OPS + 1];
@@ -1126,7 +1153,8 @@ static bool wide_enabled() {
 }
 
 static bool pair_enabled() {
-    const char *e = getenv("QIPB_FUSED_PAIR");                // block pairs of the WIDE kernel (default on; A/B knob, read per call)
+    if (!QIPB_ENABLE_PAIRS) return false;                      // compiled out (see QIPB_ENABLE_PAIRS above)
+    const char *e = getenv("QIPB_FUSED_PAIR");                // A/B knob of builds that carry them, read per call
     return !e || atoi(e) != 0;
 }
 
@@ -1230,6 +1258,9 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
         QIPB_CUDA(cudaFuncSetAttribute(fused_kernel<A, B, U, T, X, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         fused_kernel<A, B, U, T, X, ##__VA_ARGS__><<<(unsigned)grid, T, smem, ctx->stream>>>(state, f);                                      \
     } while (0)
+#ifdef QIPB_PROBE_WIDE_ONLY   /* compile-time probe (scripts/sass_probe.sh): only the WIDE complex128 kernel is instantiated */
+    if constexpr (sizeof(A) == 16) QIPB_LAUNCH_FUSED(true, true, 128, true, true);
+#else
     if (uni && !half && ring_enabled() && f.ntiles >= 4ull * (u64)ctx->sm_count && (tsize_runs(f) <= 128)) {
         constexpr int NBUF = sizeof(A) == 16 ? 3 : 6;
         const size_t rsmem = (size_t)NBUF * smem;
@@ -1246,6 +1277,7 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
     } else if (uni) QIPB_LAUNCH_FUSED(true, true, 256, false);
     else if (bulk) QIPB_LAUNCH_FUSED(true, false, 256, false);
     else QIPB_LAUNCH_FUSED(false, false, 256, false);
+#endif
 #undef QIPB_LAUNCH_FUSED
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
@@ -1630,8 +1662,10 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
         // side must avoid everything the other side reads (targets and controls; diagonal ops only read).
         if (pair_enabled() && launch_is_wide(f, dtype == QIPB_C128 ? 16 : 8)) {
             const int lowb = dtype == QIPB_C128 ? 3 : 4;       // LowBits<A>
+            std::vector<int> origin(cnt);                      // position in f.g -> index of its Op (positions move below)
+            for (size_t oi = 0; oi < cnt; ++oi) origin[oi] = (int)(first + oi);
             auto support = [&](size_t oi) -> u64 {
-                const Op &o = ops[first + oi];
+                const Op &o = ops[origin[oi]];
                 if (o.stage) return o.support;
                 const qipb_gate &g = gates[o.gate];
                 u64 m = g.ctrl_mask;
@@ -1639,7 +1673,7 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                 return m;
             };
             auto nondiag = [&](size_t oi) -> u64 {
-                const Op &o = ops[first + oi];
+                const Op &o = ops[origin[oi]];
                 if (o.stage) return 0;
                 const qipb_gate &g = gates[o.gate];
                 if (g.diagonal || g.k == 0) return 0;
@@ -1649,22 +1683,32 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
             };
             auto pairable = [&](size_t oi) {
                 const DevGate &d = f.g[oi];
-                return !ops[first + oi].stage && !d.diag && d.k == 2 && d.nins == 2 && d.post == 0 && d.in_or == 0 &&
+                return !ops[origin[oi]].stage && !d.diag && d.k == 2 && d.nins == 2 && d.post == 0 && d.in_or == 0 &&
                        d.tl[0] != 0xFF && d.tl[1] != 0xFF && d.tl[0] >= lowb && d.tl[1] >= lowb;
             };
-            for (size_t i = 0; i < cnt; ++i) {
+            for (size_t i = 0; i + 1 < cnt; ++i) {
                 if (!pairable(i)) continue;
                 u64 mid_support = 0, mid_nondiag = 0;
-                for (size_t j = i + 1; j < cnt && j - i < 200; ++j) {
+                for (size_t j = i + 1; j < cnt; ++j) {
                     if (pairable(j) && !(nondiag(j) & (support(i) | mid_support)) && !(support(j) & (nondiag(i) | mid_nondiag))) {
-                        DevGate &a = f.g[i], &b = f.g[j];
+                        // the partner moves next to the leader: rotate positions i + 1 .. j (descriptors and their origin)
+                        const DevGate moved = f.g[j];
+                        const int moved_from = origin[j];
+                        for (size_t t = j; t > i + 1; --t) {
+                            f.g[t] = f.g[t - 1];
+                            origin[t] = origin[t - 1];
+                        }
+                        f.g[i + 1] = moved;
+                        origin[i + 1] = moved_from;
+                        DevGate &a = f.g[i], &b = f.g[i + 1];
                         unsigned char pos4[4] = {a.tl[0], a.tl[1], b.tl[0], b.tl[1]};
                         for (int x = 1; x < 4; ++x)
                             for (int y = x; y > 0 && pos4[y] < pos4[y - 1]; --y) std::swap(pos4[y], pos4[y - 1]);
                         for (int x = 0; x < 4; ++x) a.nmask[2 + x] = ~((1u << pos4[x]) - 1u);
                         a.post = 4;
-                        a.pair = (unsigned char)(j - i);
+                        a.pair = 1;
                         b.post = 5;
+                        ++i;                                       // the partner is taken
                         break;
                     }
                     mid_support |= support(j);
@@ -1675,15 +1719,25 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
         f.nstages = 0;
         for (size_t oi = 0; oi < cnt; ++oi) f.nstages += f.g[oi].diag >= 2;
         if (getenv("QIPB_DEBUG")) {
-            int nst = 0, npost = 0, ndense = 0, ndiag = 0;
+            int nst = 0, npost = 0, ndiag = 0, npair = 0, nqft2 = 0, d1 = 0, d1real = 0, mk[4] = {0, 0, 0, 0}, low2 = 0, ctl2 = 0, sweeps = 0;
             for (size_t oi = 0; oi < cnt; ++oi) {
-                nst += f.g[oi].diag >= 2;
-                npost += f.g[oi].post != 0;
-                ndense += f.g[oi].diag == 0;
-                ndiag += f.g[oi].diag == 1;
+                const DevGate &g = f.g[oi];
+                nst += g.diag >= 2;
+                npost += g.post == 1;
+                ndiag += g.diag == 1;
+                npair += g.post == 4;
+                nqft2 += g.post == 2;
+                if (!g.diag && g.k == 2) {
+                    mk[g.mk & 3]++;
+                    low2 += g.nins == 2 && (g.tl[0] < 3 || g.tl[1] < 3);
+                    ctl2 += g.nins > 2;
+                }
+                if (!g.diag && g.k == 1) { d1++; d1real += g.mk == MK1_REAL; }
+                sweeps += !(g.diag == 3 || g.post == 3 || g.post == 5);
             }
-            fprintf(stderr, "[qipb] fused launch: %d input gates -> %d ops (dense %d, lone diagonal %d, stages %d of which %d ride on a dense gate), tables %zu\n",
-                    ngates, (int)cnt, ndense, ndiag, nst, npost, tables.size());
+            fprintf(stderr, "[qipb] fused launch: %d gates -> %d ops, %d sweeps | 2q general %d real %d realphase %d mono %d (low-bit %d, in-tile ctrl %d, pairs %d) | "
+                            "1q %d (real %d, +stage %d, qft2 %d) | lone diag %d | stages %d | tables %zu\n",
+                    ngates, (int)cnt, sweeps, mk[0], mk[1], mk[2], mk[3], low2, ctl2, npair, d1, d1real, npost, nqft2, ndiag, nst, tables.size());
         }
         int rc = launch(f);
         if (rc) return rc;

@@ -115,8 +115,10 @@ struct FuncArgs {
     BitRuns yruns;        // y -> state index bits of reg2
 };
 
-template <typename A>
-__global__ void __launch_bounds__(256) func_xor_kernel(A *__restrict__ state, const long long *__restrict__ table,
+// TAB: long long (the general table) or unsigned char (|reg2| <= 8: the only bits of f(x) that matter, func_apply.pyx:97,
+// fit a byte -- an eighth of the table traffic and of the upload; a Grover oracle on 27 search qubits is 128 MiB, not 1 GiB)
+template <typename A, typename TAB>
+__global__ void __launch_bounds__(256) func_xor_kernel(A *__restrict__ state, const TAB *__restrict__ table,
                                                        const __grid_constant__ FuncArgs f) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= f.n) return;
@@ -211,8 +213,9 @@ extern "C" int qipb_init_kron(qipb_ctx *ctx, void *state, int nbits, int dtype, 
     return QIPB_OK;
 }
 
-extern "C" int qipb_func_xor(qipb_ctx *ctx, void *state, int nbits, int dtype, int n1, const int *reg1_bits, int n2,
-                             const int *reg2_bits, const long long *table_dev, uint64_t x_fixed) {
+template <typename TAB>
+static int func_xor_impl(qipb_ctx *ctx, void *state, int nbits, int dtype, int n1, const int *reg1_bits, int n2,
+                         const int *reg2_bits, const TAB *table_dev, uint64_t x_fixed) {
     QIPB_REQUIRE(ctx && state && table_dev, "null argument");
     QIPB_REQUIRE(nbits >= 0 && nbits <= 40 && n1 >= 0 && n2 >= 0 && n1 <= 62 && n2 <= nbits && n2 <= 62, "bad register sizes");
     QIPB_CUDA(cudaSetDevice(ctx->device));
@@ -243,10 +246,21 @@ extern "C" int qipb_func_xor(qipb_ctx *ctx, void *state, int nbits, int dtype, i
     rc = build_runs(f.yruns, n2, src, dst);
     if (rc) return rc;
     const u64 blocks = (f.n + 255) / 256;
-    if (dtype == QIPB_C128) func_xor_kernel<double2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)state, table_dev, f);
-    else if (dtype == QIPB_C64) func_xor_kernel<float2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)state, table_dev, f);
+    if (dtype == QIPB_C128) func_xor_kernel<double2, TAB><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2 *)state, table_dev, f);
+    else if (dtype == QIPB_C64) func_xor_kernel<float2, TAB><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float2 *)state, table_dev, f);
     else QIPB_REQUIRE(false, "unknown dtype %d", dtype);
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
     return QIPB_OK;
+}
+
+extern "C" int qipb_func_xor(qipb_ctx *ctx, void *state, int nbits, int dtype, int n1, const int *reg1_bits, int n2,
+                             const int *reg2_bits, const long long *table_dev, uint64_t x_fixed) {
+    return func_xor_impl<long long>(ctx, state, nbits, dtype, n1, reg1_bits, n2, reg2_bits, table_dev, x_fixed);
+}
+
+extern "C" int qipb_func_xor_u8(qipb_ctx *ctx, void *state, int nbits, int dtype, int n1, const int *reg1_bits, int n2,
+                                const int *reg2_bits, const unsigned char *table_dev, uint64_t x_fixed) {
+    QIPB_REQUIRE(n2 <= 8, "a byte table holds at most 8 output bits (n2 = %d)", n2);
+    return func_xor_impl<unsigned char>(ctx, state, nbits, dtype, n1, reg1_bits, n2, reg2_bits, table_dev, x_fixed);
 }

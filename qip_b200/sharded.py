@@ -547,10 +547,11 @@ class ShardedB200Backend(object):
         with torch.cuda.device(self.device):
             self._stream()
             from .backend import device_table
-            dev_table = device_table(func, table, self.device)
-            _lib.check(self.L.qipb_func_xor(self.ctx, self.ptr, self.nl, self.code, len(reg1), _lib.int_array(r1bits),
-                                            len(reg2), _lib.int_array([self.layout.pos[q] for q in reg2]),
-                                            ctypes.c_void_p(dev_table.data_ptr()), x_fixed))
+            dev_table, small = device_table(func, table, self.device, len(reg2))
+            entry = self.L.qipb_func_xor_u8 if small else self.L.qipb_func_xor
+            _lib.check(entry(self.ctx, self.ptr, self.nl, self.code, len(reg1), _lib.int_array(r1bits),
+                             len(reg2), _lib.int_array([self.layout.pos[q] for q in reg2]),
+                             ctypes.c_void_p(dev_table.data_ptr()), x_fixed))
             self._keep = dev_table
 
     # ------------------------------------------------------------------ measurement

@@ -23,7 +23,6 @@ except Exception as e:
 PY
  done
 }
-run wide1_pair1 QIPB_FUSED_WIDE=1 QIPB_FUSED_PAIR=1
-run wide1_pair0 QIPB_FUSED_WIDE=1 QIPB_FUSED_PAIR=0
-run wide1_pair0_ext0 QIPB_FUSED_WIDE=1 QIPB_FUSED_PAIR=0 QIPB_FUSED_EXT=0
+run wide1 QIPB_FUSED_WIDE=1
 run wide0 QIPB_FUSED_WIDE=0
+run wide1_ext0 QIPB_FUSED_WIDE=1 QIPB_FUSED_EXT=0

@@ -155,7 +155,11 @@ class HostLib(object):
         return self._fused(self.emul.qipb_emul_fused_fill, "apply_fused_fill", state, nbits, code, ntile, tile_bits, ngates, gates)
 
     # ---- func_apply ----
-    def qipb_func_xor(self, ctx, state, nbits, code, n1, reg1, n2, reg2, table, x_fixed):
+    def qipb_func_xor_u8(self, ctx, state, nbits, code, n1, reg1, n2, reg2, table, x_fixed):
+        assert n2 <= 8
+        return self.qipb_func_xor(ctx, state, nbits, code, n1, reg1, n2, reg2, table, x_fixed, tab_dtype=np.uint8)
+
+    def qipb_func_xor(self, ctx, state, nbits, code, n1, reg1, n2, reg2, table, x_fixed, tab_dtype=np.int64):
         self.log.append("func_xor")
         a = _amps(state, nbits, code)
         i = np.arange(1 << nbits, dtype=np.int64)
@@ -164,7 +168,7 @@ class HostLib(object):
         for j, b in enumerate(r1):                   # most significant register bit first
             if b >= 0:
                 x |= ((i >> b) & 1) << (n1 - 1 - j)
-        t = _view(table, 1 << n1, np.int64)
+        t = _view(table, 1 << n1, tab_dtype).astype(np.int64)
         y = t[x] & ((1 << n2) - 1)
         flip = np.zeros_like(i)
         r2 = _ints(reg2, n2)

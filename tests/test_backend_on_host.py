@@ -140,9 +140,9 @@ def test_function_tables_are_uploaded_once_per_function_object(monkeypatch):
     uploads = []
     real = be.device_table
 
-    def counting(func, table, device):
+    def counting(func, table, device, nbits_out=64):
         before = getattr(func, "_device_table", None)
-        out = real(func, table, device)
+        out = real(func, table, device, nbits_out)
         if getattr(func, "_device_table", None) is not before or not hasattr(func, "table"):
             uploads.append(1)
         return out
