@@ -115,6 +115,16 @@ typedef struct {
 int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits,
                      const int *tile_bits, int ngates, const qipb_gate *gates);
 
+/* qipb_apply_fused_chunk: the same pass restricted to ONE CHUNK of the state -- the amplitudes whose nfix (0..4)
+ * index bits fix_bits (none of them a tile bit) equal fix_value (a mask over those bits).  The 2^nfix chunks
+ * partition the state and the pass acts on each of them independently (no gate of a pass is non-diagonal on a bit
+ * outside the tile), so running every chunk once equals qipb_apply_fused.  The sharded engine uses it to pipeline a
+ * pass against the NVLink exchange of the neighbouring chunk (qipb_peer_remap_chunk); it stands where the reference's
+ * workers interleave compute and socket traffic per 2048-amplitude message (qip/distributed/worker/worker.py:302-357). */
+int qipb_apply_fused_chunk(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits,
+                           const int *tile_bits, int ngates, const qipb_gate *gates,
+                           int nfix, const int *fix_bits, uint64_t fix_value);
+
 /* qipb_apply_fused_fill: the same pass applied to the ALL-ONES vector; the buffer's previous content is never
  * read.  A product state of one-qubit feeds v_b is prod_b diag(v_b[0], v_b[1]) . ones, so a caller that leads the
  * gate list with those diagonal gates gets "kron-product init (qip/backend.py:88-101) + first gate pass" in one
@@ -178,6 +188,9 @@ int qipb_add_range(qipb_ctx *ctx, void *state, int dtype, uint64_t start, uint64
  * qipb_peer_remap: g (1..3) rank bits <-> g local bits in ONE kernel over up to 7 peers: peers[b] is the
  *   mapped shard of the rank whose g rank bits have value b (entry my_value is ignored), lbits[t] the
  *   local bit paired with value bit t.  Moves (1 - 2^-g) of a shard per direction.
+ * qipb_peer_remap_chunk: the same exchange restricted to the chunk whose nfix (0..4) local bits fix_bits (none of
+ *   them exchanged) equal fix_value; every rank must pass the same chunk.  max_ctas > 0 bounds the grid (CTAs per
+ *   partner; a persistent, grid-striding launch that shares the SMs with a concurrently running fused pass).
  * qipb_peer_gate1: the fused compute+exchange kernel for a 1-qubit gate whose target is a GLOBAL
  *   (rank) bit: for count amplitudes, (lo, hi) <- mat * (lo, hi) where `lo` lives on the shard
  *   whose rank bit is 0 and `hi` on its partner.  The caller that owns `local` passes
@@ -191,6 +204,9 @@ int qipb_peer_swap_bit(qipb_ctx *ctx, void *local, void *peer, int nbits, int dt
                        int my_gbit, uint64_t w_begin, uint64_t count);
 int qipb_peer_remap(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g,
                     const int *lbits, int my_value);
+int qipb_peer_remap_chunk(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g,
+                          const int *lbits, int my_value, int nfix, const int *fix_bits,
+                          uint64_t fix_value, int max_ctas);
 int qipb_peer_gate1(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t off,
                     uint64_t count, const double *mat, int local_is_hi, uint64_t ctrl_mask);
 

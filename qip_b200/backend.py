@@ -293,6 +293,19 @@ class B200Backend(object):
         _lib.check(self.L.qipb_apply_fused(self.ctx, self._ptr(), self.n, self.code, len(p.tile_bits),
                                            packed[1], len(p.gates), packed[0]))
 
+    def sm_count(self) -> int:
+        try:
+            return int(_torch().cuda.get_device_properties(self.device).multi_processor_count)
+        except Exception:
+            return 148
+
+    def _launch_fused_chunk(self, p: Pass, fix_bits, fix_value: int):
+        """The fused pass on ONE chunk of the state: the amplitudes whose index bits `fix_bits` (none of them a tile
+        bit of the pass) have the values in the mask `fix_value` (qipb_apply_fused_chunk)."""
+        packed = pack_pass(p)
+        _lib.check(self.L.qipb_apply_fused_chunk(self.ctx, self._ptr(), self.n, self.code, len(p.tile_bits), packed[1],
+                                                 len(p.gates), packed[0], len(fix_bits), _lib.int_array(fix_bits), fix_value))
+
     def flush(self) -> None:
         """Execute every queued gate.  Called before anything reads or measures the state."""
         if not self.queue:

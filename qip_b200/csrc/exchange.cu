@@ -59,12 +59,18 @@ __global__ void __launch_bounds__(256) peer_swap_bit_kernel(A *__restrict__ loca
 // sub-block pair are indexed by w; the rank with the smaller value handles the first half of w, the
 // other one the second half, so every link direction and every GPU carries the same load:
 // (1 - 2^-g) of a shard per direction in total, against g/2 shards for g pairwise swaps.
+// Chunks: the remap may be restricted to the amplitudes whose `fix` local bits (at most 4, none of them exchanged) have
+// a given value -- the sharded engine exchanges a state chunk by chunk so that the NVLink traffic of one chunk runs
+// under the fused passes of its neighbours (qipb_peer_remap_chunk).  A chunked launch is PERSISTENT: a bounded number of
+// CTAs strides over the work, so that it can share the SMs with a fused pass instead of queueing millions of CTAs.
 struct RemapArgs {
     void *peers[8];               // indexed by b
-    u64 half;                     // 2^(nbits - g - 1)
-    int g, a;
+    u64 half;                     // 2^(nbits - g - nfix - 1): pairs per (sub-block pair, rank of the pair)
+    u64 nblocks;                  // ceil(half / (256 * U))
+    u64 fix_value;                // index bits of the chunk
+    int g, a, nins;
     unsigned char lbit[4];        // the local bit positions, lbit[t] pairs with value bit t
-    unsigned char ins[4];         // the same positions ascending (for zero insertion)
+    unsigned char ins[8];         // exchanged and fixed positions, ascending (for zero insertion)
 };
 
 template <typename A, int U>
@@ -80,22 +86,26 @@ __global__ void __launch_bounds__(256) peer_remap_kernel(A *__restrict__ local, 
         psel |= (u64)((r.a >> t) & 1) << r.lbit[t];
     }
     const u64 w0 = r.a < b ? 0 : r.half;
-    A x[U], y[U];
-    u64 li[U], pi[U];
-    bool live[U];
+    lsel |= r.fix_value;
+    psel |= r.fix_value;
+    for (u64 blk = blockIdx.x; blk < r.nblocks; blk += gridDim.x) {
+        A x[U], y[U];
+        u64 li[U], pi[U];
+        bool live[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const u64 t = ((u64)blockIdx.x * U + u) * blockDim.x + threadIdx.x;
-        live[u] = t < r.half;
-        u64 base = w0 + t;
-        for (int q = 0; q < r.g; ++q) base = insert_zero(base, r.ins[q]);
-        li[u] = base | lsel;
-        pi[u] = base | psel;
-        if (live[u]) { x[u] = local[li[u]]; y[u] = peer[pi[u]]; }
+        for (int u = 0; u < U; ++u) {
+            const u64 t = (blk * U + u) * blockDim.x + threadIdx.x;
+            live[u] = t < r.half;
+            u64 base = w0 + t;
+            for (int q = 0; q < r.nins; ++q) base = insert_zero(base, r.ins[q]);
+            li[u] = base | lsel;
+            pi[u] = base | psel;
+            if (live[u]) { x[u] = local[li[u]]; y[u] = peer[pi[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (live[u]) { local[li[u]] = y[u]; peer[pi[u]] = x[u]; }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (live[u]) { local[li[u]] = y[u]; peer[pi[u]] = x[u]; }
 }
 
 struct PeerGateArgs {
@@ -193,30 +203,39 @@ extern "C" int qipb_peer_swap_bit(qipb_ctx *ctx, void *local, void *peer, int nb
     return QIPB_OK;
 }
 
-extern "C" int qipb_peer_remap(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g,
-                               const int *lbits, int my_value) {
+static int peer_remap_impl(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g, const int *lbits,
+                           int my_value, int nfix, const int *fix_bits, uint64_t fix_value, int max_ctas) {
     QIPB_REQUIRE(ctx && local && peers && lbits, "null argument");
-    QIPB_REQUIRE(g >= 1 && g <= 3 && nbits > g && nbits <= 40 && my_value >= 0 && my_value < (1 << g), "bad peer_remap arguments");
+    QIPB_REQUIRE(g >= 1 && g <= 3 && nfix >= 0 && nfix <= 4 && (nfix == 0 || fix_bits) && nbits > g + nfix && nbits <= 40 &&
+                 my_value >= 0 && my_value < (1 << g), "bad peer_remap arguments");
     QIPB_CUDA(cudaSetDevice(ctx->device));
     RemapArgs r;
     memset(&r, 0, sizeof(r));
     r.g = g;
     r.a = my_value;
-    r.half = 1ull << (nbits - g - 1);
-    u64 seen = 0;
+    r.half = 1ull << (nbits - g - nfix - 1);
+    u64 seen = 0, fmask = 0;
     for (int t = 0; t < g; ++t) {
         QIPB_REQUIRE(lbits[t] >= 0 && lbits[t] < nbits && !((seen >> lbits[t]) & 1ull), "bad local bit %d", lbits[t]);
         seen |= 1ull << lbits[t];
         r.lbit[t] = (unsigned char)lbits[t];
     }
-    int n = 0;
+    for (int t = 0; t < nfix; ++t) {
+        QIPB_REQUIRE(fix_bits[t] >= 0 && fix_bits[t] < nbits && !((seen >> fix_bits[t]) & 1ull), "bad fixed bit %d", fix_bits[t]);
+        seen |= 1ull << fix_bits[t];
+        fmask |= 1ull << fix_bits[t];
+    }
+    QIPB_REQUIRE((fix_value & ~fmask) == 0, "chunk value has bits outside the fixed bits");
+    r.fix_value = fix_value;
     for (int b = 0; b < nbits; ++b)
-        if ((seen >> b) & 1ull) r.ins[n++] = (unsigned char)b;
+        if ((seen >> b) & 1ull) r.ins[r.nins++] = (unsigned char)b;
     for (int b = 0; b < (1 << g); ++b) {
         QIPB_REQUIRE(b == my_value || peers[b], "missing peer pointer for value %d", b);
         r.peers[b] = peers[b];
     }
-    const u64 bx = (r.half + 256ull * 4 - 1) / (256ull * 4);
+    r.nblocks = (r.half + 256ull * 4 - 1) / (256ull * 4);
+    u64 bx = r.nblocks;
+    if (max_ctas > 0 && bx > (u64)max_ctas) bx = (u64)max_ctas;        // persistent: blockIdx.x strides over nblocks
     QIPB_REQUIRE(bx <= 0x7fffffffull, "grid too large");
     dim3 grid((unsigned)bx, (unsigned)((1 << g) - 1));
     if (dtype == QIPB_C128) peer_remap_kernel<double2, 4><<<grid, 256, 0, ctx->stream>>>((double2 *)local, r);
@@ -225,6 +244,17 @@ extern "C" int qipb_peer_remap(qipb_ctx *ctx, void *local, void *const *peers, i
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
     return QIPB_OK;
+}
+
+extern "C" int qipb_peer_remap(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g,
+                               const int *lbits, int my_value) {
+    return peer_remap_impl(ctx, local, peers, nbits, dtype, g, lbits, my_value, 0, nullptr, 0, 0);
+}
+
+extern "C" int qipb_peer_remap_chunk(qipb_ctx *ctx, void *local, void *const *peers, int nbits, int dtype, int g,
+                                     const int *lbits, int my_value, int nfix, const int *fix_bits, uint64_t fix_value,
+                                     int max_ctas) {
+    return peer_remap_impl(ctx, local, peers, nbits, dtype, g, lbits, my_value, nfix, fix_bits, fix_value, max_ctas);
 }
 
 extern "C" int qipb_peer_gate1(qipb_ctx *ctx, void *local, void *peer, int dtype, uint64_t off, uint64_t count,

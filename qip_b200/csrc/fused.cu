@@ -68,9 +68,24 @@ struct FusedArgs {
     u64 ntiles;
     const double2 *tables;              // stage tables (global memory)
     unsigned char tbit[16];             // tile-local bit -> state bit, ascending
+    // Tile enumeration.  A launch may be restricted to a CHUNK of the state: the amplitudes whose `fix` bits (state-index
+    // bits outside the tile, at most 4) have a given value (qipb_apply_fused_chunk; the sharded engine pipelines a pass
+    // chunk by chunk against the NVLink exchange of the neighbouring chunk).  ebit = tile bits and fix bits merged,
+    // ascending: tile number t -> base index by inserting a zero at each of them, then OR fix_value.  To the gates a
+    // fix bit is an ordinary outside bit (controls, diagonal targets and stage cells read it from the base index).
+    int nexp;
+    unsigned char ebit[20];
+    u64 fix_value;
     DevGate g[FUSED_MAX_OPS];
 };
 static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel parameter space");
+
+// base index of tile t (all tile-local bits 0)
+QIPB_HD u64 fused_tile_base(const FusedArgs &f, u64 t) {
+    u64 base = t;
+    for (int j = 0; j < f.nexp; ++j) base = insert_zero(base, f.ebit[j]);
+    return base | f.fix_value;
+}
 
 // ---- device side --------------------------------------------------------------------------------
 // Every gate is one sweep over the tile in shared memory.  The sweeps are specialised on the number
@@ -955,8 +970,7 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
     u32 parity = 0;
 
     for (u64 t = blockIdx.x; t < f.ntiles; t += gridDim.x) {
-        u64 base = t;
-        for (int j = 0; j < f.tb; ++j) base = insert_zero(base, f.tbit[j]);
+        const u64 base = fused_tile_base(f, t);
 
         // ---- stage the tile: runs of 2^lowrun consecutive amplitudes ----
         if (EXT && f.g[0].diag == 5) {                          // fill mode: nothing is loaded, op 0 writes the tile
@@ -972,8 +986,7 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
                 // floor (profiles/r01_probe_fused_prefetch.txt), so it stays a profiling knob.
                 u64 nbase = t + gridDim.x;
                 const bool pf = f.prefetch && nbase < f.ntiles;
-                if (pf)
-                    for (int j = 0; j < f.tb; ++j) nbase = insert_zero(nbase, f.tbit[j]);
+                if (pf) nbase = fused_tile_base(f, nbase);
                 for (u32 r = tid; r < nruns; r += 32) {
                     u64 off = 0;
                     for (int j = f.lowrun; j < f.tb; ++j) off |= (u64)((r >> (j - f.lowrun)) & 1u) << f.tbit[j];
@@ -1070,11 +1083,7 @@ __global__ void __launch_bounds__(RING_THREADS, 1) fused_ring_kernel(A *__restri
             for (int j = f.lowrun; j < f.tb; ++j) o |= (u64)((r >> (j - f.lowrun)) & 1u) << f.tbit[j];
             off[i] = o;
         }
-        auto tile_base = [&](u64 t) {
-            u64 base = t;
-            for (int j = 0; j < f.tb; ++j) base = insert_zero(base, f.tbit[j]);
-            return base;
-        };
+        auto tile_base = [&](u64 t) { return fused_tile_base(f, t); };
         auto load_tile = [&](int b, u64 t) {
             A *tile = reinterpret_cast<A *>(smem_raw) + (size_t)b * tsize;
             const u64 base = tile_base(t);
@@ -1119,8 +1128,7 @@ __global__ void __launch_bounds__(RING_THREADS, 1) fused_ring_kernel(A *__restri
         for (u64 t = blockIdx.x; t < ntiles; t += step, ++k) {
             const int b = (int)(k % NBUF);
             A *tile = reinterpret_cast<A *>(smem_raw) + (size_t)b * tsize;
-            u64 base = t;
-            for (int j = 0; j < f.tb; ++j) base = insert_zero(base, f.tbit[j]);
+            const u64 base = fused_tile_base(f, t);
             mbar_wait(&full[b], (k / NBUF) & 1u);
             bool first = true;
             for (int gi = 0; gi < f.ngates; ++gi) {
@@ -1458,9 +1466,15 @@ int upload_tables(qipb_ctx *ctx, const std::vector<cplx> &tables, const double2 
 // tests/csrc/fused_emul.cu points at the host vector) and `launch(f)` consumes one filled FusedArgs.
 // fill: the pass acts on the all-ones vector (qipb_apply_fused_fill); the first op must then be a stage without
 // controls, executed by the EXT kernel in fill mode -- otherwise QIPB_ERR_UNSUPPORTED and nothing is launched.
+struct FusedChunk {            // restriction of a launch to the amplitudes whose `bits` have `value` (index-bit mask)
+    int nfix;
+    const int *bits;
+    u64 value;
+};
+
 template <typename Prepare, typename Launch>
 static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates, const qipb_gate *gates,
-                       Prepare prepare, Launch launch, bool fill = false) {
+                       Prepare prepare, Launch launch, bool fill = false, FusedChunk chunk = FusedChunk{0, nullptr, 0}) {
     QIPB_REQUIRE(gates && tile_bits, "null argument");
     QIPB_REQUIRE(nbits >= 0 && nbits <= 40, "nbits %d unsupported", nbits);
     QIPB_REQUIRE(ntile_bits >= 0 && ntile_bits <= QIPB_MAX_TILE_BITS && ntile_bits <= nbits, "tile bits %d unsupported", ntile_bits);
@@ -1487,6 +1501,22 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
     }
     f.lowrun = 0;
     while (f.lowrun < ntile_bits && tile_bits[f.lowrun] == f.lowrun) f.lowrun++;
+    {
+        QIPB_REQUIRE(chunk.nfix >= 0 && chunk.nfix <= 4 && (chunk.nfix == 0 || chunk.bits) && ntile_bits + chunk.nfix <= nbits,
+                     "chunk: %d fixed bits unsupported (0..4)", chunk.nfix);
+        u64 fmask = 0;
+        for (int j = 0; j < chunk.nfix; ++j) {
+            const int b = chunk.bits[j];
+            QIPB_REQUIRE(b >= 0 && b < nbits && !((tmask >> b) & 1ull) && !((fmask >> b) & 1ull), "chunk: bad fixed bit %d", b);
+            fmask |= 1ull << b;
+        }
+        QIPB_REQUIRE((chunk.value & ~fmask) == 0, "chunk: value has bits outside the fixed bits");
+        f.nexp = 0;
+        for (int b = 0; b < nbits; ++b)
+            if (((tmask | fmask) >> b) & 1ull) f.ebit[f.nexp++] = (unsigned char)b;
+        f.fix_value = chunk.value;
+        f.ntiles = 1ull << (nbits - ntile_bits - chunk.nfix);
+    }
     // ---- pass 1: validate, and fold runs of diagonal gates into stages ----
     std::vector<Op> ops;
     std::vector<cplx> tables;
@@ -1750,7 +1780,7 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
 using namespace qipb;
 
 static int apply_fused_impl(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
-                            int ngates, const qipb_gate *gates, bool fill) {
+                            int ngates, const qipb_gate *gates, bool fill, FusedChunk chunk = FusedChunk{0, nullptr, 0}) {
     QIPB_REQUIRE(ctx && state, "null argument");
     QIPB_CUDA(cudaSetDevice(ctx->device));
     return lower_fused(
@@ -1760,7 +1790,12 @@ static int apply_fused_impl(qipb_ctx *ctx, void *state, int nbits, int dtype, in
             return dtype == QIPB_C128 ? launch_fused<double2>(ctx, (double2 *)state, f)
                                       : launch_fused<float2>(ctx, (float2 *)state, f);
         },
-        fill);
+        fill, chunk);
+}
+
+extern "C" int qipb_apply_fused_chunk(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,
+                                      int ngates, const qipb_gate *gates, int nfix, const int *fix_bits, uint64_t fix_value) {
+    return apply_fused_impl(ctx, state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, false, FusedChunk{nfix, fix_bits, fix_value});
 }
 
 extern "C" int qipb_apply_fused(qipb_ctx *ctx, void *state, int nbits, int dtype, int ntile_bits, const int *tile_bits,

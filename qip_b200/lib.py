@@ -19,9 +19,9 @@ MAX_DENSE_K, MAX_BIG_K, MAX_TILE_BITS, MAX_FUSED_GATES = 4, 10, 12, 280
 EXPORTS = [
     "qipb_version", "qipb_last_error", "qipb_create", "qipb_destroy", "qipb_set_stream", "qipb_sync",
     "qipb_launch_count", "qipb_ring_launch_count", "qipb_ext_launch_count", "qipb_dev_alloc", "qipb_dev_free", "qipb_memcpy_h2d", "qipb_memcpy_d2h",
-    "qipb_init_basis", "qipb_init_kron", "qipb_apply_matrix", "qipb_apply_swap", "qipb_apply_fused", "qipb_apply_fused_fill",
+    "qipb_init_basis", "qipb_init_kron", "qipb_apply_matrix", "qipb_apply_swap", "qipb_apply_fused", "qipb_apply_fused_chunk", "qipb_apply_fused_fill",
     "qipb_func_xor", "qipb_func_xor_u8", "qipb_probabilities", "qipb_collapse", "qipb_reduce", "qipb_add_range",
-    "qipb_ipc_export", "qipb_ipc_open", "qipb_ipc_close", "qipb_peer_swap", "qipb_peer_swap_bit", "qipb_peer_remap", "qipb_peer_gate1",
+    "qipb_ipc_export", "qipb_ipc_open", "qipb_ipc_close", "qipb_peer_swap", "qipb_peer_swap_bit", "qipb_peer_remap", "qipb_peer_remap_chunk", "qipb_peer_gate1",
 ]
 
 
@@ -82,6 +82,7 @@ def load():
     L.qipb_apply_swap.argtypes = [vp, vp, ci, ci, ci, ci, u64]
     L.qipb_apply_fused.argtypes = [vp, vp, ci, ci, ci, i32p, ci, ctypes.POINTER(Gate)]
     L.qipb_apply_fused_fill.argtypes = [vp, vp, ci, ci, ci, i32p, ci, ctypes.POINTER(Gate)]
+    L.qipb_apply_fused_chunk.argtypes = [vp, vp, ci, ci, ci, i32p, ci, ctypes.POINTER(Gate), ci, i32p, u64]
     L.qipb_func_xor.argtypes = [vp, vp, ci, ci, ci, i32p, ci, i32p, vp, u64]
     L.qipb_func_xor_u8.argtypes = [vp, vp, ci, ci, ci, i32p, ci, i32p, vp, u64]
     L.qipb_probabilities.argtypes = [vp, vp, ci, ci, ci, i32p, i32p, u64, u64, vp]
@@ -94,6 +95,7 @@ def load():
     L.qipb_peer_swap.argtypes = [vp, vp, vp, ci, u64, u64, u64]
     L.qipb_peer_swap_bit.argtypes = [vp, vp, vp, ci, ci, ci, ci, u64, u64]
     L.qipb_peer_remap.argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, i32p, ci]
+    L.qipb_peer_remap_chunk.argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, i32p, ci, ci, i32p, u64, ci]
     L.qipb_peer_gate1.argtypes = [vp, vp, vp, ci, u64, u64, dblp, ci, u64]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -97,7 +97,7 @@ class ShardedState(object):
 
 class ShardedB200Backend(object):
     def __init__(self, n: int, dtype, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
-                 peer_gates: bool = False, lazy_layout: bool = True, lazy_init=None):
+                 peer_gates: bool = False, lazy_layout: bool = True, lazy_init=None, overlap=None):
         torch = _torch()
         import torch.distributed as dist
         if not dist.is_initialized():
@@ -127,6 +127,11 @@ class ShardedB200Backend(object):
         self._virtual_init = None       # (per-local-bit factors, kron arguments): product state not yet written (lazy_init)
         self.lazy_init = os.environ.get("QIPB_LAZY_INIT", "0") == "1" if lazy_init is None else bool(lazy_init)
         self.stats = {"gates": 0, "exchanges": 0, "peer_gates": 0, "nvlink_bytes_out": 0}
+        # exchange / compute overlap (see _run_overlapped): chunk bits per pipeline, passes per side that may join it
+        self.overlap = os.environ.get("QIPB_SHARD_OVERLAP", "1") != "0" if overlap is None else bool(overlap)
+        self.overlap_chunk_bits = int(os.environ.get("QIPB_OVERLAP_CHUNK_BITS", "3"))
+        self.overlap_window = int(os.environ.get("QIPB_OVERLAP_WINDOW", "3"))
+        self._xs = None                 # second CUDA stream: the exchange of chunk j runs under the passes of its neighbours
         # shard memory comes from cudaMalloc (qipb_dev_alloc) so that its IPC handle maps it exactly
         self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.peers = {}
@@ -404,27 +409,31 @@ class ShardedB200Backend(object):
         self.stats["exchanges"] += 1
         self.stats["nvlink_bytes_out"] += self.amp_bytes * total
 
-    def _multi_exchange(self, a: sp.MultiExchange):
-        torch = _torch()
-        g = len(a.pairs)
+    def _remap_args(self, pairs):
+        """(g, my value on the exchanged rank bits, peer pointer table indexed by value, local bits) of a remap."""
+        g = len(pairs)
         value = 0
-        for t, (gpos, _) in enumerate(a.pairs):
+        for t, (gpos, _) in enumerate(pairs):
             value |= ((self.rank >> (gpos - self.nl)) & 1) << t
         peers = (ctypes.c_void_p * 8)()
         for b in range(1 << g):
             if b == value:
                 continue
             r = self.rank
-            for t, (gpos, _) in enumerate(a.pairs):
+            for t, (gpos, _) in enumerate(pairs):
                 bit = 1 << (gpos - self.nl)
                 r = (r | bit) if (b >> t) & 1 else (r & ~bit)
             peers[b] = self.peers[r]
+        return g, value, peers, _lib.int_array([l for _, l in pairs])
+
+    def _multi_exchange(self, a: sp.MultiExchange):
+        torch = _torch()
+        g, value, peers, lbits = self._remap_args(a.pairs)
         self._sync_all()
         if self.eng.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.check(self.L.qipb_peer_remap(self.ctx, self.ptr, peers, self.nl, self.code, g,
-                                          _lib.int_array([l for _, l in a.pairs]), value))
+        _lib.check(self.L.qipb_peer_remap(self.ctx, self.ptr, peers, self.nl, self.code, g, lbits, value))
         nbytes = self.amp_bytes * ((1 << self.nl) - (1 << (self.nl - g)))
         if self.eng.profile is not None:
             e1.record()
@@ -433,6 +442,117 @@ class ShardedB200Backend(object):
         self.stats["exchanges"] += 1
         self.stats["multi_exchanges"] = self.stats.get("multi_exchanges", 0) + 1
         self.stats["nvlink_bytes_out"] += nbytes
+
+    # ------------------------------------------------------------------ exchange / compute overlap
+    # An exchange is NVLink-bound (0.7 TB/s per direction against 6.5 TB/s of HBM) and between two barriers: run alone it
+    # idles the SMs and most of HBM for 100 ms (one bit) to 155 ms (three bits) per layer at 33 local qubits -- a third
+    # of an 8-GPU layer.  The state is therefore cut into 2^c CHUNKS along c local bits that are neither exchanged nor
+    # tile bits of the passes next to the exchange ("quiet" bits: to those passes and to the remap they are ordinary
+    # outside bits, so each of them acts on every chunk independently), and the window
+    #       passes A (before)  ->  exchange X  ->  passes B (after)
+    # runs as a pipeline over the chunks on two streams: A(j+1) and B(j-1) compute while X(j) crosses NVLink.  Chunked
+    # launches are the same kernels (qipb_apply_fused_chunk / qipb_peer_remap_chunk: tile / pair enumeration skips the
+    # chunk bits); the remap of a chunk is a persistent launch of one CTA per SM, which fits beside the three resident
+    # CTAs of the fused kernel.  Cross-rank ordering: stream-ordered barriers on the exchange stream around every X(j)
+    # (all ranks have finished A(j) before anyone touches chunk j of a peer; all peers are done with it before B(j)).
+    def _xstream(self):
+        torch = _torch()
+        if self._xs is None:
+            self._xs = torch.cuda.Stream(device=self.device)
+        return self._xs
+
+    def _plan_overlap(self, prev_passes, xstep, next_passes):
+        """(a, b, chunk bits): how many of this rank's passes before / after the exchange join the pipeline, and the
+        local bits along which the state is cut (chosen rank-independently by shardplan.annotate_chunks); None when
+        there is nothing to overlap."""
+        cbits = list(getattr(xstep, "chunk_bits", None) or [])
+        if not self.overlap or not cbits:
+            return None
+        cset = set(cbits)
+
+        def joinable(passes):
+            k = 0
+            for p in passes:
+                if k >= self.overlap_window or not p.fused or (cset & set(p.tile_bits)):
+                    break
+                k += 1
+            return k
+
+        # (every rank runs the chunked exchange once chunk bits are set -- the number of barriers must agree -- even if
+        # none of ITS passes can join)
+        return joinable(list(reversed(prev_passes))), joinable(next_passes), cbits
+
+    def _run_overlapped(self, prev_passes, xstep, next_passes, plan):
+        """passes A -> exchange -> passes B as a pipeline over chunks (see above).  Returns nothing; every launch is
+        asynchronous, the main stream ends ordered behind the last chunk's exchange."""
+        torch = _torch()
+        a, b, cbits = plan
+        pairs = xstep.pairs if isinstance(xstep, sp.MultiExchange) else [(xstep.gpos, xstep.lpos)]
+        g, value, peers, lbits = self._remap_args(pairs)
+        K = 1 << len(cbits)
+        fix = _lib.int_array(cbits)
+        head, A = (prev_passes[:len(prev_passes) - a], prev_passes[len(prev_passes) - a:]) if a else (prev_passes, [])
+        B = next_passes[:b]
+        main = torch.cuda.current_stream(self.device)
+        xs = self._xstream()
+        sm = int(os.environ.get("QIPB_XCHG_CTAS_PER_SM", "1")) * self.eng.sm_count()
+        max_ctas = max(1, sm // ((1 << g) - 1))
+        prof = self.eng.profile
+        chunk_bytes_pass = 2.0 * self.amp_bytes * 2.0 ** self.nl / K
+        nbytes = self.amp_bytes * ((1 << self.nl) - (1 << (self.nl - g)))
+        self._run_passes(head)
+        done_x = []
+        for j in range(K):
+            fv = 0
+            for t, pbit in enumerate(cbits):
+                fv |= ((j >> t) & 1) << pbit
+            for p in A:
+                if prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                self.eng._launch_fused_chunk(p, cbits, fv)
+                if prof is not None:
+                    e1.record()
+                    prof.append(("fused_kernel", chunk_bytes_pass, e0, e1))
+            ready = torch.cuda.Event()
+            ready.record()                                    # this rank's A(j) (and everything before) is done
+            with torch.cuda.stream(xs):
+                xs.wait_event(ready)
+                self._sync_all()                              # ... on every rank
+                self._stream()
+                if prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                _lib.check(self.L.qipb_peer_remap_chunk(self.ctx, self.ptr, peers, self.nl, self.code, g, lbits, value,
+                                                        len(cbits), fix, fv, max_ctas))
+                if prof is not None:
+                    e1.record()
+                    prof.append(("peer_remap_kernel[nvlink]", float(nbytes) / K, e0, e1))
+                self._sync_all()                              # every peer is done with chunk j of this shard
+                ev = torch.cuda.Event()
+                ev.record()
+                done_x.append((fv, ev))
+            self._stream()                                    # back on the main stream
+        for fv, ev in done_x:
+            main.wait_event(ev)
+            for p in B:
+                if prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                self.eng._launch_fused_chunk(p, cbits, fv)
+                if prof is not None:
+                    e1.record()
+                    prof.append(("fused_kernel", chunk_bytes_pass, e0, e1))
+        if not B:
+            for _, ev in done_x:
+                main.wait_event(ev)
+        self.stats["exchanges"] += 1
+        if isinstance(xstep, sp.MultiExchange):
+            self.stats["multi_exchanges"] = self.stats.get("multi_exchanges", 0) + 1
+        self.stats["nvlink_bytes_out"] += nbytes
+        self.stats["overlapped_exchanges"] = self.stats.get("overlapped_exchanges", 0) + 1
+        self.stats["overlap_passes"] = self.stats.get("overlap_passes", 0) + a + b
+        self.stats["overlap_chunks"] = self.stats.get("overlap_chunks", 0) + K
 
     def _peer_gate(self, a: sp.PeerGate1):
         gb = a.gpos - self.nl
@@ -466,18 +586,51 @@ class ShardedB200Backend(object):
             self._peer_gate(a)
 
     def _run_program(self, program):
+        """Execute a rank-local program.  Wherever an exchange has fused passes next to it and quiet local bits exist,
+        the window runs as a chunk pipeline (_run_overlapped); everything else step by step."""
         torch = _torch()
+        steps = list(program)
+        xtypes = (sp.Exchange, sp.MultiExchange)
         with torch.cuda.device(self.device):
             self._stream()
-            for a in program:
-                self._run_step(a)
+            if self._virtual_init is not None:                 # lazy product state: the first fused pass writes it
+                if steps and isinstance(steps[0], tuple) and steps[0][1] and steps[0][1][0].fused:
+                    steps[0] = ("local", self._fill_first_pass(steps[0][1]))
+                else:
+                    self._materialise_virtual()
+            i = 0
+            while i < len(steps):
+                st = steps[i]
+                prev = x = None
+                if isinstance(st, tuple) and i + 1 < len(steps) and isinstance(steps[i + 1], xtypes):
+                    prev, x, xi = st[1], steps[i + 1], i + 1
+                elif isinstance(st, xtypes):
+                    prev, x, xi = [], st, i
+                if x is not None:
+                    after = steps[xi + 1][1] if (xi + 1 < len(steps) and isinstance(steps[xi + 1], tuple)) else []
+                    plan = self._plan_overlap(prev, x, after)
+                    if plan is not None:
+                        self._run_overlapped(prev, x, after[:plan[1]], plan)
+                        if after:
+                            steps[xi + 1] = ("local", after[plan[1]:])     # what is left may lead the next window
+                        i = xi + 1
+                        continue
+                self._run_step(st)
+                i += 1
 
     def _compile_and_run(self, actions):
-        """Every step is launched as soon as it is planned (the host plans batch k+1 while batch k runs)."""
+        """Plan the whole flush, then run it (the host plans flush k+1 while the device still executes flush k: every
+        launch is asynchronous and the barriers are stream-ordered)."""
         torch = _torch()
-        with torch.cuda.device(self.device):
-            self._stream()
-            return sp.compile_program(actions, self.nl, self.rank, self._plan_local, emit=self._run_step)
+        actions = list(actions)
+        ref_rank = self.P - 1
+        program = sp.compile_program(actions, self.nl, self.rank, self._plan_local)
+        if self.overlap and self.fuse and self.P > 1 and any(isinstance(a, (sp.Exchange, sp.MultiExchange)) for a in actions):
+            # the chunk bits of every exchange are read off the program of ONE agreed rank, so that all ranks cut alike
+            ref = program if self.rank == ref_rank else sp.compile_program(actions, self.nl, ref_rank, self._plan_local)
+            sp.annotate_chunks(ref, self.nl, self.overlap_chunk_bits, min(self.eng.min_low_bits, self.nl), self.overlap_window)
+        self._run_program(program)
+        return program
 
     def _execute(self, actions):
         self._compile_and_run(actions)

@@ -391,6 +391,51 @@ def coalesce_exchanges(actions: List[object], max_pairs: int = 3) -> List[object
     return out
 
 
+def annotate_chunks(program: Sequence[object], nl: int, want_bits: int, floor: int, window: int) -> None:
+    """Exchange / compute overlap (ShardedB200Backend._run_overlapped): give every Exchange / MultiExchange of a
+    program the local bit positions along which the state may be cut into chunks while the exchange is pipelined
+    against the fused passes next to it -- attribute `chunk_bits` (ascending, possibly empty) on the action object.
+
+    Every rank must cut along the SAME bits (chunk j of one shard trades with chunk j of its peers), but passes are
+    planned per rank (a control on a rank bit drops a gate, a diagonal target there picks a sub-diagonal, and the
+    planner merges and regroups accordingly), so the choice cannot depend on the caller's own passes: `program` is the
+    compiled program of ONE agreed reference rank (the last one: all its rank bits are 1, no gate drops out), which
+    every rank computes for itself.  For an exchange with passes P before and N after it, the window (a, b) = (last a
+    passes of P, first b of N, each at most `window`) with the most passes that still leaves `want_bits` quiet local
+    bits -- not exchanged, at or above `floor`, and not a tile bit of any pass of the window -- decides; the chunk bits
+    are the highest quiet positions.  A rank then lets as many of ITS passes join the pipeline as avoid those bits
+    (almost always the same ones)."""
+    xtypes = (Exchange, MultiExchange)
+    steps = list(program)
+    for i, x in enumerate(steps):
+        if not isinstance(x, xtypes):
+            continue
+        prev = steps[i - 1][1] if i > 0 and isinstance(steps[i - 1], tuple) else []
+        nxt = steps[i + 1][1] if i + 1 < len(steps) and isinstance(steps[i + 1], tuple) else []
+        victims = {l for _, l in (x.pairs if isinstance(x, MultiExchange) else [(x.gpos, x.lpos)])}
+        cands = [p for p in range(nl - 1, floor - 1, -1) if p not in victims]
+        best = None
+        for a in range(min(window, len(prev)), -1, -1):
+            for b in range(min(window, len(nxt)), -1, -1):
+                if a + b == 0:
+                    continue
+                win = (prev[len(prev) - a:] if a else []) + nxt[:b]
+                if any(not p.fused for p in win):
+                    continue
+                busy = set()
+                for p in win:
+                    busy.update(p.tile_bits)
+                quiet = [p for p in cands if p not in busy]
+                c = min(len(quiet), want_bits)
+                if c < 1:
+                    continue
+                # more passes hide more of the exchange; more chunks shorten the pipeline's fill and drain
+                score = (min(a + b, 4), min(c, 2), a + b, c)
+                if best is None or score > best[0]:
+                    best = (score, sorted(quiet[:c]))
+        x.chunk_bits = best[1] if best else []
+
+
 def compile_program(actions: Sequence[object], nl: int, rank: int, plan_local, emit=None) -> List[object]:
     """The rank-local program of a schedule: every maximal run of Apply / LocalSwap actions is resolved
     for `rank` (lower_for_rank) and handed to `plan_local(list[BitGate]) -> list[ops.Pass]`; the result is

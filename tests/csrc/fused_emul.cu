@@ -30,8 +30,7 @@ void emulate_launch(A *state, const FusedArgs &f) {
     std::vector<A> tile(tsize);
     std::vector<double2> stage_S(FUSED_MAX_OPS + 1);
     for (u64 t = 0; t < f.ntiles; ++t) {
-        u64 base = t;
-        for (int j = 0; j < f.tb; ++j) base = insert_zero(base, f.tbit[j]);
+        const u64 base = fused_tile_base(f, t);
         auto offset_of = [&](u32 e) {
             u64 off = 0;
             for (int j = 0; j < f.tb; ++j) off |= (u64)((e >> j) & 1u) << f.tbit[j];
@@ -87,7 +86,7 @@ int emulate(A *state, const FusedArgs &f, int *info) {
 // sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates, [7] launches that carry EXT ops,
 // [8] block pairs (two dense 2-qubit blocks in one sweep), [9] launches of the WIDE kernel
 static int emul_impl(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
-                     const qipb_gate *gates, int *info, bool fill) {
+                     const qipb_gate *gates, int *info, bool fill, FusedChunk chunk = FusedChunk{0, nullptr, 0}) {
     QIPB_REQUIRE(host_state && info, "null argument");
     for (int i = 0; i < 12; ++i) info[i] = 0;
     return lower_fused(
@@ -99,7 +98,13 @@ static int emul_impl(void *host_state, int nbits, int dtype, int ntile_bits, con
         [&](const FusedArgs &f) {
             return dtype == QIPB_C128 ? emulate<double2>((double2 *)host_state, f, info) : emulate<float2>((float2 *)host_state, f, info);
         },
-        fill);
+        fill, chunk);
+}
+
+// qipb_apply_fused_chunk on the host: only the amplitudes whose fix bits have the given value may change
+extern "C" int qipb_emul_fused_chunk(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
+                                     const qipb_gate *gates, int *info, int nfix, const int *fix_bits, unsigned long long fix_value) {
+    return emul_impl(host_state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, info, false, FusedChunk{nfix, fix_bits, fix_value});
 }
 
 extern "C" int qipb_emul_fused(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,

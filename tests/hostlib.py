@@ -52,6 +52,7 @@ class HostLib(object):
                 ctypes.POINTER(qlib.Gate), ctypes.POINTER(ctypes.c_int)]
         self.emul.qipb_emul_fused.argtypes = argt
         self.emul.qipb_emul_fused_fill.argtypes = argt
+        self.emul.qipb_emul_fused_chunk.argtypes = argt + [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_ulonglong]
         self.emul.qipb_emul_last_error.restype = ctypes.c_char_p
         self.launches = 0
         self.ext_launches = 0
@@ -150,6 +151,24 @@ class HostLib(object):
     def qipb_apply_fused(self, ctx, state, nbits, code, ntile, tile_bits, ngates, gates):
         return self._fused(self.emul.qipb_emul_fused, "apply_fused", state, nbits, code, ntile, tile_bits, ngates, gates)
 
+    def qipb_apply_fused_chunk(self, ctx, state, nbits, code, ntile, tile_bits, ngates, gates, nfix, fix_bits, fix_value):
+        self.log.append("apply_fused_chunk")
+        info = (ctypes.c_int * 12)()
+        before = _amps(state, nbits, code).copy()
+        rc = self.emul.qipb_emul_fused_chunk(_addr(state), nbits, code, ntile, tile_bits, ngates, gates, info, nfix, fix_bits,
+                                             ctypes.c_ulonglong(int(fix_value)))
+        if rc:
+            self.err = self.emul.qipb_emul_last_error()
+            return rc
+        fb = _ints(fix_bits, nfix)
+        mask = sum(1 << b for b in fb)
+        idx = np.arange(1 << nbits, dtype=np.int64)
+        outside = (idx & mask) != int(fix_value)
+        assert np.array_equal(_amps(state, nbits, code)[outside], before[outside]), "a chunked pass touched another chunk"
+        self.launches += info[0]
+        self.ext_launches += info[7]
+        return rc
+
     def qipb_apply_fused_fill(self, ctx, state, nbits, code, ntile, tile_bits, ngates, gates):
         _amps(state, nbits, code)[:] = np.nan              # the previous content must never matter
         return self._fused(self.emul.qipb_emul_fused_fill, "apply_fused_fill", state, nbits, code, ntile, tile_bits, ngates, gates)
@@ -230,12 +249,18 @@ class _FakeStream(object):
     def synchronize(self):
         pass
 
+    def wait_event(self, ev):
+        pass
+
 
 class _FakeEvent(object):
     def __init__(self, enable_timing=False):
         pass
 
-    def record(self):
+    def record(self, stream=None):
+        pass
+
+    def wait(self, stream=None):
         pass
 
     def elapsed_time(self, other):
@@ -260,6 +285,14 @@ class _FakeCuda(object):
     @staticmethod
     def current_stream(dev=None):
         return _FakeStream()
+
+    @staticmethod
+    def Stream(device=None, priority=0):
+        return _FakeStream()
+
+    @staticmethod
+    def stream(s):
+        return contextlib.nullcontext()
 
     @staticmethod
     def synchronize():
@@ -356,17 +389,23 @@ class _PeerMixin(object):
         return 0
 
     def qipb_peer_remap(self, ctx, local, peers, nbits, code, g, lbits, my_value):
-        self.log.append("peer_remap")
+        return self.qipb_peer_remap_chunk(ctx, local, peers, nbits, code, g, lbits, my_value, 0, None, 0, 0, name="peer_remap")
+
+    def qipb_peer_remap_chunk(self, ctx, local, peers, nbits, code, g, lbits, my_value, nfix, fix_bits, fix_value, max_ctas,
+                              name="peer_remap_chunk"):
+        self.log.append(name)
         a = _amps(local, nbits, code)
         lb = _ints(lbits, g)
-        half = 1 << (nbits - g - 1)
+        fb = _ints(fix_bits, nfix) if nfix else []
+        assert not (set(lb) & set(fb))
+        half = 1 << (nbits - g - nfix - 1)
         for slot in range((1 << g) - 1):
             bval = my_value ^ (slot + 1)
             peer = _amps(peers[bval], nbits, code)
-            lsel = sum(((bval >> t) & 1) << lb[t] for t in range(g))
-            psel = sum(((my_value >> t) & 1) << lb[t] for t in range(g))
+            lsel = sum(((bval >> t) & 1) << lb[t] for t in range(g)) | int(fix_value)
+            psel = sum(((my_value >> t) & 1) << lb[t] for t in range(g)) | int(fix_value)
             base = np.arange(half, dtype=np.int64) + (0 if my_value < bval else half)
-            for p in sorted(lb):
+            for p in sorted(lb + fb):
                 base = _insert_zero(base, p)
             tmp = a[base | lsel].copy()
             a[base | lsel] = peer[base | psel]

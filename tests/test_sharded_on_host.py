@@ -151,7 +151,8 @@ def test_sharded_backend_at_production_tile_size_on_virtual_ranks(monkeypatch, P
         g.close()
 
     L = hostlib.run_virtual_ranks(monkeypatch, P, body)
-    assert "apply_fused" in L.log and ("peer_remap" in L.log or "peer_swap_bit" in L.log)
+    assert ("apply_fused" in L.log or "apply_fused_chunk" in L.log) and \
+        ("peer_remap" in L.log or "peer_swap_bit" in L.log or "peer_remap_chunk" in L.log)
 
 
 @pytest.mark.parametrize("P", [2, 4])
@@ -283,3 +284,45 @@ def test_tiny_shards_do_not_coalesce_more_exchanges_than_local_bits(monkeypatch,
         g.close()
 
     hostlib.run_virtual_ranks(monkeypatch, P, body)
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+@pytest.mark.parametrize("chunk_bits", [1, 2, 3])
+def test_exchange_compute_overlap_pipeline_on_virtual_ranks(monkeypatch, P, chunk_bits):
+    # the chunk pipeline (passes A -> exchange -> passes B per chunk: qipb_apply_fused_chunk / qipb_peer_remap_chunk)
+    # must give what the un-overlapped program gives; the doubles also assert that a chunked pass leaves every other
+    # chunk untouched
+    from qip_b200.sharded import ShardedB200Backend
+    monkeypatch.setenv("QIPB_OVERLAP_CHUNK_BITS", str(chunk_bits))
+    n = 9 + int(np.log2(P))
+    rng = np.random.default_rng(P + chunk_bits)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    streams = {"layered": list(layered_stream(n, 4, 11)), "qfft": list(qfft_stream(n)),
+               "controls": [{(0, n - 1): CMat(X2)}, {(n - 1, 0, 4): CMat(CMat(H2))}, {0: H2}, {(1, 0): CMat(rm_mat(2))}, {1: H2},
+                            {(2, n - 2): haar_unitary(rng, 4)}, {(n - 1, 1): CMat(rm_mat(3))}, {n - 1: H2}, {(3, 0): haar_unitary(rng, 4)}]}
+    wants = {}
+    for name, ops_ in streams.items():
+        c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+        for m in ops_:
+            c.kronselect_dot(m)
+        wants[name] = c.get_state().copy()
+    seen = []
+
+    def body(rank):
+        for name, ops_ in streams.items():
+            for overlap in (True, False):
+                g = ShardedB200Backend.make_state(n, [list(range(n))], [psi], tile_bits=5, min_low_bits=2, overlap=overlap)
+                for m in ops_:
+                    g.kronselect_dot(m)
+                    if name == "layered" and len(g.queue) > 3 * n:      # several flushes: layouts evolve between them
+                        g.flush()
+                _check(name, g.get_state(), wants[name])
+                if rank == 0:
+                    seen.append((name, overlap, g.stats.get("overlapped_exchanges", 0), g.stats["exchanges"]))
+                g.close()
+
+    L = hostlib.run_virtual_ranks(monkeypatch, P, body)
+    assert any(ov and k > 0 for _, ov, k, _ in seen), seen
+    assert all(k == 0 for _, ov, k, _ in seen if not ov), seen
+    assert "apply_fused_chunk" in L.log and "peer_remap_chunk" in L.log

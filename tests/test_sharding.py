@@ -256,6 +256,7 @@ def _host_only_backend(n, gbits, rank, tile_bits=5, min_low_bits=2):
     b.eng = types.SimpleNamespace(tile_bits=tile_bits, min_low_bits=min_low_bits)
     b.stats = {"gates": 0}
     b._pending_init, b._virtual_init, b.lazy_init = None, None, False
+    b.overlap = False                               # (the chunk pipeline needs the device side: tests/test_sharded_on_host.py)
     b.device = -1                                   # torch.cuda.device(-1) is a no-op context
     b._stream = lambda: None
     b.programs = []                                 # one list of launched steps per flush
