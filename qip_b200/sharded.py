@@ -456,9 +456,14 @@ class ShardedB200Backend(object):
     # CTAs of the fused kernel.  Cross-rank ordering: stream-ordered barriers on the exchange stream around every X(j)
     # (all ranks have finished A(j) before anyone touches chunk j of a peer; all peers are done with it before B(j)).
     def _xstream(self):
+        """(compute stream, exchange stream) of the chunk pipeline.  The chunked passes run on a HIGH-priority stream, the
+        chunked remaps on a normal one: at every kernel boundary the block scheduler then hands the freed SM slots to
+        the next pass first (3 CTAs per SM), and the persistent remap CTAs -- 256 threads x 56 registers -- only ever
+        fit one per SM beside them.  Measured on 2 B200s without priorities: remap CTAs packed four to an SM whenever a
+        pass ended, the following pass ran on the SMs that were left, and the overlap bought nothing."""
         torch = _torch()
         if self._xs is None:
-            self._xs = torch.cuda.Stream(device=self.device)
+            self._xs = (torch.cuda.Stream(device=self.device, priority=-1), torch.cuda.Stream(device=self.device, priority=0))
         return self._xs
 
     def _plan_overlap(self, prev_passes, xstep, next_passes):
@@ -494,19 +499,19 @@ class ShardedB200Backend(object):
         head, A = (prev_passes[:len(prev_passes) - a], prev_passes[len(prev_passes) - a:]) if a else (prev_passes, [])
         B = next_passes[:b]
         main = torch.cuda.current_stream(self.device)
-        xs = self._xstream()
+        cs, xs = self._xstream()
         sm = int(os.environ.get("QIPB_XCHG_CTAS_PER_SM", "1")) * self.eng.sm_count()
         max_ctas = max(1, sm // ((1 << g) - 1))
         prof = self.eng.profile
         chunk_bytes_pass = 2.0 * self.amp_bytes * 2.0 ** self.nl / K
         nbytes = self.amp_bytes * ((1 << self.nl) - (1 << (self.nl - g)))
         self._run_passes(head)
-        done_x = []
-        for j in range(K):
-            fv = 0
-            for t, pbit in enumerate(cbits):
-                fv |= ((j >> t) & 1) << pbit
-            for p in A:
+        start = torch.cuda.Event()
+        start.record()                                        # everything queued so far on the caller's stream
+        cs.wait_event(start)
+
+        def chunk_passes(passes, fv):
+            for p in passes:
                 if prof is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
@@ -514,8 +519,17 @@ class ShardedB200Backend(object):
                 if prof is not None:
                     e1.record()
                     prof.append(("fused_kernel", chunk_bytes_pass, e0, e1))
-            ready = torch.cuda.Event()
-            ready.record()                                    # this rank's A(j) (and everything before) is done
+
+        done_x = []
+        for j in range(K):
+            fv = 0
+            for t, pbit in enumerate(cbits):
+                fv |= ((j >> t) & 1) << pbit
+            with torch.cuda.stream(cs):
+                self._stream()
+                chunk_passes(A, fv)
+                ready = torch.cuda.Event()
+                ready.record()                                # this rank's A(j) (and everything before) is done
             with torch.cuda.stream(xs):
                 xs.wait_event(ready)
                 self._sync_all()                              # ... on every rank
@@ -532,20 +546,18 @@ class ShardedB200Backend(object):
                 ev = torch.cuda.Event()
                 ev.record()
                 done_x.append((fv, ev))
-            self._stream()                                    # back on the main stream
-        for fv, ev in done_x:
-            main.wait_event(ev)
-            for p in B:
-                if prof is not None:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                self.eng._launch_fused_chunk(p, cbits, fv)
-                if prof is not None:
-                    e1.record()
-                    prof.append(("fused_kernel", chunk_bytes_pass, e0, e1))
+        with torch.cuda.stream(cs):
+            self._stream()
+            for fv, ev in done_x:
+                cs.wait_event(ev)
+                chunk_passes(B, fv)
+            end = torch.cuda.Event()
+            end.record()
+        main.wait_event(end)
         if not B:
             for _, ev in done_x:
                 main.wait_event(ev)
+        self._stream()                                        # the library is back on the caller's stream
         self.stats["exchanges"] += 1
         if isinstance(xstep, sp.MultiExchange):
             self.stats["multi_exchanges"] = self.stats.get("multi_exchanges", 0) + 1

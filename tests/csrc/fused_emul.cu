@@ -118,4 +118,17 @@ extern "C" int qipb_emul_fused_fill(void *host_state, int nbits, int dtype, int 
     return emul_impl(host_state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, info, true);
 }
 
+// host cost of the lowering alone (no tile is touched): what every launch of the product pays on the CPU
+extern "C" int qipb_emul_lower_only(int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates, const qipb_gate *gates) {
+    std::vector<cplx> keep;
+    return lower_fused(
+        nbits, dtype, ntile_bits, tile_bits, ngates, gates,
+        [&](const std::vector<cplx> &tables, FusedArgs &f) {
+            keep = tables;
+            f.tables = reinterpret_cast<const double2 *>(keep.data());
+            return QIPB_OK;
+        },
+        [&](const FusedArgs &) { return QIPB_OK; });
+}
+
 extern "C" const char *qipb_emul_last_error(void) { return qipb::g_emul_err; }
