@@ -44,6 +44,8 @@ extern "C" int qipb_create(int device, qipb_ctx **out) {
     c->tab_cap = 0;
     c->tab_slot = 0;
     c->kron_table = nullptr;
+    c->sched_ring = nullptr;
+    c->sched_slot = 0;
     for (int i = 0; i < 4; ++i) { c->tab_host[i] = nullptr; c->tab_ev[i] = nullptr; }
     *out = c;
     return QIPB_OK;
@@ -55,6 +57,7 @@ extern "C" int qipb_destroy(qipb_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->tab_dev) cudaFree(ctx->tab_dev);
     if (ctx->kron_table) cudaFree(ctx->kron_table);
+    if (ctx->sched_ring) cudaFree(ctx->sched_ring);
     for (int i = 0; i < 4; ++i) {
         if (ctx->tab_host[i]) cudaFreeHost(ctx->tab_host[i]);
         if (ctx->tab_ev[i]) cudaEventDestroy(ctx->tab_ev[i]);

@@ -147,4 +147,9 @@ struct qipb_ctx {
     int tab_slot;
     double2 *kron_table;           // init.cu: product of the low-bit feed groups, 2^12 entries
     unsigned long long ext_launches;   // fused launches that took the EXT kernel (opt-in forms, fused.cu)
+    // fused.cu: tile counters of the dynamically scheduled launches, a ring of {next tile, CTAs done} pairs (device
+    // memory, zero when idle: the last CTA of a launch resets its pair)
+    unsigned int *sched_ring;
+    unsigned int sched_slot;
 };
+#define QIPB_SCHED_SLOTS 256

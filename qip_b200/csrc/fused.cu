@@ -76,6 +76,12 @@ struct FusedArgs {
     int nexp;
     unsigned char ebit[20];
     u64 fix_value;
+    // Dynamic tile scheduling: {next tile, CTAs done} in device memory (null: tile t = blockIdx.x + k * gridDim.x).  The
+    // CTAs of a launch are persistent; when some of them cannot be resident from the start -- a remap of the chunk
+    // pipeline or an NCCL kernel holds part of an SM -- a static split makes the late CTAs a second wave that doubles the
+    // launch (measured: 13 ms instead of 5.5 per chunk pass beside the remap); with a shared counter they just take
+    // fewer tiles.
+    unsigned int *sched;
     DevGate g[FUSED_MAX_OPS];
 };
 static_assert(sizeof(FusedArgs) <= 32764, "FusedArgs must fit in the kernel parameter space");
@@ -968,8 +974,16 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
         __syncthreads();
     }
     u32 parity = 0;
+    __shared__ unsigned int next_tile;
+    unsigned int *const sched = f.sched;
+    u64 t = blockIdx.x;
+    if (sched) {
+        if (tid == 0) next_tile = atomicAdd(&sched[0], 1u);
+        __syncthreads();
+        t = (u64)__shfl_sync(0xffffffffu, next_tile, 0);     // (the shuffle keeps the tile number warp-uniform for ptxas)
+    }
 
-    for (u64 t = blockIdx.x; t < f.ntiles; t += gridDim.x) {
+    for (; t < f.ntiles;) {
         const u64 base = fused_tile_base(f, t);
 
         // ---- stage the tile: runs of 2^lowrun consecutive amplitudes ----
@@ -985,7 +999,7 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
                 // is computed and written back.  Measured on B200: no gain for compute-heavy passes and a worse
                 // floor (profiles/r01_probe_fused_prefetch.txt), so it stays a profiling knob.
                 u64 nbase = t + gridDim.x;
-                const bool pf = f.prefetch && nbase < f.ntiles;
+                const bool pf = f.prefetch && !sched && nbase < f.ntiles;
                 if (pf) nbase = fused_tile_base(f, nbase);
                 for (u32 r = tid; r < nruns; r += 32) {
                     u64 off = 0;
@@ -1012,10 +1026,17 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
         }
 
         // ---- run the gate list on the tile ----
+        bool fetched = false;
         for (int gi = 0; gi < f.ngates; ++gi) {
             if (fused_op_is_skipped<EXT>(f.g[gi])) continue;
             run_fused_op<A, UNI, NT, EXT>(tile, f, gi, stage_S, base, tsize, tid);
             __syncthreads();
+            // the next tile of this CTA: fetched behind the first barrier of the tile (every warp has read the current
+            // number by then), consumed behind the last one -- the atomic's latency hides under the sweeps
+            if (sched && !fetched) {
+                if (tid == 0) next_tile = atomicAdd(&sched[0], 1u);
+                fetched = true;
+            }
         }
 
         // ---- write the tile back ----
@@ -1038,6 +1059,14 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
                 state[base + off] = tile[e];
             }
             __syncthreads();
+        }
+        t = sched ? (u64)__shfl_sync(0xffffffffu, next_tile, 0) : t + gridDim.x;
+    }
+    if (sched && tid == 0) {                                  // the last CTA to leave re-arms the counters
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1u) {
+            sched[0] = 0u;
+            sched[1] = 0u;
         }
     }
 }
@@ -1249,8 +1278,27 @@ static void classify_block(const double *mat, DevGate &d, PutC put_c, PutR put_r
     d.mk = MK_GENERAL;
 }
 
+static bool dynsched_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("QIPB_FUSED_DYNSCHED");        // A/B knob: 0 = static tile split
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 template <typename A>
-static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f) {
+static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f_in) {
+    static thread_local FusedArgs f;                           // (a copy: the scheduling slot is per launch)
+    f = f_in;
+    f.sched = nullptr;
+    if (dynsched_enabled()) {
+        if (!ctx->sched_ring) {
+            QIPB_CUDA(cudaMalloc(&ctx->sched_ring, QIPB_SCHED_SLOTS * 2 * sizeof(unsigned int)));
+            QIPB_CUDA(cudaMemset(ctx->sched_ring, 0, QIPB_SCHED_SLOTS * 2 * sizeof(unsigned int)));
+        }
+        f.sched = ctx->sched_ring + 2 * (ctx->sched_slot++ % QIPB_SCHED_SLOTS);
+    }
     const size_t smem = sizeof(A) << f.tb;
     const bool bulk = launch_is_bulk(f, sizeof(A));
     int per_sm = (int)((224u * 1024u) / (smem + 3072));

@@ -23,6 +23,5 @@ except Exception as e:
 PY
  done
 }
-run wide1 QIPB_FUSED_WIDE=1
-run wide0 QIPB_FUSED_WIDE=0
-run wide1_ext0 QIPB_FUSED_WIDE=1 QIPB_FUSED_EXT=0
+run dynsched1 QIPB_FUSED_DYNSCHED=1
+run dynsched0 QIPB_FUSED_DYNSCHED=0
