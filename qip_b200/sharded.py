@@ -520,11 +520,17 @@ class ShardedB200Backend(object):
                     e1.record()
                     prof.append(("fused_kernel", chunk_bytes_pass, e0, e1))
 
+        # One barrier between consecutive chunk exchanges serves both purposes: behind it every rank has finished X(j-1)
+        # (chunk j-1 is final everywhere: B(j-1) may start) and A(j) (chunk j of every peer may be touched).  The NCCL
+        # barrier kernel does not fit beside three fused CTAs and a remap CTA, so it runs at a kernel boundary of the
+        # compute stream: every barrier costs the exchange stream about half a chunk pass -- hence K + 1 of them, not 2 K.
         done_x = []
+        fvs = []
         for j in range(K):
             fv = 0
             for t, pbit in enumerate(cbits):
                 fv |= ((j >> t) & 1) << pbit
+            fvs.append(fv)
             with torch.cuda.stream(cs):
                 self._stream()
                 chunk_passes(A, fv)
@@ -532,7 +538,11 @@ class ShardedB200Backend(object):
                 ready.record()                                # this rank's A(j) (and everything before) is done
             with torch.cuda.stream(xs):
                 xs.wait_event(ready)
-                self._sync_all()                              # ... on every rank
+                self._sync_all()                              # every rank: A(j) done, X(j-1) done
+                if j > 0:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    done_x.append((fvs[j - 1], ev))
                 self._stream()
                 if prof is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -542,10 +552,11 @@ class ShardedB200Backend(object):
                 if prof is not None:
                     e1.record()
                     prof.append(("peer_remap_kernel[nvlink]", float(nbytes) / K, e0, e1))
-                self._sync_all()                              # every peer is done with chunk j of this shard
-                ev = torch.cuda.Event()
-                ev.record()
-                done_x.append((fv, ev))
+        with torch.cuda.stream(xs):
+            self._sync_all()                                  # every peer is done with the last chunk
+            ev = torch.cuda.Event()
+            ev.record()
+            done_x.append((fvs[K - 1], ev))
         with torch.cuda.stream(cs):
             self._stream()
             for fv, ev in done_x:

@@ -354,3 +354,32 @@ def test_emulated_fill_mode_refuses_what_it_cannot_serve(emul):
     info = (ctypes.c_int * 12)()
     rc = emul.qipb_emul_fused_fill(st.ctypes.data_as(ctypes.c_void_p), n, qlib.C128, 10, tbits, ng, arr, info)
     assert rc == qlib.ERR_UNSUPPORTED and info[0] == 0 and not st.any()
+
+
+def test_chunked_fused_pass_equals_the_whole_pass_and_leaves_other_chunks_alone():
+    # qipb_apply_fused_chunk: the chunks partition the state, every chunk launch changes only its own amplitudes (the host
+    # double asserts it) and all of them together equal qipb_apply_fused -- controls, diagonal targets and stage cells on
+    # the chunk bits are read from the tile's base index like any other outside bit
+    import hostlib
+    L = hostlib.HostLib()
+    n = 14
+    rng = np.random.default_rng(1)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    for tile, fix in (((0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 13), (7,)), (tuple(range(12)), (12, 13)),
+                      ((0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 13), (8, 12))):
+        hi = [b for b in tile if b >= 7]
+        gates = [BitGate("matrix", (hi[0], hi[3]), 0, haar_unitary(rng, 4)), BitGate("matrix", (hi[1],), 1 << fix[0], H2.astype(complex)),
+                 BitGate("matrix", (fix[0],), 0, np.diag([1, 1j]), True), BitGate("matrix", (tile[0],), 0, haar_unitary(rng, 2)),
+                 BitGate("matrix", (hi[2],), 0, H2.astype(complex))]
+        gates += [BitGate("matrix", (), (1 << hi[2]) | (1 << b), np.diag([np.exp(0.1j * (b + 1))]), True) for b in range(n) if b != hi[2]]
+        p = Pass(True, gates, tile)
+        arr, tb = pack_pass(p)
+        a, b = psi.copy(), psi.copy()
+        pa, pb = ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data)
+        assert L.qipb_apply_fused(None, pa, n, qlib.C128, len(tile), tb, len(gates), arr) == 0, L.err
+        for j in range(1 << len(fix)):
+            fv = sum(((j >> t) & 1) << fb for t, fb in enumerate(fix))
+            assert L.qipb_apply_fused_chunk(None, pb, n, qlib.C128, len(tile), tb, len(gates), arr, len(fix), qlib.int_array(fix), fv) == 0, L.err
+        assert np.max(np.abs(a - b)) <= 1e-14 * np.max(np.abs(a))     # (a one-tile chunk takes the generic sweeps: other rounding)
+        want = bitsim.run_passes(psi.copy(), [p], n)
+        assert np.max(np.abs(a - want)) <= 1e-12 * np.max(np.abs(want))
