@@ -5,10 +5,14 @@ N=${1:-2}
 R=${2:-r02e}
 O=gpurun_out
 mkdir -p $O
+if [ -z "$NOTEST" ]; then
 timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q -s > $O/${R}_pytest_sharded_n$N.log 2>&1; tail -8 $O/${R}_pytest_sharded_n$N.log
+fi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 PORT=29700
-for cfg in "ov0 QIPB_SHARD_OVERLAP=0" "ov1_c3 QIPB_SHARD_OVERLAP=1 QIPB_OVERLAP_CHUNK_BITS=3" "ov1_c2 QIPB_SHARD_OVERLAP=1 QIPB_OVERLAP_CHUNK_BITS=2" "ov1_c3_2cta QIPB_SHARD_OVERLAP=1 QIPB_OVERLAP_CHUNK_BITS=3 QIPB_XCHG_CTAS_PER_SM=2"; do
+CFGS=${CFGS:-"ov0 QIPB_SHARD_OVERLAP=0|ov1_c3 QIPB_SHARD_OVERLAP=1 QIPB_OVERLAP_CHUNK_BITS=3|ov1_c2 QIPB_SHARD_OVERLAP=1 QIPB_OVERLAP_CHUNK_BITS=2"}
+IFS='|' read -ra CFG_LIST <<< "$CFGS"
+for cfg in "${CFG_LIST[@]}"; do
  set -- $cfg; name=$1; shift
  PORT=$((PORT+1))
  f=$O/${R}_bench_n${N}_$name.json
