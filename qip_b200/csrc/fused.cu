@@ -34,6 +34,9 @@ namespace qipb {
 #ifndef QIPB_ENABLE_PAIRS
 #define QIPB_ENABLE_PAIRS 0
 #endif
+#ifndef QIPB_ENABLE_TRIOS
+#define QIPB_ENABLE_TRIOS 1     // sweep_trio: a dense 2-qubit block + a lone dense 1-qubit gate per sweep (fits the register budget)
+#endif
 #ifndef QIPB_WIDE_MINB
 #define QIPB_WIDE_MINB 3
 #endif
@@ -431,6 +434,103 @@ QIPB_HD void sweep_pair2(A *tile, const DevGate &ga, const DevGate &gb, u32 ngro
         if (kb == PK_GENERAL) sweep_pair2_k<A, NT, PK_MONO, PK_GENERAL>(tile, ga, gb, ngroups, tid);
         else if (kb == PK_REAL) sweep_pair2_k<A, NT, PK_MONO, PK_REAL>(tile, ga, gb, ngroups, tid);
         else sweep_pair2_k<A, NT, PK_MONO, PK_MONO>(tile, ga, gb, ngroups, tid);
+    }
+}
+
+// ---- a dense 2-qubit block and a lone dense 1-qubit gate on a third tile bit in ONE sweep (WIDE kernel) ----
+// After the planner has tensored lone 1-qubit gates in pairs (ops.pack_lone_1q) about one per pass is left over, and it
+// costs a whole round trip of the tile through shared memory for 8-16 FP64 instructions per pair.  Block and gate act
+// on disjoint bits, so they commute: groups of 8 amplitudes (member = 2 * ia + ic, ia the block's matrix index, ic the
+// gate's) are held in registers, the block runs on both halves, the gate on the four pairs.  Host guarantees as for
+// the block pairs: no in-tile controls, three distinct targets above the bank-conflict bits, tile / 8 a multiple of NT.
+// 32 data registers + one coefficient set at a time: unlike the block pairs this fits the WIDE kernel's budget with the
+// coefficients on the uniform datapath.
+template <typename A, int NT, int PK, bool REAL1>
+QIPB_HD void sweep_trio_k(A *tile, const DevGate &ga, const DevGate &gc, u32 ngroups, int tid) {
+    typedef typename amp_traits<A>::real R;
+    const u32 nm0 = ga.nmask[2], nm1 = ga.nmask[3], nm2 = ga.nmask[4];
+    const u32 oc = 1u << gc.tl[0];
+    u32 ld[4], st[4];
+    {
+        const u32 oh = 1u << ga.tl[0], ol = 1u << ga.tl[1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ld[j] = ((j & 2) ? oh : 0u) + ((j & 1) ? ol : 0u);
+            const u32 r = PK == PK_MONO ? (ga.perm >> (2 * j)) & 3u : (u32)j;     // column j of a monomial block -> row perm[j]
+            st[j] = ((r & 2u) ? oh : 0u) + ((r & 1u) ? ol : 0u);
+        }
+    }
+#pragma unroll 1
+    for (u32 it = 0, nit = ngroups / NT, w = tid; it < nit; ++it, w += NT) {
+        u32 e = w;
+        e += e & nm0;
+        e += e & nm1;
+        e += e & nm2;
+        A *p = tile + e;
+        A x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = p[ld[k >> 1] + ((k & 1) ? oc : 0u)];
+        if (PK == PK_MONO) {
+            const u32 phmask = ga.phmask;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (phmask & (1u << j)) {
+                    const Cf<A> c = coef<A>(ga, j);
+                    x[2 * j] = cmulc<A>(c, x[2 * j]);
+                    x[2 * j + 1] = cmulc<A>(c, x[2 * j + 1]);
+                }
+        } else {
+            const Block2<A, PK == PK_GENERAL ? MK_GENERAL : MK_REALPHASE> blk(ga);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                A r[4];
+                blk.apply(x[c], x[2 + c], x[4 + c], x[6 + c], r);
+                x[c] = r[0];
+                x[2 + c] = r[1];
+                x[4 + c] = r[2];
+                x[6 + c] = r[3];
+            }
+        }
+        if (REAL1) {
+            const R m0 = rcoef<A>(gc, 0), m1 = rcoef<A>(gc, 1), m2 = rcoef<A>(gc, 2), m3 = rcoef<A>(gc, 3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const A a0 = x[2 * j], a1 = x[2 * j + 1];
+                x[2 * j].x = fma(m1, a1.x, m0 * a0.x);
+                x[2 * j].y = fma(m1, a1.y, m0 * a0.y);
+                x[2 * j + 1].x = fma(m3, a1.x, m2 * a0.x);
+                x[2 * j + 1].y = fma(m3, a1.y, m2 * a0.y);
+            }
+        } else {
+            const Cf<A> m0 = coef<A>(gc, 0), m1 = coef<A>(gc, 1), m2 = coef<A>(gc, 2), m3 = coef<A>(gc, 3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const A a0 = x[2 * j], a1 = x[2 * j + 1];
+                A r0 = cmulc<A>(m0, a0), r1 = cmulc<A>(m2, a0);
+                cfmac<A>(r0, m1, a1);
+                cfmac<A>(r1, m3, a1);
+                x[2 * j] = r0;
+                x[2 * j + 1] = r1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[st[k >> 1] + ((k & 1) ? oc : 0u)] = x[k];
+    }
+}
+
+template <typename A, int NT>
+QIPB_HD void sweep_trio(A *tile, const DevGate &ga, const DevGate &gc, u32 ngroups, int tid) {
+    const int ka = pair_kind(ga);                              // uniform: the forms come from the descriptors
+    const bool real1 = gc.mk == MK1_REAL;
+    if (ka == PK_GENERAL) {
+        if (real1) sweep_trio_k<A, NT, PK_GENERAL, true>(tile, ga, gc, ngroups, tid);
+        else sweep_trio_k<A, NT, PK_GENERAL, false>(tile, ga, gc, ngroups, tid);
+    } else if (ka == PK_REAL) {
+        if (real1) sweep_trio_k<A, NT, PK_REAL, true>(tile, ga, gc, ngroups, tid);
+        else sweep_trio_k<A, NT, PK_REAL, false>(tile, ga, gc, ngroups, tid);
+    } else {
+        if (real1) sweep_trio_k<A, NT, PK_MONO, true>(tile, ga, gc, ngroups, tid);
+        else sweep_trio_k<A, NT, PK_MONO, false>(tile, ga, gc, ngroups, tid);
     }
 }
 
@@ -900,13 +1000,13 @@ QIPB_HD void run_op(A *tile, const DevGate &g, const DevGate &next, const double
 template <bool EXT>
 QIPB_HD bool fused_op_is_skipped(const DevGate &g) {
     // stage applied by the dense gate before it / second Hadamard of a QFT pair / second block of a block pair
-    return g.diag == 3 || (EXT && (g.post == 3 || g.post == 5));
+    return g.diag == 3 || (EXT && (g.post == 3 || g.post == 5 || g.post == 7));   // (7: the 1-qubit gate of a trio)
 }
 
 static inline bool fused_has_ext(const FusedArgs &f) {
     for (int gi = 0; gi < f.ngates; ++gi) {
         const DevGate &g = f.g[gi];
-        if (g.post >= 2 || g.diag == 5 || (!g.diag && g.k == 1 && g.mk == MK1_REAL)) return true;   // incl. block pairs (post 4 / 5)
+        if (g.post >= 2 || g.diag == 5 || (!g.diag && g.k == 1 && g.mk == MK1_REAL)) return true;   // incl. block pairs (post 4 / 5), trios (6 / 7)
     }
     return false;
 }
@@ -924,6 +1024,19 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
                 run_op<A, UNI, NT>(tile, g, g, f.tables, stage_S, gi, base, f.tb, tsize, tid);
             } else if (on_b) {
                 run_op<A, UNI, NT>(tile, h, h, f.tables, stage_S, gi, base, f.tb, tsize, tid);
+            }
+            return;
+        }
+        if (QIPB_ENABLE_TRIOS && NT == 128 && g.post == 6) {    // block + lone 1-qubit gate (WIDE launches only): ops gi, gi + 1
+            const DevGate &h = f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi];
+            const bool on_a = (base & g.out_ctrl) == g.out_ctrl, on_c = (base & h.out_ctrl) == h.out_ctrl;
+            if (on_a && on_c) {
+                sweep_trio<A, NT>(tile, g, h, tsize >> 3, tid);
+            } else if (on_a) {
+                run_op<A, UNI, NT>(tile, g, g, f.tables, stage_S, gi, base, f.tb, tsize, tid);
+            } else if (on_c) {
+                if (h.mk == MK1_REAL) sweep_real1<A, UNI, NT>(tile, h, Expand<1>(h), tsize >> 1, tid);
+                else sweep_dense1<A, UNI, NT>(tile, h, Expand<1>(h), tsize >> 1, tid);
             }
             return;
         }
@@ -1195,6 +1308,12 @@ static bool pair_enabled() {
     return !e || atoi(e) != 0;
 }
 
+static bool trio_enabled() {
+    if (!QIPB_ENABLE_TRIOS) return false;
+    const char *e = getenv("QIPB_FUSED_TRIO");                // A/B knob, read per call
+    return !e || atoi(e) != 0;
+}
+
 static bool ring_enabled() {
     // opt-in (measured on B200, profiles/r01_probe_fused_ring.txt: one tile at a time on 16 warps sweeps
     // slower than three independent CTAs per SM do); read per call so that tests can toggle it
@@ -1211,6 +1330,7 @@ static inline bool launch_is_uni(const FusedArgs &f, size_t amp_bytes) { return 
 static bool wide_enabled();
 static bool ring_enabled();
 static bool pair_enabled();
+static bool trio_enabled();
 static inline bool launch_is_wide(const FusedArgs &f, size_t amp_bytes) {
     return launch_is_uni(f, amp_bytes) && f.tb == 12 && wide_enabled() && !ring_enabled();
 }
@@ -1738,7 +1858,7 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
         // register groups (sweep_pair2).  The partner may sit later in the list: it is executed early, at the leader's
         // position, which is exact when it commutes with every op in between -- the non-diagonal targets of either
         // side must avoid everything the other side reads (targets and controls; diagonal ops only read).
-        if (pair_enabled() && launch_is_wide(f, dtype == QIPB_C128 ? 16 : 8)) {
+        if ((pair_enabled() || trio_enabled()) && launch_is_wide(f, dtype == QIPB_C128 ? 16 : 8)) {
             const int lowb = dtype == QIPB_C128 ? 3 : 4;       // LowBits<A>
             std::vector<int> origin(cnt);                      // position in f.g -> index of its Op (positions move below)
             for (size_t oi = 0; oi < cnt; ++oi) origin[oi] = (int)(first + oi);
@@ -1759,40 +1879,78 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                 for (int j = 0; j < g.k; ++j) m |= 1ull << g.bits[j];
                 return m;
             };
-            auto pairable = [&](size_t oi) {
+            auto block2 = [&](size_t oi) {                     // a dense 2-qubit block the register-group sweeps can take
                 const DevGate &d = f.g[oi];
                 return !ops[origin[oi]].stage && !d.diag && d.k == 2 && d.nins == 2 && d.post == 0 && d.in_or == 0 &&
                        d.tl[0] != 0xFF && d.tl[1] != 0xFF && d.tl[0] >= lowb && d.tl[1] >= lowb;
             };
-            for (size_t i = 0; i + 1 < cnt; ++i) {
-                if (!pairable(i)) continue;
+            auto lone1 = [&](size_t oi) {                      // a lone dense 1-qubit gate (no stage rides on it)
+                const DevGate &d = f.g[oi];
+                return !ops[origin[oi]].stage && !d.diag && d.k == 1 && d.nins == 1 && d.post == 0 && d.in_or == 0 &&
+                       d.tl[0] != 0xFF && d.tl[0] >= lowb;
+            };
+            auto move_next_to = [&](size_t i, size_t j) {      // op j -> position i + 1 (the ops in between shift by one)
+                const DevGate moved = f.g[j];
+                const int moved_from = origin[j];
+                for (size_t t = j; t > i + 1; --t) {
+                    f.g[t] = f.g[t - 1];
+                    origin[t] = origin[t - 1];
+                }
+                f.g[i + 1] = moved;
+                origin[i + 1] = moved_from;
+            };
+            auto set_masks = [&](DevGate &a, const unsigned char *pos, int npos) {
+                unsigned char srt[4];
+                for (int x = 0; x < npos; ++x) srt[x] = pos[x];
+                for (int x = 1; x < npos; ++x)
+                    for (int y = x; y > 0 && srt[y] < srt[y - 1]; --y) std::swap(srt[y], srt[y - 1]);
+                for (int x = 0; x < npos; ++x) a.nmask[2 + x] = ~((1u << srt[x]) - 1u);
+            };
+            // the partner is executed at the leader's position: exact when it commutes with every op in between -- the
+            // non-diagonal targets of either side must avoid everything the other side reads (targets and controls)
+            auto find_partner = [&](size_t i, bool want_block) -> size_t {
                 u64 mid_support = 0, mid_nondiag = 0;
                 for (size_t j = i + 1; j < cnt; ++j) {
-                    if (pairable(j) && !(nondiag(j) & (support(i) | mid_support)) && !(support(j) & (nondiag(i) | mid_nondiag))) {
-                        // the partner moves next to the leader: rotate positions i + 1 .. j (descriptors and their origin)
-                        const DevGate moved = f.g[j];
-                        const int moved_from = origin[j];
-                        for (size_t t = j; t > i + 1; --t) {
-                            f.g[t] = f.g[t - 1];
-                            origin[t] = origin[t - 1];
-                        }
-                        f.g[i + 1] = moved;
-                        origin[i + 1] = moved_from;
-                        DevGate &a = f.g[i], &b = f.g[i + 1];
-                        unsigned char pos4[4] = {a.tl[0], a.tl[1], b.tl[0], b.tl[1]};
-                        for (int x = 1; x < 4; ++x)
-                            for (int y = x; y > 0 && pos4[y] < pos4[y - 1]; --y) std::swap(pos4[y], pos4[y - 1]);
-                        for (int x = 0; x < 4; ++x) a.nmask[2 + x] = ~((1u << pos4[x]) - 1u);
-                        a.post = 4;
-                        a.pair = 1;
-                        b.post = 5;
-                        ++i;                                       // the partner is taken
-                        break;
-                    }
+                    const bool kind_ok = want_block ? block2(j) : lone1(j);
+                    if (kind_ok && !(nondiag(j) & (support(i) | mid_support)) && !(support(j) & (nondiag(i) | mid_nondiag))) return j;
                     mid_support |= support(j);
                     mid_nondiag |= nondiag(j);
                 }
-            }
+                return cnt;
+            };
+            if (pair_enabled())
+                for (size_t i = 0; i + 1 < cnt; ++i) {
+                    if (!block2(i)) continue;
+                    const size_t j = find_partner(i, true);
+                    if (j >= cnt) continue;
+                    move_next_to(i, j);
+                    DevGate &a = f.g[i], &b = f.g[i + 1];
+                    const unsigned char pos4[4] = {a.tl[0], a.tl[1], b.tl[0], b.tl[1]};
+                    set_masks(a, pos4, 4);
+                    a.post = 4;
+                    a.pair = 1;
+                    b.post = 5;
+                    ++i;                                       // the partner is taken
+                }
+            if (trio_enabled())
+                for (size_t i = 0; i + 1 < cnt; ++i) {
+                    const bool is_block = block2(i), is_lone = lone1(i);
+                    if (!is_block && !is_lone) continue;
+                    const size_t j = find_partner(i, !is_block);
+                    if (j >= cnt) continue;
+                    move_next_to(i, j);
+                    if (!is_block) {                           // the block leads (they commute: disjoint bits, no in-tile controls)
+                        std::swap(f.g[i], f.g[i + 1]);
+                        std::swap(origin[i], origin[i + 1]);
+                    }
+                    DevGate &a = f.g[i], &c = f.g[i + 1];
+                    const unsigned char pos3[3] = {a.tl[0], a.tl[1], c.tl[0]};
+                    set_masks(a, pos3, 3);
+                    a.post = 6;
+                    a.pair = 1;
+                    c.post = 7;
+                    ++i;
+                }
         }
         f.nstages = 0;
         for (size_t oi = 0; oi < cnt; ++oi) f.nstages += f.g[oi].diag >= 2;

@@ -23,5 +23,5 @@ except Exception as e:
 PY
  done
 }
-run dynsched1 QIPB_FUSED_DYNSCHED=1
-run dynsched0 QIPB_FUSED_DYNSCHED=0
+run trio1 QIPB_FUSED_TRIO=1
+run trio0 QIPB_FUSED_TRIO=0

@@ -383,3 +383,48 @@ def test_chunked_fused_pass_equals_the_whole_pass_and_leaves_other_chunks_alone(
         assert np.max(np.abs(a - b)) <= 1e-14 * np.max(np.abs(a))     # (a one-tile chunk takes the generic sweeps: other rounding)
         want = bitsim.run_passes(psi.copy(), [p], n)
         assert np.max(np.abs(a - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("seed", range(3))
+def test_emulated_trios_match_separate_sweeps(emul, monkeypatch, dtype, seed):
+    # a dense 2-qubit block and a lone dense 1-qubit gate share one sweep over 8-amplitude register groups (sweep_trio):
+    # every block form x (general / real) 1-qubit gate, partner found across commuting ops, either one first, outside
+    # controls that switch one of the two off on some tiles
+    n = 15
+    rng = np.random.default_rng(200 + seed)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi = (psi / np.linalg.norm(psi)).astype(dtype)
+    hh = np.kron(H2, H2)
+    cx = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
+    sw = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+    forms = [lambda: haar_unitary(rng, 4), lambda: hh @ cx, lambda: (hh @ sw) @ np.diag(np.exp(1j * rng.uniform(0, 6, 4))),
+             lambda: cx @ np.diag([1, 1j, 1, np.exp(0.3j)]), lambda: sw]
+    ry = np.array([[np.cos(0.3), -np.sin(0.3)], [np.sin(0.3), np.cos(0.3)]], dtype=np.complex128)
+    ones = [lambda: haar_unitary(rng, 2), lambda: H2.astype(np.complex128), lambda: ry]
+    tile = list(range(7)) + [8, 10, 11, 13, 14]
+    hi = [b for b in tile if b >= 3]
+    gates = []
+    for rep in range(12):
+        bits = [int(b) for b in rng.choice(hi, size=3, replace=False)]
+        blk = BitGate("matrix", (bits[0], bits[1]), (1 << 9) if rep % 5 == 4 else 0, np.ascontiguousarray(forms[rep % 5]()))
+        one = BitGate("matrix", (bits[2],), (1 << 12) if rep % 6 == 5 else 0, np.ascontiguousarray(ones[rep % 3]()))
+        first, second = (blk, one) if rep % 2 == 0 else (one, blk)
+        gates.append(first)
+        if rep % 3 == 1:                                       # something in between that commutes with the partner
+            gates.append(BitGate("matrix", (int(rng.integers(0, n)),), 0, np.diag(np.exp(1j * rng.uniform(0, 6, 2))), True))
+        if rep % 4 == 2:                                       # ... and something that does not (a control on its bit)
+            gates.append(BitGate("matrix", (int(rng.choice([b for b in tile if b not in bits])),), 1 << bits[2], H2.astype(np.complex128)))
+        gates.append(second)
+    p = Pass(True, gates, tuple(tile))
+    monkeypatch.setenv("QIPB_FUSED_PAIR", "0")
+    monkeypatch.setenv("QIPB_FUSED_TRIO", "1")
+    trio, info = run_emulated(emul, psi.copy(), [p], n, dtype)
+    assert info[10] >= 6 and info[9] == info[0], info
+    monkeypatch.setenv("QIPB_FUSED_TRIO", "0")
+    single, info0 = run_emulated(emul, psi.copy(), [p], n, dtype)
+    assert info0[10] == 0, info0
+    tol = 1e-13 if dtype == np.complex128 else 2e-5
+    assert np.max(np.abs(trio - single)) <= tol * np.max(np.abs(single))
+    want = bitsim.run_passes(psi.astype(np.complex128), [p], n)
+    assert np.max(np.abs(trio - want)) <= (1e-12 if dtype == np.complex128 else 1e-5) * np.max(np.abs(want))
