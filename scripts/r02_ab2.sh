@@ -23,5 +23,5 @@ except Exception as e:
 PY
  done
 }
-run trio1 QIPB_FUSED_TRIO=1
-run trio0 QIPB_FUSED_TRIO=0
+run lowp1 QIPB_FUSED_LOWP=1
+run lowp0 QIPB_FUSED_LOWP=0
