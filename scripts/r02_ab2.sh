@@ -23,5 +23,4 @@ except Exception as e:
 PY
  done
 }
-run lowp1 QIPB_FUSED_LOWP=1
-run lowp0 QIPB_FUSED_LOWP=0
+run default
