@@ -34,9 +34,6 @@ namespace qipb {
 #ifndef QIPB_ENABLE_PAIRS
 #define QIPB_ENABLE_PAIRS 0
 #endif
-#ifndef QIPB_ENABLE_LOWP
-#define QIPB_ENABLE_LOWP 1      // sweep_dense2_lowp: low-bit 2-qubit blocks with per-lane permuted coefficients (WIDE kernel)
-#endif
 #ifndef QIPB_ENABLE_TRIOS
 #define QIPB_ENABLE_TRIOS 1     // sweep_trio: a dense 2-qubit block + a lone dense 1-qubit gate per sweep (fits the register budget)
 #endif
@@ -595,64 +592,6 @@ QIPB_HD void sweep_dense2_low(A *tile, const DevGate &g, const EX ex, u32 ngroup
     }
 }
 
-// The same with the permutation moved into the COEFFICIENTS (WIDE kernel: the register budget holds a per-lane copy of
-// the matrix): lane l loads member k ^ R(l) into register k -- one request covers all bank groups as above -- and applies
-// M'[i][j] = M[i ^ R][j ^ R], so the loop has no selects at all: LDS, FP64, STS (the select version costs 229 instructions
-// per group against 183 per TWO groups of the plain sweep; layered passes carry one such block in four).  REALB: real
-// matrix (MK_REAL, 16 real coefficients); otherwise the general complex form.
-template <typename A, int NT, bool REALB>
-QIPB_HD void sweep_dense2_lowp(A *tile, const DevGate &g, u32 ngroups, int tid) {
-    typedef typename amp_traits<A>::real Rl;
-    constexpr int LOWB = LowBits<A>::value;
-    const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
-    const u32 nm0 = g.nmask[0], nm1 = g.nmask[1];
-    const int c = (g.tl[0] < LOWB) + (g.tl[1] < LOWB);
-    const u32 B = (g.tl[0] < LOWB ? 2u : 0u) | (g.tl[1] < LOWB ? 1u : 0u);
-    const u32 rb = ((u32)tid >> (LOWB - c)) & ((1u << c) - 1u);
-    const u32 R = c == 2 ? rb : (rb ? B : 0u);
-    u32 off[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) off[k] = (((k ^ R) & 2u) ? oh : 0u) + (((k ^ R) & 1u) ? ol : 0u);
-    Cf<A> m[REALB ? 1 : 16];
-    Rl r[REALB ? 16 : 1];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int src = 4 * (int)((u32)i ^ R) + (int)((u32)j ^ R);         // per-lane gather, once per sweep
-            if (REALB) r[4 * i + j] = rcoef<A>(g, src);
-            else m[4 * i + j] = coef<A>(g, src);
-        }
-#pragma unroll 1
-    for (u32 it = 0, nit = ngroups / NT, w = tid; it < nit; ++it, w += NT) {
-        u32 e = w;
-        e += e & nm0;
-        e += e & nm1;
-        A *p = tile + e;
-        A x[4], o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) x[k] = p[off[k]];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (REALB) {
-                o[i].x = r[4 * i] * x[0].x;
-                o[i].y = r[4 * i] * x[0].y;
-#pragma unroll
-                for (int j = 1; j < 4; ++j) {
-                    o[i].x = fma(r[4 * i + j], x[j].x, o[i].x);
-                    o[i].y = fma(r[4 * i + j], x[j].y, o[i].y);
-                }
-            } else {
-                o[i] = cmulc<A>(m[4 * i], x[0]);
-#pragma unroll
-                for (int j = 1; j < 4; ++j) cfmac<A>(o[i], m[4 * i + j], x[j]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p[off[k]] = o[k];
-    }
-}
-
 template <typename A, bool UNI, int NT, typename EX>
 QIPB_HD void sweep_dense1_low(A *tile, const DevGate &g, const EX ex, u32 ngroups, int tid) {
     constexpr int LOWB = LowBits<A>::value;
@@ -1020,10 +959,6 @@ QIPB_HD void run_op(A *tile, const DevGate &g, const DevGate &next, const double
             if (g.mk == MK_MONOMIAL) {
                 sweep_mono2<A, UNI, NT>(tile, g, Expand<2>(g), ngroups, tid);
             } else if (g.tl[0] < LowBits<A>::value || g.tl[1] < LowBits<A>::value) {
-                if (QIPB_ENABLE_LOWP && UNI && NT == 128 && g.mk != MK_REALPHASE) {     // WIDE kernel: permuted coefficients, no selects
-                    if (g.mk == MK_REAL) sweep_dense2_lowp<A, NT, true>(tile, g, ngroups, tid);
-                    else sweep_dense2_lowp<A, NT, false>(tile, g, ngroups, tid);
-                } else
                 if (g.mk == MK_REAL) sweep_dense2_low<A, UNI, NT, MK_REAL>(tile, g, Expand<2>(g), ngroups, tid);
                 else if (g.mk == MK_REALPHASE) sweep_dense2_low<A, UNI, NT, MK_REALPHASE>(tile, g, Expand<2>(g), ngroups, tid);
                 else sweep_dense2_low<A, UNI, NT, MK_GENERAL>(tile, g, Expand<2>(g), ngroups, tid);
@@ -1373,11 +1308,6 @@ static bool pair_enabled() {
     return !e || atoi(e) != 0;
 }
 
-static bool lowp_enabled() {
-    const char *e = getenv("QIPB_FUSED_LOWP");                // A/B knob, read per call
-    return !e || atoi(e) != 0;
-}
-
 static bool trio_enabled() {
     if (!QIPB_ENABLE_TRIOS) return false;
     const char *e = getenv("QIPB_FUSED_TRIO");                // A/B knob, read per call
@@ -1401,7 +1331,6 @@ static bool wide_enabled();
 static bool ring_enabled();
 static bool pair_enabled();
 static bool trio_enabled();
-static bool lowp_enabled();
 static inline bool launch_is_wide(const FusedArgs &f, size_t amp_bytes) {
     return launch_is_uni(f, amp_bytes) && f.tb == 12 && wide_enabled() && !ring_enabled();
 }
@@ -1872,11 +1801,6 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                     classify_block(mat, d, [&](int slot, double re, double im) { mc[slot] = make_float2((float)re, (float)im); },
                                    [&](int slot, double v) { mr[slot] = (float)v; });
                     if (d.mk == MK_GENERAL) memcpy(mc, keep, sizeof(keep));
-                    if (QIPB_ENABLE_LOWP && d.mk == MK_REALPHASE && (d.tl[0] < 4 || d.tl[1] < 4) && lowp_enabled() &&
-                        launch_is_wide(f, 8)) {
-                        d.mk = MK_GENERAL;
-                        memcpy(mc, keep, sizeof(keep));
-                    }
                 } else {
                     double2 keep[16];
                     memcpy(keep, d.m, sizeof(keep));
@@ -1884,11 +1808,6 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                     classify_block(mat, d, [&](int slot, double re, double im) { d.m[slot] = make_double2(re, im); },
                                    [&](int slot, double v) { mr[slot] = v; });
                     if (d.mk == MK_GENERAL) memcpy(d.m, keep, sizeof(keep));
-                    if (QIPB_ENABLE_LOWP && d.mk == MK_REALPHASE && (d.tl[0] < 3 || d.tl[1] < 3) && lowp_enabled() &&
-                        launch_is_wide(f, 16)) {               // low-bit block of a WIDE launch: the permuted-coefficient sweep
-                        d.mk = MK_GENERAL;                     // knows the real and the general form only
-                        memcpy(d.m, keep, sizeof(keep));
-                    }
                 }
             }
         }
