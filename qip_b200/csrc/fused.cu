@@ -1139,7 +1139,7 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
         }
 
         // ---- run the gate list on the tile ----
-        bool fetched = false;
+        bool fetched = false, prefetched = false;
         for (int gi = 0; gi < f.ngates; ++gi) {
             if (fused_op_is_skipped<EXT>(f.g[gi])) continue;
             run_fused_op<A, UNI, NT, EXT>(tile, f, gi, stage_S, base, tsize, tid);
@@ -1149,6 +1149,21 @@ __global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB :
             if (sched && !fetched) {
                 if (tid == 0) next_tile = atomicAdd(&sched[0], 1u);
                 fetched = true;
+            } else if (BULK && sched && f.prefetch && fetched && !prefetched) {
+                // optional (QIPB_FUSED_PREFETCH=1): one barrier later every thread may read the next tile's number --
+                // warp 0 pulls that tile into L2 while this one is still being swept, so the CTA's next load is an L2 hit
+                prefetched = true;
+                if (tid < 32) {
+                    const u64 tn = (u64)next_tile;
+                    if (tn < f.ntiles) {
+                        const u64 nbase = fused_tile_base(f, tn);
+                        for (u32 r = tid; r < nruns; r += 32) {
+                            u64 off = 0;
+                            for (int j = f.lowrun; j < f.tb; ++j) off |= (u64)((r >> (j - f.lowrun)) & 1u) << f.tbit[j];
+                            bulk_prefetch_l2(state + nbase + off, run_bytes);
+                        }
+                    }
+                }
             }
         }
 

@@ -113,37 +113,65 @@ __global__ void __launch_bounds__(256) gate1_bit0_kernel(double2 *__restrict__ s
         }
 }
 
-// Dense gate on many target bits (QIPB_MAX_DENSE_K < k <= QIPB_MAX_BIG_K): one CTA per group
-// batch, group staged in shared memory, matrix streamed from global memory (L2 resident).
+// Dense gate on many target bits (QIPB_MAX_DENSE_K < k <= QIPB_MAX_BIG_K): a batched 2^k x 2^k matrix-vector product
+// (kronprod.pyx:157-197 with a wide K: 2^K column probes per output row there).
 struct BigArgs {
     u64 nwork;
     u64 fixed_or;
     int nins;
     int k;
+    int gb;                               // groups per batch (a power of two, <= 32; X[D][gb] fits 128 KiB of shared memory)
     unsigned char ins[QIPB_MAX_INS];
     unsigned char tbit[QIPB_MAX_BIG_K];   // bit position of matrix-index bit j (j = 0 least significant)
 };
-template <typename A>
+// A batch of GB groups (columns) is staged in shared memory as X[D][GB]; thread (gc, rb) = (tid % GB, tid / GB) owns
+// column gc and the rows rb, rb + NRB, ... (NRB = 256 / GB): out[i][gc] = sum_j M[i][j] X[j][gc], RPT rows at a time in
+// registers.  With GB = 32 a warp shares its rows, so the matrix entries are warp-uniform loads served by L1 / L2 (16 KiB
+// at K = 5, 16 MiB at K = 10), the X reads are conflict-free (32 consecutive amplitudes) and for every X value loaded a
+// thread issues 4 * RPT FP64 FMAs: the kernel is FP64 bound (4 * 2^K FMAs per amplitude against 32 bytes moved).  Every
+// input of a batch is in shared memory before the first output is written, so the update is in place.
+template <typename A, int RPT>
 __global__ void __launch_bounds__(256) big_gate_kernel(A *__restrict__ state, const double2 *__restrict__ mat,
                                                         const __grid_constant__ BigArgs g) {
-    extern __shared__ unsigned char smem_raw[];
-    A *grp = reinterpret_cast<A *>(smem_raw);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    A *X = reinterpret_cast<A *>(smem_raw);
     const int D = 1 << g.k;
-    for (u64 w = blockIdx.x; w < g.nwork; w += gridDim.x) {
-        const u64 base = expand_index(w, g.ins, g.nins, g.fixed_or);
-        for (int j = threadIdx.x; j < D; j += blockDim.x) {
-            u64 off = 0;
-            for (int b = 0; b < g.k; ++b) off |= (u64)((j >> b) & 1) << g.tbit[b];
-            grp[j] = state[base + off];
+    const int GB = g.gb, NRB = 256 / GB;
+    const int gc = threadIdx.x % GB, rb = threadIdx.x / GB;
+    for (u64 w0 = (u64)blockIdx.x * GB; w0 < g.nwork; w0 += (u64)gridDim.x * GB) {
+        for (int idx = threadIdx.x; idx < D * GB; idx += 256) {
+            const int j = idx / GB, c = idx % GB;
+            if (w0 + c < g.nwork) {
+                u64 off = 0;
+                for (int b = 0; b < g.k; ++b) off |= (u64)((j >> b) & 1) << g.tbit[b];
+                X[idx] = state[expand_index(w0 + c, g.ins, g.nins, g.fixed_or) + off];
+            }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < D; i += blockDim.x) {
-            A r = make_amp<A>(0, 0);
-            const double2 *row = mat + (size_t)i * D;
-            for (int j = 0; j < D; ++j) cfma<A>(r, row[j], grp[j]);
-            u64 off = 0;
-            for (int b = 0; b < g.k; ++b) off |= (u64)((i >> b) & 1) << g.tbit[b];
-            state[base + off] = r;
+        if (w0 + gc < g.nwork) {
+            const u64 base = expand_index(w0 + gc, g.ins, g.nins, g.fixed_or);
+            for (int i0 = rb; i0 < D; i0 += NRB * RPT) {
+                A acc[RPT];
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) acc[r] = make_amp<A>(0, 0);
+                for (int j = 0; j < D; ++j) {
+                    const A x = X[j * GB + gc];
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        const int i = i0 + NRB * r;
+                        if (i < D) cfma<A>(acc[r], __ldg(mat + (size_t)i * D + j), x);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int i = i0 + NRB * r;
+                    if (i < D) {
+                        u64 off = 0;
+                        for (int b = 0; b < g.k; ++b) off |= (u64)((i >> b) & 1) << g.tbit[b];
+                        state[base + off] = acc[r];
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -225,8 +253,24 @@ static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits,
     double2 *dmat = nullptr;
     QIPB_CUDA(cudaMallocAsync(&dmat, D * D * sizeof(double2), ctx->stream));
     QIPB_CUDA(cudaMemcpyAsync(dmat, mat, D * D * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
-    u64 blocks = g.nwork < (u64)ctx->sm_count * 8 ? g.nwork : (u64)ctx->sm_count * 8;
-    big_gate_kernel<A><<<(unsigned)blocks, 256, D * sizeof(A), ctx->stream>>>(state, dmat, g);
+    g.gb = 32;
+    while ((size_t)g.gb * D * sizeof(A) > 128u * 1024u) g.gb >>= 1;
+    const size_t smem = (size_t)g.gb * D * sizeof(A);
+    const int rows_per_thread = (int)(D / (256 / g.gb));
+    const u64 nbatch = (g.nwork + g.gb - 1) / g.gb;
+    const int per_sm = smem > 100u * 1024u ? 1 : (int)((200u * 1024u) / (smem + 1024));
+    u64 blocks = (u64)ctx->sm_count * (per_sm > 8 ? 8 : per_sm);
+    if (blocks > nbatch) blocks = nbatch;
+    if (rows_per_thread <= 4) {
+        QIPB_CUDA(cudaFuncSetAttribute(big_gate_kernel<A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        big_gate_kernel<A, 4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
+    } else if (rows_per_thread <= 8) {
+        QIPB_CUDA(cudaFuncSetAttribute(big_gate_kernel<A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        big_gate_kernel<A, 8><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
+    } else {
+        QIPB_CUDA(cudaFuncSetAttribute(big_gate_kernel<A, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        big_gate_kernel<A, 16><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
+    }
     ctx->launches++;
     QIPB_CUDA(cudaGetLastError());
     QIPB_CUDA(cudaFreeAsync(dmat, ctx->stream));

@@ -23,4 +23,5 @@ except Exception as e:
 PY
  done
 }
-run default
+run prefetch0 QIPB_FUSED_PREFETCH=0
+run prefetch1 QIPB_FUSED_PREFETCH=1
