@@ -27,7 +27,10 @@ PY
 timeout 600 $TR --master-port 29612 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > $O/${R}_bench_reference_n$N.json 2> $O/${R}_ref.err
 cut -c1-600 $O/${R}_bench_reference_n$N.json
 if [ -n "$EXTRA" ]; then
- timeout 600 $TR --master-port 29613 bench.py --gpus $N --workload qft --statetype complex64 --steps 2 --warmup 1 --no-parity > $O/${R}_bench_qft_c64_n$N.json 2> $O/${R}_x.err
+ QIPB_SHARD_OVERLAP=0 timeout 600 $TR --master-port 29615 bench.py --gpus $N --steps 6 --warmup 3 --no-parity > $O/${R}_bench_n${N}_overlap0.json 2> $O/${R}_x.err
+ python -c "
+import json; d = json.load(open('$O/${R}_bench_n${N}_overlap0.json')); print('overlap OFF N=$N layered ms/step %.1f, qft %.3f s' % (d['ms_per_step'], d['qft']['seconds']))" || tail -20 $O/${R}_x.err
+ timeout 600 $TR --master-port 29613 bench.py --gpus $N --workload qft --statetype complex64 --total-qubits 36 --steps 2 --warmup 1 --no-parity > $O/${R}_bench_qft_c64_n$N.json 2> $O/${R}_x.err
  python -c "
 import json; d = json.load(open('$O/${R}_bench_qft_c64_n$N.json')); print('qft c64 N=$N qubits', d['config']['qubits'], 'seconds', d.get('qft_seconds'), d['config']['stats'])" || tail -20 $O/${R}_x.err
  timeout 600 $TR --master-port 29614 bench.py --gpus $N --workload qft --total-qubits 33 --steps 2 --warmup 1 --no-parity > $O/${R}_bench_qft_strong33_n$N.json 2> $O/${R}_x.err
