@@ -416,7 +416,7 @@ class B200Backend(object):
             self._keepalive = dev_table
 
     # ------------------------------------------------------------------ measurement
-    def _probabilities(self, indices, order: str, filter_mask: int = 0, filter_value: int = 0):
+    def _probabilities(self, indices, order: str, filter_mask: int = 0, filter_value: int = 0, on_device: bool = False):
         """order 'given-le': bit j of the bin = qubit indices[j] (measure_probabilities,
         qip/ext/kronprod.pyx:258-259).  order 'sorted-be': big-endian over the measured qubits
         sorted by index (entwine_bit, qip/ext/util.pyx:1-23)."""
@@ -440,7 +440,7 @@ class B200Backend(object):
             _lib.check(self.L.qipb_probabilities(self.ctx, self._ptr(), n, self.code, k, _lib.int_array(bits),
                                                  _lib.int_array(outb), filter_mask, filter_value,
                                                  ctypes.c_void_p(out.data_ptr())))
-            return out.cpu().numpy()
+            return out if on_device else out.cpu().numpy()
 
     def _mask_value(self, indices, m):
         """State-index mask of the measured qubits and the bit pattern of outcome m (big-endian
@@ -522,6 +522,8 @@ class B200Backend(object):
     def measure_probabilities(self, indices, top_k: int = 0):
         """qip/backend.py:158-163."""
         if top_k:
+            if len(indices) > _DEVICE_TOPK_MIN_QUBITS:         # wide histograms are ranked where they are
+                return top_probabilities_device(self._probabilities(indices, "sorted-be", on_device=True), top_k)
             probs = self._probabilities(indices, "sorted-be")
             return top_probabilities(probs, top_k)
         return self._probabilities(indices, "given-le")
@@ -721,6 +723,19 @@ def top_probabilities(probs_big_endian, top_k):
     k = min(int(top_k), len(probs))
     order = np.argsort(-probs, kind="stable")[:k]
     return [int(i) for i in order], [float(probs[i]) for i in order]
+
+
+_DEVICE_TOPK_MIN_QUBITS = 16     # histograms over more measured qubits are ranked on the device
+
+
+def top_probabilities_device(probs_dev, top_k):
+    """top_probabilities on a device-resident histogram: a stable descending sort keeps equal probabilities in ascending
+    outcome order, like numpy's stable argsort of the negated values; only the k winners cross PCIe (a 27-qubit Grover
+    histogram is 1 GiB).  torch's sort is plumbing here, not the hot path: one call per StochasticMeasure node."""
+    torch = _torch()
+    k = min(int(top_k), int(probs_dev.shape[0]))
+    vals, idx = torch.sort(probs_dev, descending=True, stable=True)
+    return [int(i) for i in idx[:k].cpu().numpy()], [float(v) for v in vals[:k].cpu().numpy()]
 
 
 def device_table(func, table: np.ndarray, device, nbits_out: int = 64):

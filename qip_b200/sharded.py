@@ -739,7 +739,7 @@ class ShardedB200Backend(object):
         glob = [p for p in pos_list if p >= self.nl]
         return loc, glob
 
-    def _probabilities(self, indices, order: str, filter_qubits=(), filter_value_bits=()):
+    def _probabilities(self, indices, order: str, filter_qubits=(), filter_value_bits=(), on_device: bool = False):
         """Histogram over `indices`; filter = (qubits, their required bit values)."""
         torch = _torch()
         n = self.n
@@ -785,7 +785,7 @@ class ShardedB200Backend(object):
                     tgt |= ((j >> t) & 1) << ob
                 out.index_copy_(0, torch.from_numpy(tgt).to(self.device), part)
             self.dist.all_reduce(out)
-            return out.cpu().numpy()
+            return out if on_device else out.cpu().numpy()
 
     def total_prob(self) -> float:
         return float(self._probabilities([], "sorted-be")[0])
@@ -891,6 +891,9 @@ class ShardedB200Backend(object):
 
     def measure_probabilities(self, indices, top_k: int = 0):
         if top_k:
+            from .backend import _DEVICE_TOPK_MIN_QUBITS, top_probabilities_device
+            if len(indices) > _DEVICE_TOPK_MIN_QUBITS:
+                return top_probabilities_device(self._probabilities(indices, "sorted-be", on_device=True), top_k)
             return top_probabilities(self._probabilities(indices, "sorted-be"), top_k)
         return self._probabilities(indices, "given-le")
 

@@ -209,3 +209,21 @@ def test_bench_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_wide_top_k_is_ranked_on_the_device_with_the_same_tie_order(monkeypatch):
+    # measure_probabilities(top_k) over more than 16 qubits sorts the histogram where it is (stable, descending: equal
+    # probabilities in ascending outcome order, like the host path) and brings only the winners back
+    from qip_b200 import B200Backend
+    from qip_b200 import backend as be
+    hostlib.install(monkeypatch)
+    n = 17
+    feeds = [np.array([1.0, 1.0]) / np.sqrt(2)] * 14 + [np.array([0.6, 0.8]), np.array([1.0, 0.0]), np.array([0.8, 0.6])]
+    b = B200Backend.make_state(n, [[q] for q in range(n)], feeds)
+    idx = np.arange(n, dtype=np.int32)
+    got_i, got_p = b.measure_probabilities(idx, top_k=9)
+    monkeypatch.setattr(be, "_DEVICE_TOPK_MIN_QUBITS", 64)
+    want_i, want_p = b.measure_probabilities(idx, top_k=9)
+    assert got_i == want_i and got_p == want_p
+    assert got_i == sorted(got_i) and len(set(got_p)) == 1          # nine tied winners, ascending outcomes
+    b.close()
