@@ -44,6 +44,19 @@ def run_cases(quick=False, log=print):
     / compiled-circuit / lazy-init cases stay with the pytest tier.  Returns {"cases": checks passed, "max_err": ...}."""
     REPORT["cases"], REPORT["max_err"] = 0, 0.0
     rank, world = dist.get_rank(), dist.get_world_size()
+    # the exchange / compute pipeline is on for large shards only; the parity tier runs it at every size
+    saved = os.environ.get("QIPB_OVERLAP_MIN_BYTES")
+    os.environ["QIPB_OVERLAP_MIN_BYTES"] = "0"
+    try:
+        return _run_cases(quick, log, rank, world)
+    finally:
+        if saved is None:
+            os.environ.pop("QIPB_OVERLAP_MIN_BYTES", None)
+        else:
+            os.environ["QIPB_OVERLAP_MIN_BYTES"] = saved
+
+
+def _run_cases(quick, log, rank, world):
     n = 12
     rng = np.random.default_rng(5)
     psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)

@@ -294,6 +294,7 @@ def test_exchange_compute_overlap_pipeline_on_virtual_ranks(monkeypatch, P, chun
     # chunk untouched
     from qip_b200.sharded import ShardedB200Backend
     monkeypatch.setenv("QIPB_OVERLAP_CHUNK_BITS", str(chunk_bits))
+    monkeypatch.setenv("QIPB_OVERLAP_MIN_BYTES", "0")
     n = 9 + int(np.log2(P))
     rng = np.random.default_rng(P + chunk_bits)
     psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
