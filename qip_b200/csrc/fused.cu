@@ -307,6 +307,48 @@ QIPB_HD void sweep_dense2(A *tile, const DevGate &g, const EX ex, u32 ngroups, i
     }
 }
 
+// ---- dense 2-qubit block (no controls) with the following stage applied to the group while it is in registers ----
+// (WIDE kernel.)  The planner sinks the lone diagonal gates of a pass into one table stage; on its own that stage is a
+// whole round trip of the tile through shared memory for one table look-up and two complex multiplies per amplitude.  Here
+// it rides on the block's sweep like a QFT stage rides on its Hadamard: member m of the group gets S * T_lo * T_hi at its
+// own index; a thread's indices keep their low `lo` bits over the sweep, so the four S * T_lo factors are folded once.
+template <typename A, int NT, int MK>
+QIPB_HD void sweep_dense2_stage(A *tile, const DevGate &g, const StageRef sr, u32 ngroups, int tid) {
+    const u32 oh = 1u << g.tl[0], ol = 1u << g.tl[1];
+    const u32 nm0 = g.nmask[0], nm1 = g.nmask[1];
+    const u32 sor = sr.sor, lom = sr.nlo - 1u;
+    const int lo = sr.lo;
+    const Block2<A, MK> blk(g);
+    const double2 *__restrict__ Th = sr.T + sr.nlo;
+    u32 e0 = (u32)tid;
+    e0 += e0 & nm0;
+    e0 += e0 & nm1;
+    const u32 off[4] = {0u, ol, oh, oh + ol};
+    double2 SL[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) SL[m] = cmul<double2>(sr.S, sr.T[(e0 | off[m]) & lom]);
+#pragma unroll 1
+    for (u32 it = 0, nit = ngroups / NT, w = tid; it < nit; ++it, w += NT) {
+        u32 e = w;
+        e += e & nm0;
+        e += e & nm1;
+        A *p = tile + e;
+        const A a0 = p[0], a1 = p[ol], a2 = p[oh], a3 = p[oh + ol];
+        double2 th[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) th[m] = Th[(e | off[m]) >> lo];
+        A r[4];
+        blk.apply(a0, a1, a2, a3, r);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (((e | off[m]) & sor) == sor) r[m] = cmul<A>(cmul<double2>(SL[m], th[m]), r[m]);
+        p[0] = r[0];
+        p[ol] = r[1];
+        p[oh] = r[2];
+        p[oh + ol] = r[3];
+    }
+}
+
 // permutation with phases (Swap, CX / CZ-like blocks with phase gates folded in): pure data movement plus at
 // most one complex multiply per amplitude; column j goes to row perm[j]
 template <typename A, bool UNI, int NT, typename EX>
@@ -1027,6 +1069,13 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
             }
             return;
         }
+        if (NT == 128 && g.post == 8) {                         // dense 2-qubit block + the stage behind it (WIDE launches only)
+            const StageRef sr = stage_ref(f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tables, stage_S[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi], f.tb);
+            if (g.mk == MK_REAL) sweep_dense2_stage<A, NT, MK_REAL>(tile, g, sr, tsize >> 2, tid);
+            else if (g.mk == MK_REALPHASE) sweep_dense2_stage<A, NT, MK_REALPHASE>(tile, g, sr, tsize >> 2, tid);
+            else sweep_dense2_stage<A, NT, MK_GENERAL>(tile, g, sr, tsize >> 2, tid);
+            return;
+        }
         if (QIPB_ENABLE_TRIOS && NT == 128 && g.post == 6) {    // block + lone 1-qubit gate (WIDE launches only): ops gi, gi + 1
             const DevGate &h = f.g[gi + 1 < FUSED_MAX_OPS ? gi + 1 : gi];
             const bool on_a = (base & g.out_ctrl) == g.out_ctrl, on_c = (base & h.out_ctrl) == h.out_ctrl;
@@ -1323,6 +1372,11 @@ static bool pair_enabled() {
     return !e || atoi(e) != 0;
 }
 
+static bool ride2_enabled() {
+    const char *e = getenv("QIPB_FUSED_RIDE2");               // stage riding on a dense 2-qubit sweep (WIDE kernel); A/B knob
+    return !e || atoi(e) != 0;
+}
+
 static bool trio_enabled() {
     if (!QIPB_ENABLE_TRIOS) return false;
     const char *e = getenv("QIPB_FUSED_TRIO");                // A/B knob, read per call
@@ -1346,6 +1400,7 @@ static bool wide_enabled();
 static bool ring_enabled();
 static bool pair_enabled();
 static bool trio_enabled();
+static bool ride2_enabled();
 static inline bool launch_is_wide(const FusedArgs &f, size_t amp_bytes) {
     return launch_is_uni(f, amp_bytes) && f.tb == 12 && wide_enabled() && !ring_enabled();
 }
@@ -1832,6 +1887,12 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                 DevGate &d = f.g[oi], &nx = f.g[oi + 1];
                 if (!d.diag && d.k == 1 && d.nins == 1 && d.out_ctrl == 0 && nx.diag == 2) {
                     d.post = 1;
+                    nx.diag = 3;
+                } else if (ride2_enabled() && launch_is_wide(f, dtype == QIPB_C128 ? 16 : 8) && !d.diag && d.k == 2 && d.nins == 2 &&
+                           d.out_ctrl == 0 && d.in_or == 0 && d.mk != MK_MONOMIAL && d.tl[0] != 0xFF && d.tl[1] != 0xFF &&
+                           d.tl[0] >= (dtype == QIPB_C128 ? 3 : 4) && d.tl[1] >= (dtype == QIPB_C128 ? 3 : 4) &&
+                           nx.diag == 2 && nx.out_ctrl == 0) {
+                    d.post = 8;                                // the stage rides on the block's sweep (sweep_dense2_stage)
                     nx.diag = 3;
                 }
             }

@@ -23,5 +23,5 @@ except Exception as e:
 PY
  done
 }
-run prefetch0 QIPB_FUSED_PREFETCH=0
-run prefetch1 QIPB_FUSED_PREFETCH=1
+run ride2_1 QIPB_FUSED_RIDE2=1
+run ride2_0 QIPB_FUSED_RIDE2=0

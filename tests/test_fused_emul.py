@@ -428,3 +428,37 @@ def test_emulated_trios_match_separate_sweeps(emul, monkeypatch, dtype, seed):
     assert np.max(np.abs(trio - single)) <= tol * np.max(np.abs(single))
     want = bitsim.run_passes(psi.astype(np.complex128), [p], n)
     assert np.max(np.abs(trio - want)) <= (1e-12 if dtype == np.complex128 else 1e-5) * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_emulated_stage_rides_on_a_dense_two_qubit_sweep(emul, monkeypatch, dtype):
+    # sweep_dense2_stage: the table stage behind an un-controlled dense 2-qubit block is applied while the group is in
+    # registers (every block form; stages with and without a common in-tile control; targets below and above the table split)
+    n = 15
+    rng = np.random.default_rng(7)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi = (psi / np.linalg.norm(psi)).astype(dtype)
+    hh = np.kron(H2, H2)
+    cx = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
+    tile = list(range(7)) + [8, 10, 11, 13, 14]
+    gates = []
+    for rep, (bits, mat) in enumerate([((10, 13), haar_unitary(rng, 4)), ((4, 11), hh @ cx), ((8, 5), (hh @ cx) @ np.diag(np.exp(1j * rng.uniform(0, 6, 4)))),
+                                       ((14, 3), haar_unitary(rng, 4))]):
+        gates.append(BitGate("matrix", bits, 0, np.ascontiguousarray(mat)))
+        common = (1 << 6) if rep % 2 else 0                       # a stage needs >= 3 diagonal gates in a row
+        for b in (0, 2, 7, 9, 12, bits[0]):
+            if (1 << b) != common:
+                gates.append(BitGate("matrix", (), (1 << b) | common, np.diag([np.exp(0.2j * (b + 1 + rep))]), True))
+    p = Pass(True, gates, tuple(tile))
+    monkeypatch.setenv("QIPB_FUSED_TRIO", "0")
+    monkeypatch.setenv("QIPB_FUSED_PAIR", "0")
+    monkeypatch.setenv("QIPB_FUSED_RIDE2", "1")
+    ride, info = run_emulated(emul, psi.copy(), [p], n, dtype)
+    assert info[11] >= 3, info                                    # (complex64: bit 3 is a bank-conflict bit, that block does not ride)
+    monkeypatch.setenv("QIPB_FUSED_RIDE2", "0")
+    plain, info0 = run_emulated(emul, psi.copy(), [p], n, dtype)
+    assert info0[11] == 0, info0
+    tol = 1e-13 if dtype == np.complex128 else 2e-5
+    assert np.max(np.abs(ride - plain)) <= tol * np.max(np.abs(plain))
+    want = bitsim.run_passes(psi.astype(np.complex128), [p], n)
+    assert np.max(np.abs(ride - want)) <= (1e-12 if dtype == np.complex128 else 1e-5) * np.max(np.abs(want))
