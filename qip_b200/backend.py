@@ -118,7 +118,7 @@ class B200Backend(object):
 
     def __init__(self, n: int, dtype, device=None, fuse: bool = True, tile_bits: int = 12, min_low_bits: int = 7,
                  strategy: str = "auto", relabel_swaps: bool = True, host_state_max_qubits: int = _HOST_STATE_MAX_QUBITS,
-                 lazy_init=None):
+                 lazy_init=None, adopt_feed: bool = False):
         torch = _torch()
         self.L = _lib.load()
         if not torch.cuda.is_available():
@@ -134,6 +134,10 @@ class B200Backend(object):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.fuse = fuse
         self.host_state_max_qubits = host_state_max_qubits   # get_state(): host ndarray up to here, DeviceState beyond
+        # adopt_feed: a whole-register DEVICE feed (a DeviceState / CUDA tensor of a previous run) becomes this state's buffer
+        # instead of being copied -- the caller gives it up (its content changes with the first gate).  Without it an
+        # iterated re-feed holds two states at once: 2 x 128 GiB at 33 qubits does not fit a 180 GB part.
+        self.adopt_feed = bool(adopt_feed)
         self.plan_cache = None       # (dict, key) set by qip_b200.graph.CompiledCircuit: planned passes per gate segment
         import os
         self.tile_bits = int(os.environ.get("QIPB_TILE_BITS", tile_bits))               # tuning knob for profiling runs
@@ -190,6 +194,16 @@ class B200Backend(object):
                 src = feed_list[0].tensor if isinstance(feed_list[0], DeviceState) else feed_list[0]
                 if src.shape[0] != 2 ** n:
                     raise ValueError("feed length must be 2**len(group)")
+                same = src.device == self.device and src.dtype == self.tdtype and src.is_contiguous()
+                if self.adopt_feed and same:
+                    self.state = src                          # ownership handed over: no second 2^n buffer
+                    return
+                need = self.amp_bytes * 2 ** n
+                free = torch.cuda.mem_get_info(self.device)[0] if hasattr(torch.cuda, "mem_get_info") else None
+                if free is not None and need > free:
+                    raise ValueError("a copy of the fed {}-qubit device state needs {:.0f} GiB, {:.0f} GiB are free: pass "
+                                     "adopt_feed=True to make_state (the fed buffer then becomes this state)".format(
+                                         n, need / 2 ** 30, free / 2 ** 30))
                 self.state = src.to(device=self.device, dtype=self.tdtype, copy=True)
                 return
             self.state = torch.empty(2 ** n, dtype=self.tdtype, device=self.device)
@@ -769,8 +783,15 @@ def device_table(func, table: np.ndarray, device, nbits_out: int = 64):
 
 
 def tabulate(func, nbits_in: int) -> np.ndarray:
-    """f(x) for x < 2^nbits_in as int64 (qip/ext/func_apply.pyx:66-69).  Tries one vectorised call
-    on a numpy array first (and cross-checks it on a sample), falls back to the reference's loop."""
+    """f(x) for x < 2^nbits_in as int64 (qip/ext/func_apply.pyx:66-69: the reference calls `func` once per x).
+
+    One vectorised call on a numpy int64 array replaces the 2^n python calls when that is safe:
+      * functions that declare it (`func.vectorized = True`: everything in qip_b200.functions) are trusted;
+      * for any other callable the vectorised result is accepted only after it has been checked against plain python
+        calls -- on EVERY x for tables of up to 2^16 entries, on 256 sampled points (both ends included) beyond.  numpy
+        wraps int64 silently where python integers grow, and a data-dependent branch may act on the whole array at once;
+        both show up as a mismatch and the reference's loop is used instead.
+    A function that carries its table (`func.table`, qip_b200.functions.tabulated) is returned as it is."""
     size = 2 ** nbits_in
     table = getattr(func, "table", None)                       # a function that carries its own table (qip_b200.functions)
     if isinstance(table, np.ndarray) and table.shape == (size,) and table.dtype.kind in "iu":
@@ -783,7 +804,12 @@ def tabulate(func, nbits_in: int) -> np.ndarray:
             ys = np.full(size, int(ys), dtype=np.int64)
         if ys.shape == (size,) and ys.dtype.kind in "iub":
             ys = ys.astype(np.int64)
-            probe = np.unique(np.concatenate(([0, size - 1], np.random.default_rng(0).integers(0, size, 14))))
+            if getattr(func, "vectorized", False):
+                return np.ascontiguousarray(ys)
+            if size <= (1 << 16):
+                probe = xs
+            else:
+                probe = np.unique(np.concatenate(([0, 1, size - 2, size - 1], np.random.default_rng(0).integers(0, size, 252))))
             if all(int(func(int(x))) == int(ys[x]) for x in probe):
                 return np.ascontiguousarray(ys)
     except Exception:

@@ -11,6 +11,7 @@ def equals(x0: int):
     """x -> 1 if x == x0 else 0: the Grover oracle of examples/grovers_iterative.py:20-21."""
     def f(x):
         return (x == x0) * 1
+    f.vectorized = True                     # accepts numpy int64 arrays (backend.tabulate trusts the vectorised call)
     return f
 
 
@@ -33,6 +34,7 @@ def modexp(base: int, modulus: int):
             b = (b * b) % modulus
             e >>= 1
         return result
+    f.vectorized = True                     # exact on int64 arrays while modulus < 2**31 (checked above)
     return f
 
 
