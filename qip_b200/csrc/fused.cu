@@ -38,7 +38,7 @@ namespace qipb {
 #define QIPB_ENABLE_TRIOS 1     // sweep_trio: a dense 2-qubit block + a lone dense 1-qubit gate per sweep (fits the register budget)
 #endif
 #ifndef QIPB_WIDE_MINB
-#define QIPB_WIDE_MINB 3
+#define QIPB_WIDE_MINB 4      /* cap 128 registers: three CTAs of the pass AND one 256-thread remap CTA fit an SM (the chunk pipeline) */
 #endif
 #define FUSED_THREADS 256
 #define FUSED_MAX_INS 12
@@ -879,6 +879,80 @@ QIPB_HD void sweep_qft2(A *tile, const DevGate &ga, const StageRef sa, const Dev
     }
 }
 
+// Four QFT steps in one sweep: a radix-16 butterfly on groups of 16 amplitudes held in registers (WIDE kernel).  Member
+// index k has bit j = the bit of step j's Hadamard (steps in execution order).  Step j: for every pair (k0, k1 = k0 | 2^j)
+//   x[k0] <- x[k0] + x[k1],   x[k1] <- (x[k0] - x[k1]) * phase_j(k1)
+// and the four Hadamard scales are applied once at the end.  The stage phase at a member's index factorises into what the
+// rest of the index contributes -- S * T_lo * T_hi at the group's base index: one table look-up per step and group, the
+// low-cell factor folded once per thread -- times what the member's own bits contribute: M_j[k1 without bit j], eight
+// complex constants per step that the host derives from the tables (slots 8..15 of the Hadamard's descriptor, always
+// double2) after checking that the tables really factorise over those bits (true for the controlled phases of a QFT:
+// every gate of the stage couples the target with ONE other bit).  Same FP64 work as two radix-4 sweeps (about 26
+// instructions per amplitude), half the shared-memory traffic, index arithmetic and barriers.
+template <typename A, int NT>
+QIPB_HD void sweep_qft4(A *tile, const FusedArgs &f, int gi, const double2 *stage_S, u32 ngroups, int tid) {
+    typedef typename amp_traits<A>::real R;
+    const DevGate &h0 = f.g[gi], &h1 = f.g[gi + 2], &h2 = f.g[gi + 4], &h3 = f.g[gi + 6];
+    const StageRef s0 = stage_ref(f.g[gi + 1], f.tables, stage_S[gi + 1], f.tb), s1 = stage_ref(f.g[gi + 3], f.tables, stage_S[gi + 3], f.tb);
+    const StageRef s2 = stage_ref(f.g[gi + 5], f.tables, stage_S[gi + 5], f.tb), s3 = stage_ref(f.g[gi + 7], f.tables, stage_S[gi + 7], f.tb);
+    const u32 o0 = 1u << h0.tl[0], o1 = 1u << h1.tl[0], o2 = 1u << h2.tl[0], o3 = 1u << h3.tl[0];
+    const u32 nm0 = h0.nmask[2], nm1 = h0.nmask[3], nm2 = h0.nmask[4], nm3 = h0.nmask[5];
+    const u32 lom = s0.nlo - 1u;
+    const int lo = s0.lo;
+    const double2 *__restrict__ T0 = s0.T + s0.nlo, *__restrict__ T1 = s1.T + s1.nlo;
+    const double2 *__restrict__ T2 = s2.T + s2.nlo, *__restrict__ T3 = s3.T + s3.nlo;
+    const double scale = (double)rcoef<A>(h0, 0) * (double)rcoef<A>(h1, 0) * (double)rcoef<A>(h2, 0) * (double)rcoef<A>(h3, 0);
+    u32 e0 = (u32)tid;
+    e0 += e0 & nm0;
+    e0 += e0 & nm1;
+    e0 += e0 & nm2;
+    e0 += e0 & nm3;
+    const double2 SL0 = cmul<double2>(s0.S, s0.T[e0 & lom]), SL1 = cmul<double2>(s1.S, s1.T[e0 & lom]);
+    const double2 SL2 = cmul<double2>(s2.S, s2.T[e0 & lom]);
+    double2 SL3 = cmul<double2>(s3.S, s3.T[e0 & lom]);
+    SL3.x *= scale;                                            // the last step's phased members take the scale with their phase
+    SL3.y *= scale;
+#pragma unroll 1
+    for (u32 it = 0, nit = ngroups / NT, w = tid; it < nit; ++it, w += NT) {
+        u32 e = w;
+        e += e & nm0;
+        e += e & nm1;
+        e += e & nm2;
+        e += e & nm3;
+        A *p = tile + e;
+        A x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = p[((k & 1) ? o0 : 0u) + ((k & 2) ? o1 : 0u) + ((k & 4) ? o2 : 0u) + ((k & 8) ? o3 : 0u)];
+        const u32 eh = e >> lo;
+        const double2 P0 = cmul<double2>(SL0, T0[eh]), P1 = cmul<double2>(SL1, T1[eh]);
+        const double2 P2 = cmul<double2>(SL2, T2[eh]), P3 = cmul<double2>(SL3, T3[eh]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const DevGate &h = j == 0 ? h0 : j == 1 ? h1 : j == 2 ? h2 : h3;
+            const double2 P = j == 0 ? P0 : j == 1 ? P1 : j == 2 ? P2 : P3;
+#pragma unroll
+            for (int k0 = 0; k0 < 16; ++k0) {
+                if (k0 & (1 << j)) continue;
+                const int k1 = k0 | (1 << j);
+                const int idx = (k1 & ((1 << j) - 1)) | ((k1 >> (j + 1)) << j);      // k1 without bit j
+                A u, d;
+                u.x = x[k0].x + x[k1].x;
+                u.y = x[k0].y + x[k1].y;
+                d.x = x[k0].x - x[k1].x;
+                d.y = x[k0].y - x[k1].y;
+                if (j == 3) {
+                    u.x *= (R)scale;
+                    u.y *= (R)scale;
+                }
+                x[k0] = u;
+                x[k1] = cmul<A>(cmul<double2>(P, h.m[8 + idx]), d);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) p[((k & 1) ? o0 : 0u) + ((k & 2) ? o1 : 0u) + ((k & 4) ? o2 : 0u) + ((k & 8) ? o3 : 0u)] = x[k];
+    }
+}
+
 // Fill mode (EXT kernel, qipb_apply_fused_fill): the pass acts on the all-ones vector instead of the buffer's
 // content, and its first op is a stage without controls -- the tile is WRITTEN from the phase tables instead of being
 // loaded from HBM.  A product state of one-qubit feeds is exactly that: prod_b diag(v_b[0], v_b[1]) . ones
@@ -1091,6 +1165,10 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
         }
         if (g.diag == 5) {                                      // fill mode: op 0 writes the tile (no controls, host-checked)
             sweep_stage_fill<A, NT>(tile, stage_ref(g, f.tables, stage_S[gi], f.tb), tsize, tid);
+            return;
+        }
+        if (NT == 128 && g.post == 9) {                         // ops gi .. gi+7 = four QFT steps (WIDE launches only)
+            sweep_qft4<A, NT>(tile, f, gi, stage_S, tsize >> 4, tid);
             return;
         }
         if (g.post == 2) {                                      // ops gi .. gi+3 = H_a, stage a, H_b, stage b
@@ -1372,6 +1450,11 @@ static bool pair_enabled() {
     return !e || atoi(e) != 0;
 }
 
+static bool qft4_enabled() {
+    const char *e = getenv("QIPB_FUSED_QFT4");                // four QFT steps per sweep (WIDE kernel); A/B knob, read per call
+    return !e || atoi(e) != 0;
+}
+
 static bool ride2_enabled() {
     const char *e = getenv("QIPB_FUSED_RIDE2");               // stage riding on a dense 2-qubit sweep (WIDE kernel); A/B knob
     return !e || atoi(e) != 0;
@@ -1401,6 +1484,7 @@ static bool ring_enabled();
 static bool pair_enabled();
 static bool trio_enabled();
 static bool ride2_enabled();
+static bool qft4_enabled();
 static inline bool launch_is_wide(const FusedArgs &f, size_t amp_bytes) {
     return launch_is_uni(f, amp_bytes) && f.tb == 12 && wide_enabled() && !ring_enabled();
 }
@@ -1917,11 +2001,68 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                     for (int e = 0; e < 4; ++e) mr[e] = mat[2 * e];
                 }
             }
+            // a QFT step = Hadamard (post == 1, exact s * [[1, 1], [1, -1]]) + its stage (diag == 3, controlled by exactly the
+            // Hadamard's target, nothing outside the tile)
+            auto qft_step = [&](size_t oi) {
+                if (oi + 1 >= cnt) return false;
+                const DevGate &a = f.g[oi], &sa = f.g[oi + 1];
+                return a.post == 1 && a.mk == MK1_REAL && a.phmask && sa.diag == 3 && sa.out_ctrl == 0 && ops[first + oi + 1].stage;
+            };
+            const bool wide = launch_is_wide(f, dtype == QIPB_C128 ? 16 : 8);
+            const int lo_bits = f.tb < FUSED_LO_BITS ? f.tb : FUSED_LO_BITS;
+            // M_j[k1 without bit j] of sweep_qft4 for the stage at op `so`, member positions pos[0..3]; false if the stage's
+            // tile tables do not factorise over the member bits
+            auto member_factors = [&](size_t so, const unsigned char *pos, int j, cplx *out8) {
+                const cplx *Tlo = tables.data() + ops[first + so].tab_off, *Thi = Tlo + ((size_t)1 << lo_bits);
+                u32 mlo = 0, mhi = 0;
+                for (int t = 0; t < 4; ++t) {
+                    if (pos[t] < lo_bits) mlo |= 1u << pos[t];
+                    else mhi |= 1u << (pos[t] - lo_bits);
+                }
+                auto factorises = [&](const cplx *T, u32 size, u32 mask) {
+                    if (T[0] == cplx(0.0, 0.0)) return false;
+                    for (u32 v = 0; v < size; ++v) {
+                        const cplx lhs = T[v] * T[0], rhs = T[v & mask] * T[v & ~mask];
+                        if (std::abs(lhs - rhs) > 1e-13 * (std::abs(lhs) + std::abs(rhs) + 1e-300)) return false;
+                    }
+                    return true;
+                };
+                if (!factorises(Tlo, 1u << lo_bits, mlo) || !factorises(Thi, 1u << (f.tb - lo_bits), mhi)) return false;
+                for (int k1 = 0; k1 < 16; ++k1) {
+                    if (!(k1 & (1 << j))) continue;
+                    u32 vlo = 0, vhi = 0;
+                    for (int t = 0; t < 4; ++t)
+                        if (k1 & (1 << t)) {
+                            if (pos[t] < lo_bits) vlo |= 1u << pos[t];
+                            else vhi |= 1u << (pos[t] - lo_bits);
+                        }
+                    const int idx = (k1 & ((1 << j) - 1)) | ((k1 >> (j + 1)) << j);
+                    out8[idx] = (Tlo[vlo] / Tlo[0]) * (Thi[vhi] / Thi[0]);
+                }
+                return true;
+            };
             for (size_t oi = 0; oi + 3 < cnt;) {
-                DevGate &a = f.g[oi], &sa = f.g[oi + 1], &b = f.g[oi + 2], &sb = f.g[oi + 3];
-                const bool pair = a.post == 1 && b.post == 1 && a.mk == MK1_REAL && b.mk == MK1_REAL && a.phmask && b.phmask &&
-                                  a.tl[0] != b.tl[0] && sa.diag == 3 && sb.diag == 3 && sa.out_ctrl == 0 && sb.out_ctrl == 0;
-                if (pair) {
+                if (wide && qft4_enabled() && oi + 7 < cnt && qft_step(oi) && qft_step(oi + 2) && qft_step(oi + 4) && qft_step(oi + 6)) {
+                    const unsigned char pos[4] = {f.g[oi].tl[0], f.g[oi + 2].tl[0], f.g[oi + 4].tl[0], f.g[oi + 6].tl[0]};
+                    bool ok = pos[0] != pos[1] && pos[0] != pos[2] && pos[0] != pos[3] && pos[1] != pos[2] && pos[1] != pos[3] && pos[2] != pos[3];
+                    cplx M[4][8];
+                    for (int j = 0; j < 4 && ok; ++j) ok = member_factors(oi + 2 * j + 1, pos, j, M[j]);
+                    if (ok) {
+                        for (int j = 0; j < 4; ++j) {
+                            DevGate &h = f.g[oi + 2 * j];
+                            for (int t = 0; t < 8; ++t) h.m[8 + t] = make_double2(M[j][t].real(), M[j][t].imag());
+                            h.post = j == 0 ? 9 : 3;
+                        }
+                        unsigned char srt[4] = {pos[0], pos[1], pos[2], pos[3]};
+                        for (int x = 1; x < 4; ++x)
+                            for (int y = x; y > 0 && srt[y] < srt[y - 1]; --y) std::swap(srt[y], srt[y - 1]);
+                        for (int x = 0; x < 4; ++x) f.g[oi].nmask[2 + x] = ~((1u << srt[x]) - 1u);
+                        oi += 8;
+                        continue;
+                    }
+                }
+                DevGate &a = f.g[oi], &b = f.g[oi + 2];
+                if (qft_step(oi) && qft_step(oi + 2) && a.tl[0] != b.tl[0]) {
                     a.post = 2;
                     b.post = 3;
                     oi += 4;

@@ -23,5 +23,5 @@ except Exception as e:
 PY
  done
 }
-run ride2_1 QIPB_FUSED_RIDE2=1
-run ride2_0 QIPB_FUSED_RIDE2=0
+run qft4_1 QIPB_FUSED_QFT4=1
+run qft4_0 QIPB_FUSED_QFT4=0

@@ -67,6 +67,7 @@ int emulate(A *state, const FusedArgs &f, int *info) {
         info[8] += g.post == 4;
         info[10] += g.post == 6;
         info[11] += g.post == 8;
+        info[12] += g.post == 9;
     }
     // the same choice of kernel instantiation as launch_fused (qip_b200/csrc/fused.cu)
     if (half) emulate_launch<A, true, 128, false>(state, f);
@@ -86,11 +87,12 @@ int emulate(A *state, const FusedArgs &f, int *info) {
 
 // info[0] launches, [1] of which take the specialised (UNI) sweeps, [2] stages, [3] stages riding on a dense 1-qubit
 // sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates, [7] launches that carry EXT ops,
-// [8] block pairs (two dense 2-qubit blocks in one sweep), [9] launches of the WIDE kernel, [10] trios (block + lone 1-qubit gate), [11] stages riding on a dense 2-qubit sweep
+// [8] block pairs (two dense 2-qubit blocks in one sweep), [9] launches of the WIDE kernel, [10] trios (block + lone 1-qubit gate), [11] stages riding on a dense 2-qubit sweep,
+// [12] radix-16 QFT sweeps (four steps each)
 static int emul_impl(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
                      const qipb_gate *gates, int *info, bool fill, FusedChunk chunk = FusedChunk{0, nullptr, 0}) {
     QIPB_REQUIRE(host_state && info, "null argument");
-    for (int i = 0; i < 12; ++i) info[i] = 0;
+    for (int i = 0; i < 16; ++i) info[i] = 0;
     return lower_fused(
         nbits, dtype, ntile_bits, tile_bits, ngates, gates,
         [&](const std::vector<cplx> &tables, FusedArgs &f) {

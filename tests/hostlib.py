@@ -142,7 +142,7 @@ class HostLib(object):
 
     def _fused(self, fn, name, state, nbits, code, ntile, tile_bits, ngates, gates):
         self.log.append(name)
-        info = (ctypes.c_int * 12)()
+        info = (ctypes.c_int * 16)()
         rc = fn(_addr(state), nbits, code, ntile, tile_bits, ngates, gates, info)
         if rc:
             self.err = self.emul.qipb_emul_last_error()
@@ -155,7 +155,7 @@ class HostLib(object):
 
     def qipb_apply_fused_chunk(self, ctx, state, nbits, code, ntile, tile_bits, ngates, gates, nfix, fix_bits, fix_value):
         self.log.append("apply_fused_chunk")
-        info = (ctypes.c_int * 12)()
+        info = (ctypes.c_int * 16)()
         before = _amps(state, nbits, code).copy() if self.check_chunk_isolation else None
         rc = self.emul.qipb_emul_fused_chunk(_addr(state), nbits, code, ntile, tile_bits, ngates, gates, info, nfix, fix_bits,
                                              ctypes.c_ulonglong(int(fix_value)))

@@ -51,14 +51,14 @@ def logical_gates(stream, n):
 def run_emulated(L, state, passes, n, dtype):
     """Fused passes through the emulator, stand-alone passes through the bit simulator."""
     code = qlib.C128 if dtype == np.complex128 else qlib.C64
-    info_total = np.zeros(12, dtype=np.int64)
+    info_total = np.zeros(16, dtype=np.int64)
     st = np.ascontiguousarray(state, dtype=dtype)
     for p in passes:
         if not p.fused:
             st = np.ascontiguousarray(bitsim.run_passes(st.astype(np.complex128), [p], n), dtype=dtype)
             continue
         arr, tbits = pack_pass(p)
-        info = (ctypes.c_int * 12)()
+        info = (ctypes.c_int * 16)()
         rc = L.qipb_emul_fused(st.ctypes.data_as(ctypes.c_void_p), n, code, len(p.tile_bits), tbits, len(p.gates), arr, info)
         assert rc == 0, L.qipb_emul_last_error()
         info_total += np.array(list(info))
@@ -138,7 +138,7 @@ def test_emulated_block_pairs_match_unpaired_passes(emul, monkeypatch, dtype, se
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
 def test_emulated_qfft_stages_ride_on_the_hadamard_sweeps(emul, dtype):
     info = check(emul, qfft_stream(15), 15, 1, dtype)
-    assert info[2] >= 10 and info[3] + 2 * info[5] >= 10, info    # (paired steps carry post = 2 / 3 instead of 1)
+    assert info[2] >= 10 and info[3] + 2 * info[5] + 4 * info[12] >= 10, info    # (grouped steps carry post = 2 / 3 / 9 instead of 1)
 
 
 def test_emulated_small_tiles_take_the_generic_sweeps(emul):
@@ -193,7 +193,7 @@ def test_emulator_reports_lowering_errors(emul):
     g[0].bits[0] = 12                      # non-diagonal target that is not a tile bit
     g[0].mat[0] = 1.0
     st = np.zeros(2 ** 13, dtype=np.complex128)
-    info = (ctypes.c_int * 12)()
+    info = (ctypes.c_int * 16)()
     rc = emul.qipb_emul_fused(st.ctypes.data_as(ctypes.c_void_p), 13, qlib.C128, 12, qlib.int_array(range(12)), 1, g, info)
     assert rc != 0 and b"not a tile bit" in emul.qipb_emul_last_error()
 
@@ -203,6 +203,7 @@ def test_emulator_reports_lowering_errors(emul):
 @pytest.mark.parametrize("n", [13, 15, 16])
 def test_emulated_ext_qfft_pairs_two_steps_per_sweep(emul, monkeypatch, dtype, n):
     monkeypatch.setenv("QIPB_FUSED_EXT", "1")
+    monkeypatch.setenv("QIPB_FUSED_QFT4", "0")                 # (the radix-16 form has its own test)
     info = check(emul, qfft_stream(n), n, n, dtype)
     assert info[5] >= 3 and info[6] >= 2 * info[5] and info[7] >= 1, info
     monkeypatch.setenv("QIPB_FUSED_EXT", "0")
@@ -324,7 +325,7 @@ def test_emulated_fill_mode_builds_the_product_state_inside_the_first_pass(emul,
     want = bitsim.run_passes(psi.copy(), passes[:1], n)
     st = np.full(2 ** n, np.nan + 1j * np.nan, dtype=dtype)            # the buffer's content must never be read
     arr, tbits, ng = _fill_args(factors, passes[0])
-    info = (ctypes.c_int * 12)()
+    info = (ctypes.c_int * 16)()
     rc = emul.qipb_emul_fused_fill(st.ctypes.data_as(ctypes.c_void_p), n, qlib.C128 if dtype == np.complex128 else qlib.C64,
                                    len(passes[0].tile_bits), tbits, ng, arr, info)
     assert rc == 0, emul.qipb_emul_last_error()
@@ -351,7 +352,7 @@ def test_emulated_fill_mode_refuses_what_it_cannot_serve(emul):
     p = ops.Pass(True, [g, g], tuple(range(10)))
     arr, tbits, ng = _fill_args(factors, p)
     st = np.zeros(2 ** n, dtype=np.complex128)
-    info = (ctypes.c_int * 12)()
+    info = (ctypes.c_int * 16)()
     rc = emul.qipb_emul_fused_fill(st.ctypes.data_as(ctypes.c_void_p), n, qlib.C128, 10, tbits, ng, arr, info)
     assert rc == qlib.ERR_UNSUPPORTED and info[0] == 0 and not st.any()
 
@@ -462,3 +463,30 @@ def test_emulated_stage_rides_on_a_dense_two_qubit_sweep(emul, monkeypatch, dtyp
     assert np.max(np.abs(ride - plain)) <= tol * np.max(np.abs(plain))
     want = bitsim.run_passes(psi.astype(np.complex128), [p], n)
     assert np.max(np.abs(ride - want)) <= (1e-12 if dtype == np.complex128 else 1e-5) * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n", [13, 15, 17])
+def test_emulated_qfft_takes_four_steps_per_sweep(emul, monkeypatch, dtype, n):
+    # sweep_qft4: a radix-16 butterfly with the member phases factorised out of the stage tables by the host; against the
+    # radix-4 / single-step forms and the bit simulator, incl. a QFT on a sub-register and a stage that does NOT factorise
+    monkeypatch.setenv("QIPB_FUSED_QFT4", "1")
+    info = check(emul, qfft_stream(n), n, n, dtype)
+    assert info[12] >= 1, info
+    monkeypatch.setenv("QIPB_FUSED_QFT4", "0")
+    info0 = check(emul, qfft_stream(n), n, n, dtype)
+    assert info0[12] == 0 and info0[5] > info[5], (info0, info)
+    monkeypatch.setenv("QIPB_FUSED_QFT4", "1")
+    stream = list(qfft_stream(9, first_qubit=2)) + list(layered_stream(n, 1, 3)) + list(qfft_stream(n))
+    check(emul, stream, n, 4, dtype)
+    # a stage whose gates couple TWO other bits (a doubly-controlled phase) does not factorise: that group must fall back
+    q = list(range(n))
+    odd = []
+    for k in range(4):
+        odd.append({q[k]: H2})
+        for i in range(k + 1, n):
+            odd.append({(q[i], q[k]): CMat(rm_mat(1 + i - k))})
+        if k == 1:
+            odd.append({(q[5], q[6], q[k]): CMat(CMat(rm_mat(3)))})
+            odd.append({(q[7], q[6], q[k]): CMat(CMat(rm_mat(2)))})
+    check(emul, odd, n, 5, dtype)
