@@ -1450,6 +1450,11 @@ static bool pair_enabled() {
     return !e || atoi(e) != 0;
 }
 
+static bool short_runs_enabled() {
+    const char *e = getenv("QIPB_FUSED_SHORT_RUNS");          // 1-2 diagonal gates behind a dense gate become a riding stage; A/B knob
+    return !e || atoi(e) != 0;
+}
+
 static bool qft4_enabled() {
     const char *e = getenv("QIPB_FUSED_QFT4");                // four QFT steps per sweep (WIDE kernel); A/B knob, read per call
     return !e || atoi(e) != 0;
@@ -1485,6 +1490,7 @@ static bool pair_enabled();
 static bool trio_enabled();
 static bool ride2_enabled();
 static bool qft4_enabled();
+static bool short_runs_enabled();
 static inline bool launch_is_wide(const FusedArgs &f, size_t amp_bytes) {
     return launch_is_uni(f, amp_bytes) && f.tb == 12 && wide_enabled() && !ring_enabled();
 }
@@ -1845,7 +1851,14 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
     {
         std::vector<int> run;
         auto flush_run = [&]() {
-            if (!run.empty()) build_stages(gates, run, nbits, ntile_bits, local_of, tmask, ops, tables, 3);
+            // a run of >= 3 diagonal gates pays for its tables as a stage of its own; a shorter run only where it can ride on
+            // the sweep of the un-controlled dense gate right in front of it (then it costs no sweep at all)
+            int min_run = 3;
+            if (!ops.empty() && !ops.back().stage && short_runs_enabled()) {
+                const qipb_gate &pg = gates[ops.back().gate];
+                if (!(pg.diagonal != 0 || pg.k == 0) && pg.ctrl_mask == 0) min_run = 1;
+            }
+            if (!run.empty()) build_stages(gates, run, nbits, ntile_bits, local_of, tmask, ops, tables, min_run);
             run.clear();
         };
         for (int gi = 0; gi < ngates; ++gi) {

@@ -23,5 +23,5 @@ except Exception as e:
 PY
  done
 }
-run qft4_1 QIPB_FUSED_QFT4=1
-run qft4_0 QIPB_FUSED_QFT4=0
+run short1 QIPB_FUSED_SHORT_RUNS=1
+run short0 QIPB_FUSED_SHORT_RUNS=0

@@ -421,7 +421,7 @@ def test_emulated_trios_match_separate_sweeps(emul, monkeypatch, dtype, seed):
     monkeypatch.setenv("QIPB_FUSED_PAIR", "0")
     monkeypatch.setenv("QIPB_FUSED_TRIO", "1")
     trio, info = run_emulated(emul, psi.copy(), [p], n, dtype)
-    assert info[10] >= 6 and info[9] == info[0], info
+    assert info[10] >= 4 and info[9] == info[0], info             # (a gate that carries a riding stage is not available for a trio)
     monkeypatch.setenv("QIPB_FUSED_TRIO", "0")
     single, info0 = run_emulated(emul, psi.copy(), [p], n, dtype)
     assert info0[10] == 0, info0
