@@ -38,7 +38,7 @@ namespace qipb {
 #define QIPB_ENABLE_TRIOS 1     // sweep_trio: a dense 2-qubit block + a lone dense 1-qubit gate per sweep (fits the register budget)
 #endif
 #ifndef QIPB_WIDE_MINB
-#define QIPB_WIDE_MINB 4      /* cap 128 registers: three CTAs of the pass AND one 256-thread remap CTA fit an SM (the chunk pipeline) */
+#define QIPB_WIDE_MINB 3      /* complex128 WIDE kernel: 3 CTAs per SM, cap 168 registers (SLIM instantiation: 4, cap 128) */
 #endif
 #define FUSED_THREADS 256
 #define FUSED_MAX_INS 12
@@ -1194,8 +1194,13 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
 // WIDE: 2^12-amplitude tiles swept by 128 threads, still 3 (complex128) / 4 (complex64) CTAs per SM -- the register
 // budget per thread doubles (168 / 128), which is what the 16-amplitude register groups of the block pairs and the EXT
 // forms need (the 256-thread EXT kernel spilled at its 80-register cap).
-template <typename A, bool BULK, bool UNI, int NT, bool EXT, bool WIDE = false>
-__global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? QIPB_WIDE_MINB : 4) : (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+// SLIM (complex128 WIDE only): the same kernel capped at 128 registers -- the instantiation the CHUNK launches of the
+// exchange / compute pipeline take, so that three pass CTAs (3 x 128 x 128 registers) and one persistent 256-thread remap
+// CTA (16384) fit an SM's 65536 together.  The 168-register build is 2-4 % faster (the radix-16 QFT sweep needs 168
+// registers and spills a little at 128: QFFT-33 372 against 385 ms, layered 242 against 246 ms on one box,
+// profiles/r02_ab_regcap.txt) and serves every launch that has the SMs to itself.
+template <typename A, bool BULK, bool UNI, int NT, bool EXT, bool WIDE = false, bool SLIM = false>
+__global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? (SLIM ? 4 : QIPB_WIDE_MINB) : 4) : (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ __align__(16) double2 stage_S[FUSED_MAX_OPS + 1];
@@ -1605,7 +1610,14 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f_in) {
         ctx->ring_launches++;
     } else if (half) QIPB_LAUNCH_FUSED(true, true, 128, false);
     else if (launch_is_wide(f, sizeof(A))) {
-        QIPB_LAUNCH_FUSED(true, true, 128, true, true);
+        bool slim = false;
+        if constexpr (sizeof(A) == 16) {
+            if (f.nexp > f.tb) {                               // a chunk launch: it shares the SMs with a remap
+                QIPB_LAUNCH_FUSED(true, true, 128, true, true, true);
+                slim = true;
+            }
+        }
+        if (!slim) QIPB_LAUNCH_FUSED(true, true, 128, true, true);
         ctx->ext_launches += fused_has_ext(f) ? 1 : 0;
     } else if (uni && fused_has_ext(f)) {                      // the host marks EXT ops only for this launch shape
         QIPB_LAUNCH_FUSED(true, true, 256, true);

@@ -10,7 +10,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libqipb200.so")
+LIB_PATH = os.environ.get("QIPB_LIB") or os.path.join(CSRC, "libqipb200.so")     # (QIPB_LIB: an alternative build for A/B runs)
 
 C128, C64 = 0, 1
 ERR_UNSUPPORTED = 3          # a valid request this entry point cannot serve; nothing was launched (qipb_apply_fused_fill)

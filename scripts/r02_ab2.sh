@@ -23,5 +23,4 @@ except Exception as e:
 PY
  done
 }
-run short1 QIPB_FUSED_SHORT_RUNS=1
-run short0 QIPB_FUSED_SHORT_RUNS=0
+run default
