@@ -953,6 +953,105 @@ QIPB_HD void sweep_qft4(A *tile, const FusedArgs &f, int gi, const double2 *stag
     }
 }
 
+// QFT steps on the LOWEST tile bits (0..2, the bank-conflict bits): up to three consecutive "Hadamard + stage" steps in one
+// sweep, butterflies across LANES.  A thread keeps amplitude e = tid + NT * i, so consecutive lanes hold consecutive
+// amplitudes (every shared-memory request is conflict free) and the partner of a pair on bit b <= 4 sits in lane ^ 2^b:
+// one __shfl_xor of the two components.  With y = the partner's value a lane computes y + x (its bit b clear) or
+// y - x (bit set), both as fma(sign, x, y), times a per-lane multiplier: s, or s * S * T_lo * T_hi at its own index where
+// the stage's in-tile controls are satisfied (T_lo folded once per thread: the low six bits of e never change).  10 FP64 instructions, 4 shuffles and one table
+// look-up per amplitude and step -- against a sweep of its own per step with 2- to 4-way bank conflicts before: the 12-bit
+// pass at the low end of a QFT carried three such sweeps (128 ms of a 372 ms QFFT-33, profiles/r02_ab_qft4.txt).
+template <typename A, int NT>
+QIPB_HD void sweep_qft_low(A *tile, const FusedArgs &f, int gi, int nsteps, const double2 *stage_S, u32 tsize, int tid) {
+    typedef typename amp_traits<A>::real R;
+#if defined(__CUDA_ARCH__)
+    const u32 lane_e = (u32)tid;
+    u32 bpos[3], sor[3];
+    double sc[3];
+    double2 SL[3];
+    const double2 *Th[3];
+    int lo = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int gj = j < nsteps ? gi + 2 * j : gi;            // (unused slots mirror step 0; never applied)
+        const DevGate &h = f.g[gj];
+        const StageRef sr = stage_ref(f.g[gj + 1], f.tables, stage_S[gj + 1], f.tb);
+        bpos[j] = h.tl[0];
+        sor[j] = sr.sor;                                       // in-tile controls of the stage (usually just the target bit)
+        sc[j] = (double)coef<A>(h, 0).x;
+        SL[j] = cmul<double2>(sr.S, sr.T[lane_e & (sr.nlo - 1u)]);
+        SL[j].x *= sc[j];
+        SL[j].y *= sc[j];
+        Th[j] = sr.T + sr.nlo;
+        lo = sr.lo;
+    }
+    constexpr int U = 4;
+#pragma unroll 1
+    for (u32 i = 0, n = tsize / NT; i < n; i += U) {
+        A x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = tile[lane_e + NT * (i + u)];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j >= nsteps) break;
+            const u32 b = bpos[j];
+            const bool hi = ((lane_e >> b) & 1u) != 0u;
+            const double sgn = hi ? -1.0 : 1.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const u32 e = lane_e + NT * (i + u);
+                const double2 th = Th[j][e >> lo];
+                A y;
+                y.x = __shfl_xor_sync(0xffffffffu, x[u].x, 1 << b);
+                y.y = __shfl_xor_sync(0xffffffffu, x[u].y, 1 << b);
+                A r;
+                r.x = fma((R)sgn, x[u].x, y.x);
+                r.y = fma((R)sgn, x[u].y, y.y);
+                double2 mult = cmul<double2>(SL[j], th);
+                if ((e & sor[j]) != sor[j]) mult = make_double2(sc[j], 0.0);
+                x[u] = cmul<A>(mult, r);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) tile[lane_e + NT * (i + u)] = x[u];
+    }
+#else
+    // host emulation (tests/csrc/fused_emul.cu runs "threads" one after another: no shuffles): the same arithmetic pair by
+    // pair, executed once by the thread that owns the pair's lower member
+    for (int j = 0; j < nsteps; ++j) {
+        const DevGate &h = f.g[gi + 2 * j];
+        const StageRef sr = stage_ref(f.g[gi + 2 * j + 1], f.tables, stage_S[gi + 2 * j + 1], f.tb);
+        const u32 b = h.tl[0];
+        const double s = (double)coef<A>(h, 0).x;
+        const double2 *T_hi = sr.T + sr.nlo;
+        // a step is complete over the whole tile before the next one starts on the device (all lanes advance together per
+        // batch, and batches are independent); on the host "thread" tid handles its amplitudes for step j only when called
+        // with that step -- the emulator calls this function once per thread, so thread 0 does the whole tile
+        if (tid != 0) continue;
+        for (u32 e = 0; e < tsize; ++e) {
+            if ((e >> b) & 1u) continue;
+            const u32 e1 = e | (1u << b);
+            const A x0 = tile[e], x1 = tile[e1];
+            double2 SLl = cmul<double2>(sr.S, sr.T[e1 & (sr.nlo - 1u)]);
+            SLl.x *= s;
+            SLl.y *= s;
+            const double2 ph = cmul<double2>(SLl, T_hi[e1 >> sr.lo]);
+            double2 SL0 = cmul<double2>(sr.S, sr.T[e & (sr.nlo - 1u)]);
+            SL0.x *= s;
+            SL0.y *= s;
+            const double2 ph0 = cmul<double2>(SL0, T_hi[e >> sr.lo]);
+            A u, d;
+            u.x = fma((R)1.0, x0.x, x1.x);
+            u.y = fma((R)1.0, x0.y, x1.y);
+            d.x = fma((R)-1.0, x1.x, x0.x);
+            d.y = fma((R)-1.0, x1.y, x0.y);
+            tile[e] = cmul<A>((e & sr.sor) == sr.sor ? ph0 : make_double2(s, 0.0), u);
+            tile[e1] = cmul<A>((e1 & sr.sor) == sr.sor ? ph : make_double2(s, 0.0), d);
+        }
+    }
+#endif
+}
+
 // Fill mode (EXT kernel, qipb_apply_fused_fill): the pass acts on the all-ones vector instead of the buffer's
 // content, and its first op is a stage without controls -- the tile is WRITTEN from the phase tables instead of being
 // loaded from HBM.  A product state of one-qubit feeds is exactly that: prod_b diag(v_b[0], v_b[1]) . ones
@@ -1165,6 +1264,10 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
         }
         if (g.diag == 5) {                                      // fill mode: op 0 writes the tile (no controls, host-checked)
             sweep_stage_fill<A, NT>(tile, stage_ref(g, f.tables, stage_S[gi], f.tb), tsize, tid);
+            return;
+        }
+        if (NT == 128 && g.post == 10) {                        // g.pair consecutive QFT steps on the lowest tile bits (WIDE launches)
+            sweep_qft_low<A, NT>(tile, f, gi, (int)g.pair, stage_S, tsize, tid);
             return;
         }
         if (NT == 128 && g.post == 9) {                         // ops gi .. gi+7 = four QFT steps (WIDE launches only)
@@ -1455,6 +1558,11 @@ static bool pair_enabled() {
     return !e || atoi(e) != 0;
 }
 
+static bool qftlow_enabled() {
+    const char *e = getenv("QIPB_FUSED_QFTLOW");              // QFT steps on the lowest tile bits as lane butterflies; A/B knob
+    return !e || atoi(e) != 0;
+}
+
 static bool short_runs_enabled() {
     const char *e = getenv("QIPB_FUSED_SHORT_RUNS");          // 1-2 diagonal gates behind a dense gate become a riding stage; A/B knob
     return !e || atoi(e) != 0;
@@ -1496,6 +1604,7 @@ static bool trio_enabled();
 static bool ride2_enabled();
 static bool qft4_enabled();
 static bool short_runs_enabled();
+static bool qftlow_enabled();
 static inline bool launch_is_wide(const FusedArgs &f, size_t amp_bytes) {
     return launch_is_uni(f, amp_bytes) && f.tb == 12 && wide_enabled() && !ring_enabled();
 }
@@ -2066,6 +2175,35 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                 }
                 return true;
             };
+            // QFT steps on the bank-conflict bits: Hadamard-like dense 1-qubit gate (general descriptor form: the real forms
+            // are only marked above those bits) + its stage, up to three in a row -> one lane-butterfly sweep
+            auto low_step = [&](size_t oi) {
+                if (oi + 1 >= cnt) return false;
+                const DevGate &a = f.g[oi], &sa = f.g[oi + 1];
+                if (!(a.post == 1 && !a.diag && a.k == 1 && a.nins == 1 && a.tl[0] < lowb && a.out_ctrl == 0 && a.in_or == 0)) return false;
+                if (!(sa.diag == 3 && sa.out_ctrl == 0 && ops[first + oi + 1].stage) || ops[first + oi].stage) return false;
+                const double *mat = gates[ops[first + oi].gate].mat;
+                return mat[1] == 0.0 && mat[3] == 0.0 && mat[5] == 0.0 && mat[7] == 0.0 && mat[0] != 0.0 && mat[0] == mat[2] &&
+                       mat[0] == mat[4] && mat[0] == -mat[6];
+            };
+            if (wide && qftlow_enabled())
+                for (size_t oi = 0; oi + 1 < cnt;) {
+                    int nst = 0;
+                    while (nst < 3 && low_step(oi + 2 * nst)) {
+                        bool distinct = true;
+                        for (int t = 0; t < nst; ++t) distinct = distinct && f.g[oi + 2 * t].tl[0] != f.g[oi + 2 * nst].tl[0];
+                        if (!distinct) break;
+                        ++nst;
+                    }
+                    if (nst == 0) {
+                        ++oi;
+                        continue;
+                    }
+                    f.g[oi].post = 10;
+                    f.g[oi].pair = (unsigned char)nst;
+                    for (int t = 1; t < nst; ++t) f.g[oi + 2 * t].post = 3;
+                    oi += 2 * nst;
+                }
             for (size_t oi = 0; oi + 3 < cnt;) {
                 if (wide && qft4_enabled() && oi + 7 < cnt && qft_step(oi) && qft_step(oi + 2) && qft_step(oi + 4) && qft_step(oi + 6)) {
                     const unsigned char pos[4] = {f.g[oi].tl[0], f.g[oi + 2].tl[0], f.g[oi + 4].tl[0], f.g[oi + 6].tl[0]};
@@ -2213,6 +2351,11 @@ static int lower_fused(int nbits, int dtype, int ntile_bits, const int *tile_bit
                 if (!g.diag && g.k == 1) { d1++; d1real += g.mk == MK1_REAL; }
                 sweeps += !(g.diag == 3 || g.post == 3 || g.post == 5);
             }
+            if (atoi(getenv("QIPB_DEBUG")) >= 2)
+                for (size_t oi = 0; oi < cnt; ++oi)
+                    fprintf(stderr, "[qipb]   op %2zu: k=%d diag=%d post=%d mk=%d nins=%d tl=(%d,%d) in_or=%x out_ctrl=%llx pair=%d\n", oi, f.g[oi].k,
+                            f.g[oi].diag, f.g[oi].post, f.g[oi].mk, f.g[oi].nins, f.g[oi].tl[0], f.g[oi].tl[1], f.g[oi].in_or,
+                            (unsigned long long)f.g[oi].out_ctrl, f.g[oi].pair);
             fprintf(stderr, "[qipb] fused launch: %d gates -> %d ops, %d sweeps | 2q general %d real %d realphase %d mono %d (low-bit %d, in-tile ctrl %d, pairs %d) | "
                             "1q %d (real %d, +stage %d, qft2 %d) | lone diag %d | stages %d | tables %zu\n",
                     ngates, (int)cnt, sweeps, mk[0], mk[1], mk[2], mk[3], low2, ctl2, npair, d1, d1real, npost, nqft2, ndiag, nst, tables.size());

@@ -23,4 +23,5 @@ except Exception as e:
 PY
  done
 }
-run default
+run qftlow1 QIPB_FUSED_QFTLOW=1
+run qftlow0 QIPB_FUSED_QFTLOW=0

@@ -68,6 +68,7 @@ int emulate(A *state, const FusedArgs &f, int *info) {
         info[10] += g.post == 6;
         info[11] += g.post == 8;
         info[12] += g.post == 9;
+        info[13] += g.post == 10 ? g.pair : 0;
     }
     // the same choice of kernel instantiation as launch_fused (qip_b200/csrc/fused.cu)
     if (half) emulate_launch<A, true, 128, false>(state, f);
@@ -88,7 +89,7 @@ int emulate(A *state, const FusedArgs &f, int *info) {
 // info[0] launches, [1] of which take the specialised (UNI) sweeps, [2] stages, [3] stages riding on a dense 1-qubit
 // sweep, [4] structured 2-qubit blocks, [5] paired QFT steps, [6] real 1-qubit gates, [7] launches that carry EXT ops,
 // [8] block pairs (two dense 2-qubit blocks in one sweep), [9] launches of the WIDE kernel, [10] trios (block + lone 1-qubit gate), [11] stages riding on a dense 2-qubit sweep,
-// [12] radix-16 QFT sweeps (four steps each)
+// [12] radix-16 QFT sweeps (four steps each), [13] QFT steps on the lowest tile bits taken by lane-butterfly sweeps
 static int emul_impl(void *host_state, int nbits, int dtype, int ntile_bits, const int *tile_bits, int ngates,
                      const qipb_gate *gates, int *info, bool fill, FusedChunk chunk = FusedChunk{0, nullptr, 0}) {
     QIPB_REQUIRE(host_state && info, "null argument");

@@ -490,3 +490,20 @@ def test_emulated_qfft_takes_four_steps_per_sweep(emul, monkeypatch, dtype, n):
             odd.append({(q[5], q[6], q[k]): CMat(CMat(rm_mat(3)))})
             odd.append({(q[7], q[6], q[k]): CMat(CMat(rm_mat(2)))})
     check(emul, odd, n, 5, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n", [13, 16])
+def test_emulated_qft_steps_on_the_lowest_bits(emul, monkeypatch, dtype, n):
+    # sweep_qft_low: the Hadamard + phase steps on tile bits 0..2 (one sweep for up to three of them; on the device the
+    # butterflies cross lanes, the emulator runs the same arithmetic pair by pair) against the per-step sweeps
+    monkeypatch.setenv("QIPB_FUSED_QFTLOW", "1")
+    info = check(emul, qfft_stream(n), n, n + 1, dtype)
+    assert info[13] >= 2, info                                    # (the last Hadamard of a QFT has no phases behind it)
+    monkeypatch.setenv("QIPB_FUSED_QFTLOW", "0")
+    info0 = check(emul, qfft_stream(n), n, n + 1, dtype)
+    assert info0[13] == 0, info0
+    monkeypatch.setenv("QIPB_FUSED_QFTLOW", "1")
+    # a QFT whose register ends on bit 1 / bit 0 only, and one that is followed by other gates on the low bits
+    check(emul, list(qfft_stream(n - 1, first_qubit=0)) + list(layered_stream(n, 1, 2)), n, 3, dtype)
+    check(emul, list(layered_stream(n, 1, 5)) + list(qfft_stream(n - 2, first_qubit=2)), n, 4, dtype)
