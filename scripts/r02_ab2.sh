@@ -23,5 +23,4 @@ except Exception as e:
 PY
  done
 }
-run qftlow1 QIPB_FUSED_QFTLOW=1
-run qftlow0 QIPB_FUSED_QFTLOW=0
+run default
