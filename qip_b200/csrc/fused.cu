@@ -37,6 +37,10 @@ namespace qipb {
 #ifndef QIPB_ENABLE_TRIOS
 #define QIPB_ENABLE_TRIOS 1     // sweep_trio: a dense 2-qubit block + a lone dense 1-qubit gate per sweep (fits the register budget)
 #endif
+#ifndef QIPB_WIDE_MINB_C64
+#define QIPB_WIDE_MINB_C64 6  /* complex64 WIDE kernel: 32 KiB tiles, SIX CTAs per SM fit the shared memory -- keep the registers at <= 80 so
+                                 that they fit the register file too (at 110 registers only four did: layered 34 q 282 -> 350 ms) */
+#endif
 #ifndef QIPB_WIDE_MINB
 #define QIPB_WIDE_MINB 3      /* complex128 WIDE kernel: 3 CTAs per SM, cap 168 registers (SLIM instantiation: 4, cap 128) */
 #endif
@@ -1303,7 +1307,7 @@ QIPB_HD void run_fused_op(A *tile, const FusedArgs &f, int gi, const double2 *st
 // registers and spills a little at 128: QFFT-33 372 against 385 ms, layered 242 against 246 ms on one box,
 // profiles/r02_ab_regcap.txt) and serves every launch that has the SMs to itself.
 template <typename A, bool BULK, bool UNI, int NT, bool EXT, bool WIDE = false, bool SLIM = false>
-__global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? (SLIM ? 4 : QIPB_WIDE_MINB) : 4) : (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
+__global__ void __launch_bounds__(NT, WIDE ? (sizeof(A) == 16 ? (SLIM ? 4 : QIPB_WIDE_MINB) : QIPB_WIDE_MINB_C64) : (sizeof(A) == 16 ? 3 : 4) * (256 / NT)) fused_kernel(A *__restrict__ state, const __grid_constant__ FusedArgs f) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ __align__(16) double2 stage_S[FUSED_MAX_OPS + 1];
