@@ -12,7 +12,9 @@ typedef unsigned int u32;
 
 // Sweep arithmetic and index helpers are host+device so that tests/csrc/fused_emul.cu can run the very same
 // code on a CPU tile (the product never executes them on the host).
+#ifndef QIPB_HD      /* (tests/csrc/fused_emul.cu overrides it: forced inlining of every sweep makes the HOST compile take minutes) */
 #define QIPB_HD __host__ __device__ __forceinline__
+#endif
 
 // ---- amplitude types -------------------------------------------------------------------
 // complex128 amplitude = double2 (one 128-bit transaction), complex64 = float2 (64-bit).

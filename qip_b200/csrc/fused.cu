@@ -1685,8 +1685,11 @@ static bool dynsched_enabled() {
     return v != 0;
 }
 
+// The kernels are compiled in two translation units so that `make -j` halves the build: this file as it is carries the
+// complex128 instantiations and all host code; compiled with -DQIPB_FUSED_TU_C64 (-> fused_c64.o) it carries nothing but
+// launch_fused<float2> and the complex64 kernels behind it.
 template <typename A>
-static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f_in) {
+int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f_in) {
     static thread_local FusedArgs f;                           // (a copy: the scheduling slot is per launch)
     f = f_in;
     f.sched = nullptr;
@@ -1746,6 +1749,11 @@ static int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f_in) {
 }
 
 
+#ifdef QIPB_FUSED_TU_C64
+template int launch_fused<float2>(qipb_ctx *ctx, float2 *state, const FusedArgs &f_in);
+}  // namespace qipb
+#else
+extern template int launch_fused<float2>(qipb_ctx *ctx, float2 *state, const FusedArgs &f_in);     // fused_c64.o
 
 // ---- host side: folding runs of diagonal gates into stages -------------------------------------
 static bool post_enabled() {
@@ -2402,3 +2410,4 @@ extern "C" int qipb_apply_fused_fill(qipb_ctx *ctx, void *state, int nbits, int 
                                      int ngates, const qipb_gate *gates) {
     return apply_fused_impl(ctx, state, nbits, dtype, ntile_bits, tile_bits, ngates, gates, true);
 }
+#endif  // QIPB_FUSED_TU_C64

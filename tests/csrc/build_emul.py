@@ -13,7 +13,7 @@ def build() -> str:
     deps.append(os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "qip_b200.h"))
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
-    cmd = ["nvcc", "-O1", "-std=c++17", "-DQIPB_ENABLE_PAIRS=1", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared",
+    cmd = ["nvcc", "-O1", "-Xptxas", "-O0", "-Xcicc", "-O0", "-std=c++17", "-DQIPB_ENABLE_PAIRS=1", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared",
            "-o", SO, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
