@@ -1753,7 +1753,9 @@ int launch_fused(qipb_ctx *ctx, A *state, const FusedArgs &f_in) {
 template int launch_fused<float2>(qipb_ctx *ctx, float2 *state, const FusedArgs &f_in);
 }  // namespace qipb
 #else
+#ifndef QIPB_FUSED_SINGLE_TU                                  /* (the test harness tests/csrc/fused_emul.cu is one translation unit) */
 extern template int launch_fused<float2>(qipb_ctx *ctx, float2 *state, const FusedArgs &f_in);     // fused_c64.o
+#endif
 
 // ---- host side: folding runs of diagonal gates into stages -------------------------------------
 static bool post_enabled() {

@@ -10,6 +10,7 @@
 // lowering and the sweep arithmetic against the numpy bit simulator (tests/test_fused_emul.py).
 #include <math.h>
 #include <stdarg.h>
+#define QIPB_FUSED_SINGLE_TU
 #define QIPB_HD __host__ __device__ inline      /* no forced inlining here: the host compile of this harness drops from minutes to seconds */
 #include "../../qip_b200/csrc/fused.cu"
 
