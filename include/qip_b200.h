@@ -36,7 +36,7 @@ extern "C" {
 #define QIPB_C64 1
 
 #define QIPB_MAX_DENSE_K 4     /* register-blocked dense kernels: 1..4 target bits            */
-#define QIPB_MAX_BIG_K 10      /* shared-memory dense kernel: up to 10 target bits             */
+#define QIPB_MAX_BIG_K 10      /* batched dense kernel (FP64 tensor tiles): up to 10 target bits */
 #define QIPB_MAX_TILE_BITS 12  /* fused pass: tiles of 2^12 amplitudes (64 KiB complex128, 32 KiB complex64) */
 #define QIPB_MAX_FUSED_GATES 280 /* gates per qipb_apply_fused call (runs of diagonal gates fold into stages) */
 
@@ -88,7 +88,8 @@ int qipb_init_kron(qipb_ctx *ctx, void *state, int nbits, int dtype, int ngroups
  *   significant bit of the matrix index (kronprod.pyx:184-189).  mat is row-major 2^k x 2^k
  *   complex128.  k = 0 multiplies the controlled sub-space by the scalar mat[0] (phase gates).
  *   diagonal != 0 promises off-diagonal entries are zero (only the diagonal is read).
- *   k <= QIPB_MAX_DENSE_K runs register-blocked; up to QIPB_MAX_BIG_K through shared memory.
+ *   k <= QIPB_MAX_DENSE_K runs register-blocked; up to QIPB_MAX_BIG_K as batched matrix products staged in shared
+ *   memory (complex128: FP64 tensor tiles).
  * qipb_apply_swap: exchanges bit_a and bit_b of the index (SwapMat(1)) under ctrl_mask; only the
  *   amplitudes whose two bits differ move.                                                     */
 int qipb_apply_matrix(qipb_ctx *ctx, void *state, int nbits, int dtype, int k, const int *bits,

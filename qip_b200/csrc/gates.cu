@@ -120,7 +120,8 @@ struct BigArgs {
     u64 fixed_or;
     int nins;
     int k;
-    int gb;                               // groups per batch (a power of two, <= 32; X[D][gb] fits 128 KiB of shared memory)
+    int gb;                               // groups per batch (a power of two; X[D][gb] fits the shared memory of an SM)
+    int nbuf;                             // tensor path: 1 or 2 batch buffers
     unsigned char ins[QIPB_MAX_INS];
     unsigned char tbit[QIPB_MAX_BIG_K];   // bit position of matrix-index bit j (j = 0 least significant)
 };
@@ -174,6 +175,117 @@ __global__ void __launch_bounds__(256) big_gate_kernel(A *__restrict__ state, co
             }
         }
         __syncthreads();
+    }
+}
+
+// complex128 batches on the FP64 tensor path: Y[D][GB] = M[D][D] X[D][GB] as 8x8x4 `mma.sync` tiles (DMMA), four real
+// products per complex one.  The scalar kernel above issues one shared-memory load and RPT matrix loads per 4 * RPT
+// FMAs and stays at a fifth of the FP64 rate; here a warp task (S row strips of 8 x CB column blocks of 8, S * CB = 4)
+// issues S matrix-fragment loads (global, L1 / L2 resident) and CB shared-memory loads per 16 tile products = 4096 FMAs.
+// Fragment layout of mma.m8n8k4.f64 (lane = 4 * g + t): A[g][t], B[t][g], C[g][2t], C[g][2t + 1].
+// X rows are padded to GB + 2 amplitudes so that the B-fragment loads (4 rows x 2 columns per quarter warp) fall into
+// distinct 16-byte bank groups.  The update stays in place: a batch is complete in shared memory before its first store.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// The gather of a batch is asynchronous (16-byte cp.async, every copy of a thread in flight at once); with g.nbuf == 2 the
+// next batch is gathered while the tiles of the current one are multiplied.
+template <int S, int CB>
+__global__ void __launch_bounds__(256, 3) big_gate_mma_kernel(double2 *__restrict__ state, const double2 *__restrict__ mat,
+                                                            const __grid_constant__ BigArgs g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = 1 << g.k;
+    const int GB = g.gb, LD = GB + 2, gshift = 31 - __clz(GB);
+    double2 *Xall = reinterpret_cast<double2 *>(smem_raw);
+    u64 *rowoff = reinterpret_cast<u64 *>(Xall + (size_t)g.nbuf * D * LD);
+    u64 *colall = rowoff + D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fg = lane >> 2, ft = lane & 3;
+    for (int j = threadIdx.x; j < D; j += 256) {
+        u64 off = 0;
+        for (int b = 0; b < g.k; ++b) off |= (u64)((j >> b) & 1) << g.tbit[b];
+        rowoff[j] = off;
+    }
+    // start the gather of the batch at w into buffer b (the caller has made sure nobody still reads that buffer)
+    auto gather = [&](const u64 w, const int b) {
+        double2 *X = Xall + (size_t)b * D * LD;
+        u64 *colbase = colall + b * GB;
+        if (threadIdx.x < GB && w + threadIdx.x < g.nwork)
+            colbase[threadIdx.x] = expand_index(w + threadIdx.x, g.ins, g.nins, g.fixed_or);
+        __syncthreads();                                  // colbase (and, the first time, rowoff)
+        for (int idx = threadIdx.x; idx < D * GB; idx += 256) {
+            const int j = idx >> gshift, c = idx & (GB - 1);
+            if (w + c < g.nwork) cp_async16(X + j * LD + c, state + colbase[c] + rowoff[j]);
+            else X[j * LD + c] = make_double2(0.0, 0.0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int ncg = GB / (8 * CB), ntask = (D / (8 * S)) * ncg;
+    const u64 stride = (u64)gridDim.x * GB;
+    u64 w0 = (u64)blockIdx.x * GB;
+    if (w0 < g.nwork) gather(w0, 0);
+    for (int buf = 0; w0 < g.nwork; w0 += stride) {
+        const bool more = w0 + stride < g.nwork;
+        if (g.nbuf == 2 && more) {
+            gather(w0 + stride, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double2 *X = Xall + (size_t)buf * D * LD;
+        const u64 *colbase = colall + buf * GB;
+        for (int t = warp; t < ntask; t += 8) {
+            const int sg = t / ncg, c0 = (t % ncg) * 8 * CB;
+            if (w0 + c0 >= g.nwork) continue;             // warp-uniform: a column group past the end of the state
+            double yr[S][CB][2], yi[S][CB][2];
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) yr[s][cb][0] = yr[s][cb][1] = yi[s][cb][0] = yi[s][cb][1] = 0.0;
+            const double2 *mrow = mat + (size_t)(sg * 8 * S + fg) * D + ft;
+            const double2 *xcol = X + ft * LD + c0 + fg;
+#pragma unroll 2
+            for (int j0 = 0; j0 < D; j0 += 4) {
+                double2 a[S], x[CB];
+#pragma unroll
+                for (int s = 0; s < S; ++s) a[s] = __ldg(mrow + (size_t)s * 8 * D + j0);
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) x[cb] = xcol[j0 * LD + cb * 8];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const double nai = -a[s].y;
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) dmma884(yr[s][cb][0], yr[s][cb][1], a[s].x, x[cb].x);
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) dmma884(yi[s][cb][0], yi[s][cb][1], a[s].x, x[cb].y);
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) dmma884(yr[s][cb][0], yr[s][cb][1], nai, x[cb].y);
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) dmma884(yi[s][cb][0], yi[s][cb][1], a[s].y, x[cb].x);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const u64 ro = rowoff[(sg * S + s) * 8 + fg];
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = c0 + cb * 8 + 2 * ft + e;
+                        if (w0 + c < g.nwork) state[colbase[c] + ro] = make_double2(yr[s][cb][e], yi[s][cb][e]);
+                    }
+            }
+        }
+        __syncthreads();                                  // every warp is done with this buffer
+        if (g.nbuf == 2) buf ^= 1;
+        else if (more) gather(w0 + stride, 0);
     }
 }
 
@@ -253,6 +365,47 @@ static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits,
     double2 *dmat = nullptr;
     QIPB_CUDA(cudaMallocAsync(&dmat, D * D * sizeof(double2), ctx->stream));
     QIPB_CUDA(cudaMemcpyAsync(dmat, mat, D * D * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    if (sizeof(A) == sizeof(double2)) {
+        static const int use_mma = [] { const char *e = getenv("QIPB_BIG_MMA"); return e ? atoi(e) : 1; }();
+        if (use_mma) {
+            // batch width and buffers, measured on B200 (scripts/big_gate_probe.py, profiles/r02_big_gate_probe.txt): three CTAs
+            // per SM (registers allow no more) matter more than a wide batch, and with three CTAs overlapping their phases a
+            // second buffer (gather of batch i + 1 behind the tiles of batch i) costs more in barriers than it hides
+            int gb = k == 5 ? 64 : k <= 7 ? 32 : 8;
+            int nbuf = 1;
+            if (const char *e = getenv("QIPB_BIG_GB")) {   // tuning knobs for profiling runs
+                const int v = atoi(e);
+                if (v == 8 || v == 16 || v == 32 || v == 64) gb = v;
+            }
+            if (const char *e = getenv("QIPB_BIG_NBUF")) nbuf = atoi(e) == 2 ? 2 : 1;
+            while (gb > 8 && (u64)gb > 2 * g.nwork) gb >>= 1;
+            auto smem_of = [&](int w, int nb) { return (size_t)nb * D * (w + 2) * sizeof(double2) + (D + 2 * w) * sizeof(u64); };
+            if (smem_of(gb, nbuf) > 220u * 1024u) nbuf = 1;
+            while (gb > 8 && smem_of(gb, nbuf) > 220u * 1024u) gb >>= 1;
+            g.gb = gb;
+            g.nbuf = nbuf;
+            const size_t smem = smem_of(gb, nbuf);
+            const u64 nbatch = (g.nwork + gb - 1) / gb;
+            const int per_sm = (int)((226u * 1024u) / (smem + 1024));
+            u64 blocks = (u64)ctx->sm_count * (per_sm > 3 ? 3 : per_sm < 1 ? 1 : per_sm);
+            if (blocks > nbatch) blocks = nbatch;
+            double2 *st = reinterpret_cast<double2 *>(state);
+            if (gb >= 32) {
+                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                big_gate_mma_kernel<1, 4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(st, dmat, g);
+            } else if (gb == 16) {
+                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                big_gate_mma_kernel<2, 2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(st, dmat, g);
+            } else {
+                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                big_gate_mma_kernel<4, 1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(st, dmat, g);
+            }
+            ctx->launches++;
+            QIPB_CUDA(cudaGetLastError());
+            QIPB_CUDA(cudaFreeAsync(dmat, ctx->stream));
+            return QIPB_OK;
+        }
+    }
     g.gb = 32;
     while ((size_t)g.gb * D * sizeof(A) > 128u * 1024u) g.gb >>= 1;
     const size_t smem = (size_t)g.gb * D * sizeof(A);
