@@ -182,7 +182,7 @@ def _run_cases(quick, log, rank, world):
 
 def run_single_gpu_cases(log=print):
     """The single-GPU subset bench.py runs before its timed region at N = 1: the production fused kernels at many
-    tiles per CTA against the oracle (layered, n = 20), the QFFT closed form at 26 qubits, a mixed small circuit."""
+    tiles per CTA against the oracle (layered, n = 20), dense 5-, 6- and 8-qubit gates (n = 16), the QFFT closed form at 26 qubits."""
     from qip_b200 import B200Backend
     REPORT["cases"], REPORT["max_err"] = 0, 0.0
     n2 = 20
@@ -201,6 +201,20 @@ def run_single_gpu_cases(log=print):
     assert mg == mc and abs(pg - pc) < 1e-13, (mg, mc, pg, pc)
     check("layered n=20 collapsed", g.get_state(), c.get_state())
     log("OK layered n=%d vs %s err=%.1e" % (n2, type(c).__name__, err))
+    g.close()
+    # dense gates on 6 and 8 qubits (complex128: the FP64-tensor kernel) against the oracle, scattered targets, un-fused
+    n3 = 16
+    rng = np.random.default_rng(11)
+    from qip_b200.circuits import haar_unitary
+    g = B200Backend.make_state(n3, [], [])
+    c = orc.RefBackend.make_state(n3, [], []) if _have_ref() else orc.OracleBackend.make_state(n3, [], [])
+    for k in (1, 6, 8, 5):
+        qs = tuple(int(q) for q in rng.permutation(n3)[:k])
+        u = haar_unitary(rng, 2 ** k)
+        g.kronselect_dot({qs if k > 1 else qs[0]: u})
+        c.kronselect_dot({qs if k > 1 else qs[0]: u})
+    err = check("dense 5/6/8-qubit gates n=16 vs oracle", g.get_state(), c.get_state())
+    log("OK dense K=5,6,8 gates n=%d vs %s err=%.1e" % (n3, type(c).__name__, err))
     g.close()
     nb = 26
     j = 0x5A5A5A5 & ((1 << nb) - 1)
