@@ -122,6 +122,46 @@ def test_compiled_circuit_replays_through_the_real_backend_with_cached_plans(mon
     assert len(circ._plans) == 3                      # one cached plan per gate segment, shared by all replays
 
 
+def test_whole_register_device_refeed_copies_by_default_and_adopts_on_request(monkeypatch):
+    # a re-fed device state is copied (the reference never aliases a feed, qip/backend.py:86-104); with
+    # adopt_feed=True the fed buffer BECOMES the state (no second 2^n allocation: the Grover loop at 33 qubits)
+    from oracle import oracle as orc
+    from qip_b200 import B200Backend, DeviceState
+    from qip_b200.graph import CompiledCircuit
+    hostlib.install(monkeypatch)
+    n = 12
+    ops_k = list(layered_stream(n, 1, 9))
+    first = B200Backend.make_state(n, [], [], host_state_max_qubits=-1)
+    for m in ops_k:
+        first.kronselect_dot(m)
+    handle = first.get_state()
+    assert isinstance(handle, DeviceState)
+    before = np.asarray(handle).copy()
+    c = orc.OracleBackend.make_state(n, [], [])
+    for m in ops_k + ops_k:
+        c.kronselect_dot(m)
+    want = c.get_state()
+    b = B200Backend.make_state(n, [list(range(n))], [handle])                       # default: a copy
+    assert b.state.data_ptr() != handle.tensor.data_ptr()
+    for m in ops_k:
+        b.kronselect_dot(m)
+    assert float(np.max(np.abs(np.asarray(b.get_state()) - want))) <= 1e-12
+    assert np.array_equal(np.asarray(handle), before)                                # the fed state is untouched
+    a = B200Backend.make_state(n, [list(range(n))], [handle], adopt_feed=True)      # the fed buffer becomes the state
+    assert a.state.data_ptr() == handle.tensor.data_ptr()
+    for m in ops_k:
+        a.kronselect_dot(m)
+    assert float(np.max(np.abs(np.asarray(a.get_state()) - want))) <= 1e-12
+    # and through CompiledCircuit.run (backend keyword arguments are forwarded to make_state)
+    circ = CompiledCircuit.from_ops(n, [list(range(n))], [handle], [("k", m) for m in ops_k])
+    state, _ = circ.run(feed={(0,): DeviceState(a.state)}, device_state=True, adopt_feed=True)
+    assert state.tensor.data_ptr() == a.state.data_ptr()
+    c3 = orc.OracleBackend.make_state(n, [list(range(n))], [want])
+    for m in ops_k:
+        c3.kronselect_dot(m)
+    assert float(np.max(np.abs(np.asarray(state) - c3.get_state()))) <= 1e-12
+
+
 @pytest.mark.parametrize("seed", range(16))
 def test_random_sessions_through_the_real_backend_on_host(monkeypatch, seed):
     import fuzzlib

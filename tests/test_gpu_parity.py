@@ -398,7 +398,8 @@ def test_compiled_shor_circuit_replays_on_device_with_cached_plan():
     assert type(state).__name__ == "DeviceState" and len(state) == 2 ** n
 
 
-def test_grover_28_qubits_matches_closed_form():
+@pytest.mark.parametrize("adopt", [False, True])
+def test_grover_28_qubits_matches_closed_form(adopt):
     # BASELINE configs[2] (examples/grovers_iterative.py:20-39 scaled up): 27 search qubits + ancilla, K iterations
     # re-fed on the device; P(x0) after K iterations = sin^2((2K+1) asin(2^(-27/2)))  
     from qip_b200.functions import equals, tabulated
@@ -414,8 +415,10 @@ def test_grover_28_qubits_matches_closed_form():
     state, _ = first.run(device_state=True)
     again = CompiledCircuit.from_ops(n, [search + anc], [state], ops_)
     for _ in range(K - 1):
-        state, _ = again.run(feed={(0,): state}, device_state=True)
-    g = _backend().make_state(n, [search + anc], [state])
+        ptr = state.tensor.data_ptr()
+        state, _ = again.run(feed={(0,): state}, device_state=True, adopt_feed=adopt)
+        assert (state.tensor.data_ptr() == ptr) == adopt          # adopted: the fed buffer is the state, no second 4 GiB
+    g = _backend().make_state(n, [search + anc], [state], adopt_feed=adopt)
     _, p = g.soft_measure(np.array(search, dtype=np.int32), measured=x0)
     theta = np.arcsin(2.0 ** (-ns / 2.0))
     assert abs(p - np.sin((2 * K + 1) * theta) ** 2) <= 1e-12
