@@ -89,7 +89,7 @@ int qipb_init_kron(qipb_ctx *ctx, void *state, int nbits, int dtype, int ngroups
  *   complex128.  k = 0 multiplies the controlled sub-space by the scalar mat[0] (phase gates).
  *   diagonal != 0 promises off-diagonal entries are zero (only the diagonal is read).
  *   k <= QIPB_MAX_DENSE_K runs register-blocked; up to QIPB_MAX_BIG_K as batched matrix products staged in shared
- *   memory (complex128: FP64 tensor tiles).
+ *   memory and multiplied as FP64 tensor tiles (complex64 states are widened on the way in).
  * qipb_apply_swap: exchanges bit_a and bit_b of the index (SwapMat(1)) under ctrl_mask; only the
  *   amplitudes whose two bits differ move.                                                     */
 int qipb_apply_matrix(qipb_ctx *ctx, void *state, int nbits, int dtype, int k, const int *bits,

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) big_gate_kernel(A *__restrict__ state, co
     }
 }
 
-// complex128 batches on the FP64 tensor path: Y[D][GB] = M[D][D] X[D][GB] as 8x8x4 `mma.sync` tiles (DMMA), four real
+// Batches on the FP64 tensor path: Y[D][GB] = M[D][D] X[D][GB] as 8x8x4 `mma.sync` tiles (DMMA), four real
 // products per complex one.  The scalar kernel above issues one shared-memory load and RPT matrix loads per 4 * RPT
 // FMAs and stays at a fifth of the FP64 rate; here a warp task (S row strips of 8 x CB column blocks of 8, S * CB = 4)
 // issues S matrix-fragment loads (global, L1 / L2 resident) and CB shared-memory loads per 16 tile products = 4096 FMAs.
@@ -196,8 +196,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 
 // The gather of a batch is asynchronous (16-byte cp.async, every copy of a thread in flight at once); with g.nbuf == 2 the
 // next batch is gathered while the tiles of the current one are multiplied.
-template <int S, int CB>
-__global__ void __launch_bounds__(256, 3) big_gate_mma_kernel(double2 *__restrict__ state, const double2 *__restrict__ mat,
+// complex64 states use the same tiles: amplitudes are widened to double on the way into shared memory (register-staged
+// loads instead of cp.async) and rounded once on the way out, so a K-qubit gate costs one rounding per amplitude.
+template <typename A, int S, int CB>
+__global__ void __launch_bounds__(256, 3) big_gate_mma_kernel(A *__restrict__ state, const double2 *__restrict__ mat,
                                                             const __grid_constant__ BigArgs g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = 1 << g.k;
@@ -219,10 +221,26 @@ __global__ void __launch_bounds__(256, 3) big_gate_mma_kernel(double2 *__restric
         if (threadIdx.x < GB && w + threadIdx.x < g.nwork)
             colbase[threadIdx.x] = expand_index(w + threadIdx.x, g.ins, g.nins, g.fixed_or);
         __syncthreads();                                  // colbase (and, the first time, rowoff)
-        for (int idx = threadIdx.x; idx < D * GB; idx += 256) {
-            const int j = idx >> gshift, c = idx & (GB - 1);
-            if (w + c < g.nwork) cp_async16(X + j * LD + c, state + colbase[c] + rowoff[j]);
-            else X[j * LD + c] = make_double2(0.0, 0.0);
+        if constexpr (sizeof(A) == sizeof(double2)) {
+            for (int idx = threadIdx.x; idx < D * GB; idx += 256) {
+                const int j = idx >> gshift, c = idx & (GB - 1);
+                if (w + c < g.nwork) cp_async16(X + j * LD + c, state + colbase[c] + rowoff[j]);
+                else X[j * LD + c] = make_double2(0.0, 0.0);
+            }
+        } else {
+            for (int i0 = threadIdx.x; i0 < D * GB; i0 += 256 * 4) {          // four loads in flight per thread
+                A v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = i0 + 256 * u, j = idx >> gshift, c = idx & (GB - 1);
+                    v[u] = (idx < D * GB && w + c < g.nwork) ? state[colbase[c] + rowoff[j]] : make_amp<A>(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = i0 + 256 * u, j = idx >> gshift, c = idx & (GB - 1);
+                    if (idx < D * GB) X[j * LD + c] = make_double2((double)v[u].x, (double)v[u].y);
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -279,7 +297,7 @@ __global__ void __launch_bounds__(256, 3) big_gate_mma_kernel(double2 *__restric
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int c = c0 + cb * 8 + 2 * ft + e;
-                        if (w0 + c < g.nwork) state[colbase[c] + ro] = make_double2(yr[s][cb][e], yi[s][cb][e]);
+                        if (w0 + c < g.nwork) state[colbase[c] + ro] = make_amp<A>(yr[s][cb][e], yi[s][cb][e]);
                     }
             }
         }
@@ -365,7 +383,7 @@ static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits,
     double2 *dmat = nullptr;
     QIPB_CUDA(cudaMallocAsync(&dmat, D * D * sizeof(double2), ctx->stream));
     QIPB_CUDA(cudaMemcpyAsync(dmat, mat, D * D * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
-    if (sizeof(A) == sizeof(double2)) {
+    {
         static const int use_mma = [] { const char *e = getenv("QIPB_BIG_MMA"); return e ? atoi(e) : 1; }();
         if (use_mma) {
             // batch width and buffers, measured on B200 (scripts/big_gate_probe.py, profiles/r02_big_gate_probe.txt): three CTAs
@@ -389,16 +407,15 @@ static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits,
             const int per_sm = (int)((226u * 1024u) / (smem + 1024));
             u64 blocks = (u64)ctx->sm_count * (per_sm > 3 ? 3 : per_sm < 1 ? 1 : per_sm);
             if (blocks > nbatch) blocks = nbatch;
-            double2 *st = reinterpret_cast<double2 *>(state);
             if (gb >= 32) {
-                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                big_gate_mma_kernel<1, 4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(st, dmat, g);
+                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                big_gate_mma_kernel<A, 1, 4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
             } else if (gb == 16) {
-                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                big_gate_mma_kernel<2, 2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(st, dmat, g);
+                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                big_gate_mma_kernel<A, 2, 2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
             } else {
-                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                big_gate_mma_kernel<4, 1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(st, dmat, g);
+                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                big_gate_mma_kernel<A, 4, 1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
             }
             ctx->launches++;
             QIPB_CUDA(cudaGetLastError());

@@ -129,12 +129,14 @@ def test_dense_kq_register_and_shared_memory_kernels(k):
     _agree(g, c)
 
 
-@pytest.mark.parametrize("k,n", [(5, 5), (5, 6), (6, 9), (8, 13), (9, 13), (10, 12), (10, 14)])
-def test_dense_kq_tensor_path_batch_shapes(k, n):
-    """The complex128 FP64-tensor kernel (8x8x4 tiles): every batch width it picks (64 ... 8 columns), states
-    with fewer groups than a batch is wide (n - k = 0, 1, 2), targets on the lowest and on scattered bits, a control."""
+@pytest.mark.parametrize("statetype,tol", [(np.complex128, TOL128), (np.complex64, TOL64)])
+@pytest.mark.parametrize("k,n", [(5, 5), (5, 6), (6, 9), (7, 12), (8, 13), (9, 13), (10, 12), (10, 14)])
+def test_dense_kq_tensor_path_batch_shapes(k, n, statetype, tol):
+    """The FP64-tensor kernel (8x8x4 tiles; complex64 states are widened on the way in): every batch width it picks
+    (64 ... 8 columns), states with fewer groups than a batch is wide (n - k = 0, 1, 2), targets on the lowest and on
+    scattered bits, a control."""
     rng = np.random.default_rng(100 + 16 * k + n)
-    g, c = _pair(n, _rand_state(rng, n), fuse=False)
+    g, c = _pair(n, _rand_state(rng, n), statetype, fuse=False)
     for qs in (tuple(range(n - k, n)), tuple(int(q) for q in rng.permutation(n)[:k])):
         u = haar_unitary(rng, 2 ** k)
         g.kronselect_dot({qs: u})
@@ -144,7 +146,7 @@ def test_dense_kq_tensor_path_batch_shapes(k, n):
         u = haar_unitary(rng, 2 ** k)
         g.kronselect_dot({qs: CMat(u)})
         c.kronselect_dot({qs: CMat(u)})
-    _agree(g, c)
+    _agree(g, c, tol * 4)
 
 
 def test_controls_diagonals_swaps_every_bit():
