@@ -33,7 +33,8 @@ def test_sharded_backend_matches_oracle_on_virtual_ranks(monkeypatch, P):
     rngu = np.random.default_rng(6)
     extra = [{(0, 5): CMat(X2)}, {(1, 0, 6): CMat(CMat(haar_unitary(rngu, 2)))}, {0: rm_mat(3)},
              {(1, 0): CMat(rm_mat(2))}, {(0, 7): SwapMat(1)}, {(0, 1): haar_unitary(rngu, 4)},
-             {(10, 0, 3): CMat(SwapMat(1))}, {0: H2}, {(2, 9, 0): haar_unitary(rngu, 8)}]
+             {(10, 0, 3): CMat(SwapMat(1))}, {0: H2}, {(2, 9, 0): haar_unitary(rngu, 8)},
+             {(2, 9, 0, 4, 7, 1): haar_unitary(rngu, 64)}]   # six qubits, three of them global at P = 8: the batched dense kernel on a shard
     cases = {"layered": list(layered_stream(n, 3, 2)), "qfft": list(qfft_stream(n)), "mixed": extra}
 
     def body(rank):
