@@ -360,6 +360,46 @@ static int apply_k(qipb_ctx *ctx, A *state, int nbits, const int *bits, const do
     return launch_gate<A, K, U, false>(ctx, state, g);
 }
 
+// Launch of the FP64-tensor kernel for one dense gate on g.k >= 5 bits (dmat: the matrix on the device).
+template <typename A>
+static int launch_big_mma(qipb_ctx *ctx, A *state, const double2 *dmat, BigArgs &g) {
+    const size_t D = (size_t)1 << g.k;
+    // batch width and buffers, measured on B200 (scripts/big_gate_probe.py, profiles/r02_big_gate_probe.txt): three CTAs per SM
+    // (registers allow no more) matter more than a wide batch, and with three CTAs overlapping their phases a second buffer
+    // (gather of batch i + 1 behind the tiles of batch i) costs more in barriers than it hides
+    int gb = g.k == 5 ? 64 : g.k <= 7 ? 32 : 8;
+    int nbuf = 1;
+    if (const char *e = getenv("QIPB_BIG_GB")) {           // tuning knobs for profiling runs
+        const int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32 || v == 64 || v == 128) gb = v;
+    }
+    if (const char *e = getenv("QIPB_BIG_NBUF")) nbuf = atoi(e) == 2 ? 2 : 1;
+    while (gb > 8 && (u64)gb > 2 * g.nwork) gb >>= 1;      // a state with fewer groups than a batch is wide
+    auto smem_of = [&](int w, int nb) { return (size_t)nb * D * (w + 2) * sizeof(double2) + (D + 2 * w) * sizeof(u64); };
+    if (smem_of(gb, nbuf) > 220u * 1024u) nbuf = 1;
+    while (gb > 8 && smem_of(gb, nbuf) > 220u * 1024u) gb >>= 1;
+    g.gb = gb;
+    g.nbuf = nbuf;
+    const size_t smem = smem_of(gb, nbuf);
+    const u64 nbatch = (g.nwork + gb - 1) / gb;
+    const int per_sm = (int)((226u * 1024u) / (smem + 1024));
+    u64 blocks = (u64)ctx->sm_count * (per_sm > 3 ? 3 : per_sm < 1 ? 1 : per_sm);
+    if (blocks > nbatch) blocks = nbatch;
+    if (gb >= 32) {
+        QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        big_gate_mma_kernel<A, 1, 4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
+    } else if (gb == 16) {
+        QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        big_gate_mma_kernel<A, 2, 2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
+    } else {
+        QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        big_gate_mma_kernel<A, 4, 1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
+    }
+    ctx->launches++;
+    QIPB_CUDA(cudaGetLastError());
+    return QIPB_OK;
+}
+
 template <typename A>
 static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits, const double *mat, u64 ctrl_mask) {
     BigArgs g;
@@ -383,45 +423,13 @@ static int apply_big(qipb_ctx *ctx, A *state, int nbits, int k, const int *bits,
     double2 *dmat = nullptr;
     QIPB_CUDA(cudaMallocAsync(&dmat, D * D * sizeof(double2), ctx->stream));
     QIPB_CUDA(cudaMemcpyAsync(dmat, mat, D * D * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
-    {
-        static const int use_mma = [] { const char *e = getenv("QIPB_BIG_MMA"); return e ? atoi(e) : 1; }();
-        if (use_mma) {
-            // batch width and buffers, measured on B200 (scripts/big_gate_probe.py, profiles/r02_big_gate_probe.txt): three CTAs
-            // per SM (registers allow no more) matter more than a wide batch, and with three CTAs overlapping their phases a
-            // second buffer (gather of batch i + 1 behind the tiles of batch i) costs more in barriers than it hides
-            int gb = k == 5 ? 64 : k <= 7 ? 32 : 8;
-            int nbuf = 1;
-            if (const char *e = getenv("QIPB_BIG_GB")) {   // tuning knobs for profiling runs
-                const int v = atoi(e);
-                if (v == 8 || v == 16 || v == 32 || v == 64) gb = v;
-            }
-            if (const char *e = getenv("QIPB_BIG_NBUF")) nbuf = atoi(e) == 2 ? 2 : 1;
-            while (gb > 8 && (u64)gb > 2 * g.nwork) gb >>= 1;
-            auto smem_of = [&](int w, int nb) { return (size_t)nb * D * (w + 2) * sizeof(double2) + (D + 2 * w) * sizeof(u64); };
-            if (smem_of(gb, nbuf) > 220u * 1024u) nbuf = 1;
-            while (gb > 8 && smem_of(gb, nbuf) > 220u * 1024u) gb >>= 1;
-            g.gb = gb;
-            g.nbuf = nbuf;
-            const size_t smem = smem_of(gb, nbuf);
-            const u64 nbatch = (g.nwork + gb - 1) / gb;
-            const int per_sm = (int)((226u * 1024u) / (smem + 1024));
-            u64 blocks = (u64)ctx->sm_count * (per_sm > 3 ? 3 : per_sm < 1 ? 1 : per_sm);
-            if (blocks > nbatch) blocks = nbatch;
-            if (gb >= 32) {
-                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                big_gate_mma_kernel<A, 1, 4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
-            } else if (gb == 16) {
-                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                big_gate_mma_kernel<A, 2, 2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
-            } else {
-                QIPB_CUDA(cudaFuncSetAttribute(big_gate_mma_kernel<A, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                big_gate_mma_kernel<A, 4, 1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(state, dmat, g);
-            }
-            ctx->launches++;
-            QIPB_CUDA(cudaGetLastError());
-            QIPB_CUDA(cudaFreeAsync(dmat, ctx->stream));
-            return QIPB_OK;
-        }
+    static const int use_mma = [] { const char *e = getenv("QIPB_BIG_MMA"); return e ? atoi(e) : 1; }();
+    if (use_mma) {
+        const int rc = launch_big_mma<A>(ctx, state, dmat, g);
+        const cudaError_t fe = cudaFreeAsync(dmat, ctx->stream);
+        if (rc) return rc;
+        QIPB_CUDA(fe);
+        return QIPB_OK;
     }
     g.gb = 32;
     while ((size_t)g.gb * D * sizeof(A) > 128u * 1024u) g.gb >>= 1;
