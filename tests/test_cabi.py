@@ -55,3 +55,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "qip_oracle" not in text, f
+
+
+def test_shipped_library_carries_the_blackwell_paths_it_claims():
+    """SASS of the built library (cuobjdump, no GPU needed): the fused pass moves its tiles with TMA bulk copies on
+    mbarriers (UBLKCP + SYNCS), dense K >= 5 gates multiply FP64 tensor tiles (DMMA) fed by cp.async (LDGSTS), and the
+    code is sm_100a only (the mnemonics of /opt/skills/guides/B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not installed")
+    lib.build()
+    arch = subprocess.run([exe, "-lelf", lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    assert "sm_100a" in arch and not re.search(r"sm_(?!100a)\d+", arch), arch
+    csrc = os.path.dirname(lib.LIB_PATH)
+    sass = {}
+    for obj in ("gates.o", "fused.o"):
+        path = os.path.join(csrc, obj)
+        assert os.path.exists(path), path
+        sass[obj] = subprocess.run([exe, "-sass", path], capture_output=True, text=True, timeout=600).stdout
+    assert sass["gates.o"].count("DMMA.8x8x4") >= 48 and "LDGSTS" in sass["gates.o"]
+    assert "big_gate_mma_kernel" in sass["gates.o"]
+    for mnemonic in ("UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT"):
+        assert mnemonic in sass["fused.o"], mnemonic
