@@ -302,7 +302,10 @@ def test_exchange_compute_overlap_pipeline_on_virtual_ranks(monkeypatch, P, chun
     psi /= np.linalg.norm(psi)
     streams = {"layered": list(layered_stream(n, 4, 11)), "qfft": list(qfft_stream(n)),
                "controls": [{(0, n - 1): CMat(X2)}, {(n - 1, 0, 4): CMat(CMat(H2))}, {0: H2}, {(1, 0): CMat(rm_mat(2))}, {1: H2},
-                            {(2, n - 2): haar_unitary(rng, 4)}, {(n - 1, 1): CMat(rm_mat(3))}, {n - 1: H2}, {(3, 0): haar_unitary(rng, 4)}]}
+                            {(2, n - 2): haar_unitary(rng, 4)}, {(n - 1, 1): CMat(rm_mat(3))}, {n - 1: H2}, {(3, 0): haar_unitary(rng, 4)}],
+               # dense gates on 6 and 5 qubits (never fused: the batched kernel on a shard) between fusable layers, global targets
+               "dense6": list(layered_stream(n, 1, 5)) + [{(2, n - 1, 0, 4, n - 2, 1): haar_unitary(rng, 64)}] + list(layered_stream(n, 1, 6)) +
+                         [{(0, 3, 5, 6, n - 3): haar_unitary(rng, 32)}, {(1, 0): CMat(rm_mat(2))}] + list(layered_stream(n, 1, 7))}
     wants = {}
     for name, ops_ in streams.items():
         c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
