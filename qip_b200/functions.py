@@ -3,7 +3,8 @@
 The reference tabulates `func` with 2^|reg1| python calls on every `func_apply`
 (qip/ext/func_apply.pyx:66-69).  The functions here accept python ints AND numpy int64 arrays, so
 B200Backend.func_apply tabulates them with one vectorised call; `tabulated(f, nbits)` attaches the table
-itself (built once, reused by every application and by compiled circuits)."""
+itself (built once, reused by every application and by compiled circuits); `controlled(f, c, m)` is C(F) as a plain F
+on a joined register."""
 import numpy as np
 
 
@@ -35,6 +36,33 @@ def modexp(base: int, modulus: int):
             e >>= 1
         return result
     f.vectorized = True                     # exact on int64 arrays while modulus < 2**31 (checked above)
+    return f
+
+
+def controlled(func, n_controls: int, n_inputs: int):
+    """Controlled F as a plain F on a joined register: apply `F(controlled(f, c, m), joined, reg2)` where `joined` holds the
+    c control qubits FIRST and then the m input qubits (x is read big-endian over reg1, qip/ext/func_apply.pyx:81-103, so the
+    controls are the most significant bits).  The result is f(x) when every control is 1 and 0 otherwise, and q xor 0 leaves
+    reg2 alone.  The reference has no controlled F (`COp` only wraps `MatrixOp`s, qip/operators.py:183-231); this needs no
+    new kernel: the extended table goes through the same `func_apply` path, on one GPU and sharded."""
+    n_controls, n_inputs = int(n_controls), int(n_inputs)
+    if n_controls < 0 or n_inputs < 0:
+        raise ValueError("n_controls and n_inputs must be non-negative")
+    full, mask = (1 << n_controls) - 1, (1 << n_inputs) - 1
+    vec = bool(getattr(func, "vectorized", False))
+
+    def f(xp):
+        if isinstance(xp, (int, np.integer)):
+            xp = int(xp)
+            return int(func(xp & mask)) if (xp >> n_inputs) == full else 0
+        xp = np.asarray(xp, dtype=np.int64)
+        on = (xp >> n_inputs) == full
+        out = np.zeros_like(xp)
+        if on.any():
+            x = xp[on] & mask
+            out[on] = np.asarray(func(x), dtype=np.int64) if vec else np.array([int(func(int(v))) for v in x], dtype=np.int64)
+        return out
+    f.vectorized = True                     # arrays are handled here (element by element when `func` itself is scalar-only)
     return f
 
 

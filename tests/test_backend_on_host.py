@@ -200,6 +200,28 @@ def test_function_tables_are_uploaded_once_per_function_object(monkeypatch):
     b.close()
 
 
+def test_controlled_function_through_the_real_backend_on_host(monkeypatch):
+    # qip_b200.functions.controlled: C(F) as a plain F on [controls ++ reg1]; byte table (3 output qubits), real B200Backend
+    from oracle import oracle as orc
+    from qip_b200 import B200Backend
+    from qip_b200.functions import controlled, modexp
+    hostlib.install(monkeypatch)
+    n = 12
+    rng = np.random.default_rng(21)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    ctrl, reg1, reg2 = [9, 2], [0, 7, 4, 1], [3, 11, 5, 8]
+    cf = controlled(modexp(7, 15), 2, 4)
+    g = B200Backend.make_state(n, [list(range(n))], [psi])
+    c = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+    g.func_apply(np.array(ctrl + reg1, dtype=np.int32), np.array(reg2, dtype=np.int32), cf)
+    c.func_apply(ctrl + reg1, reg2, cf)
+    got = np.asarray(g.get_state())
+    assert float(np.max(np.abs(got - c.get_state()))) <= 1e-15
+    off = np.array([not (((i >> (n - 1 - 9)) & 1) and ((i >> (n - 1 - 2)) & 1)) for i in range(2 ** n)])
+    assert np.array_equal(got[off], psi[off])                                        # a control at 0: untouched
+
+
 def test_graft_entry_smoke_runs_on_the_host_double(monkeypatch, capsys):
     # the driver's smoke() (one small hot-path invocation checked against the oracle) exercised end to end on the CPU tier
     import __graft_entry__ as entry

@@ -13,7 +13,7 @@ import pytest
 
 from oracle.ref_loader import have_ref_ext, have_reference_tree
 from qip_b200.backend import split_feeds
-from qip_b200.functions import equals, modexp, tabulated
+from qip_b200.functions import controlled, equals, modexp, tabulated
 from qip_b200.graph import CompiledCircuit, compile_circuit
 from test_host_logic import TileHostBackend
 
@@ -192,6 +192,59 @@ def test_vectorised_oracle_functions():
     assert (tabulate(tb, 5) == np.arange(32) % 3).all() and len(calls) == ncalls      # the table is reused, no new calls
     with pytest.raises(ValueError):
         modexp(3, 2 ** 40)
+
+
+def test_controlled_function_is_a_plain_F_on_the_joined_register():
+    # SURVEY 8f row 3 (controlled-F; the reference has none): controls first, then reg1; f(x) only where every control is 1
+    from oracle import oracle as orc
+    from qip_b200.backend import tabulate
+    f = lambda x: (5 * x + 3) % 8
+    cf = controlled(f, 2, 3)
+    t = tabulate(cf, 5)
+    assert all(int(t[(c << 3) | x]) == (f(x) if c == 3 else 0) for c in range(4) for x in range(8))
+    assert cf(0b11101) == f(0b101) and cf(0b10101) == 0
+    tv = tabulate(controlled(modexp(7, 15), 1, 4), 5)                      # vectorised inner function
+    assert all(int(tv[16 + x]) == pow(7, x, 15) for x in range(16)) and not tv[:16].any()
+    # against the oracle's func_apply: control qubit 6 (not adjacent), reg1 = [0, 3, 1], reg2 = [2, 4, 5]
+    n = 7
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    reg1, reg2, ctrl = [0, 3, 1], [2, 4, 5], 6
+    for make in (orc.OracleBackend.make_state, TileHostBackend.make_state):
+        b = make(n, [list(range(n))], [psi])
+        b.func_apply(np.array([ctrl] + reg1, dtype=np.int32), np.array(reg2, dtype=np.int32), controlled(f, 1, 3))
+        got = np.asarray(b.get_state())
+        plain = orc.OracleBackend.make_state(n, [list(range(n))], [psi])
+        plain.func_apply(reg1, reg2, f)
+        applied = plain.get_state()
+        on = np.array([(i >> (n - 1 - ctrl)) & 1 for i in range(2 ** n)], dtype=bool)     # qubit q = index bit n-1-q
+        assert np.allclose(got[on], applied[on], atol=1e-15, rtol=0) and np.allclose(got[~on], psi[~on], atol=1e-15, rtol=0)
+    with pytest.raises(ValueError):
+        controlled(f, -1, 3)
+
+
+@needs_ref
+def test_controlled_function_through_the_reference_front_end():
+    # the same function object works in the UNMODIFIED reference (python-int calls, func_apply.pyx:66-69) and compiled here
+    O, P, Q, QFFT = _ref()
+    f = lambda x: (3 * x + 1) % 8
+    rng = np.random.default_rng(8)
+    psi = rng.normal(size=16) + 1j * rng.normal(size=16)
+    psi /= np.linalg.norm(psi)
+    joined = Q.Qubit(n=4, default=psi)                               # qubit 0 = control, qubits 1..3 = x
+    phi = rng.normal(size=8) + 1j * rng.normal(size=8)
+    phi /= np.linalg.norm(phi)
+    reg2 = Q.Qubit(n=3, default=phi)
+    u1, u2 = O.F(controlled(f, 1, 3), joined, reg2)
+    want, _ = P.run(u1, u2)
+    got, _ = compile_circuit(u1, u2).run(backend_constructor=TileHostBackend.make_state)
+    assert np.allclose(got, want, atol=1e-15, rtol=0)
+    # control = 0 half: the product state is untouched; control = 1 half: reg2 index q -> q xor f(x)
+    amp = np.asarray(got).reshape(2, 8, 8)
+    for x in range(8):
+        assert np.allclose(amp[0, x], psi[x] * phi, atol=1e-15, rtol=0)
+        assert np.allclose(amp[1, x, np.arange(8) ^ f(x)], psi[8 + x] * phi, atol=1e-15, rtol=0)
 
 
 def test_distributed_front_door_conventions(monkeypatch):
